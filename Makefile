@@ -42,7 +42,7 @@ minihost/libavs_minihost.so: minihost/minihost.cpp minihost/minihost.h minihost/
 	$(CXX) $(CXXFLAGS_COMMON) -O2 $(HOSTI) -shared -o $@ minihost/minihost.cpp -ldl -lpthread
 
 oracle/libjinc_oracle.so: oracle/jinc_oracle.c oracle/jinc_oracle.h
-	$(CC) -std=c11 -O2 -fPIC -ffp-contract=off -shared -o $@ oracle/jinc_oracle.c -lm
+	$(CC) -std=c11 -O2 -fPIC -Wall -Werror=implicit-function-declaration -ffp-contract=off -shared -o $@ oracle/jinc_oracle.c -lm
 
 # The reference's own CMake defaults to Release (-O3 -DNDEBUG), C++17, and gives the three SIMD files their ISA
 # flags (CMakeLists.txt:3-7,57-61,65).  The same flags are used here; the sources are read from the mount.
