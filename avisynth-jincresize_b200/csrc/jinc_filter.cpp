@@ -512,6 +512,44 @@ extern "C" int jinc_filter_process(jinc_filter* f, const jinc_frame* frame)
     return rc;
 }
 
+extern "C" int jinc_filter_process_device(jinc_filter* f, int device_index, const jinc_frame* frame, int table_mask, int parts,
+                                          void* stream)
+{
+    if (int rc = check_frame(f, frame))
+        return rc;
+    if (device_index < 0 || device_index >= static_cast<int>(f->devs.size()))
+        return jinc_fail(JINC_E_INVALID, "jinc_filter_process_device: bad device index %d", device_index);
+    DeviceState& d = f->devs[device_index];
+    JINC_CUDA(cudaSetDevice(d.ctx->device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : d.ctx->stream;
+    for (int k = 0; k < f->n_tables; ++k) {
+        if (!(table_mask & (1 << k)))
+            continue;
+        const void* src[JINC_MAX_PLANES];
+        void* dst[JINC_MAX_PLANES];
+        ptrdiff_t sp[JINC_MAX_PLANES], dp[JINC_MAX_PLANES];
+        int n = 0;
+        for (int i = 0; i < f->p.n_planes; ++i) {
+            if (f->planes[i].table != k)
+                continue;
+            src[n] = frame->src[i];
+            dst[n] = frame->dst[i];
+            sp[n] = frame->src_pitch[i];
+            dp[n] = frame->dst_pitch[i];
+            ++n;
+        }
+        if (n == 0)
+            continue;
+        int launched = 0;
+        const int rc = jinc_launch_resize_planes(d.ctx, d.tables[k], f->p.sample_bytes, f->peak, n, src, sp, dst, dp, 0,
+                                                 d.tables[k]->sc.dst_h, st, &launched, parts);
+        f->launches.fetch_add(launched);
+        if (rc != JINC_OK)
+            return rc;
+    }
+    return JINC_OK;
+}
+
 extern "C" int jinc_filter_submit(jinc_filter* f, const jinc_frame* frame, int64_t* ticket)
 {
     if (int rc = check_frame(f, frame))

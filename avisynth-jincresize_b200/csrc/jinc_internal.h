@@ -111,7 +111,8 @@ int jinc_launch_resize(jinc_ctx* ctx, const jinc_table* t, int sample_bytes, flo
 // several planes that share one table in a single launch (blockIdx.z / .y = plane); rows [y_begin,y_end)
 int jinc_launch_resize_planes(jinc_ctx* ctx, const jinc_table* t, int sample_bytes, float peak, int n_planes,
                               const void* const* d_src, const ptrdiff_t* src_pitch, void* const* d_dst,
-                              const ptrdiff_t* dst_pitch, int y_begin, int y_end, cudaStream_t stream, int* launches);
+                              const ptrdiff_t* dst_pitch, int y_begin, int y_end, cudaStream_t stream, int* launches,
+                              int parts = JINC_PART_ALL);
 int jinc_debug_pixel_weights(const jinc_table* t, int x, int y, float* out);
 
 #endif

@@ -449,7 +449,7 @@ int launch_general(const jinc_table* t, GeneralArgs& a, const Rect* rects, int n
 
 template <typename T>
 int launch_typed(jinc_ctx* ctx, const jinc_table* t, float peak, const PlanePtrs& pl, int n_planes, int y_begin, int y_end,
-                 cudaStream_t st, int* launches)
+                 cudaStream_t st, int* launches, int parts)
 {
     (void)ctx;
     GeneralArgs ga;
@@ -466,7 +466,12 @@ int launch_typed(jinc_ctx* ctx, const jinc_table* t, float peak, const PlanePtrs
         // cell rows whose 2 output rows lie inside [y_begin, y_end); bands are cut on cell-pair boundaries
         int cb = (std::max(y_begin, u.y0) - u.y0 + 1) / 2;
         int ce = (std::min(y_end, u.y0 + 2 * u.ncy) - u.y0) / 2;
-        if (ce > cb) {
+        if (ce > cb && !(parts & JINC_PART_INTERIOR)) {
+            // interior deliberately skipped: still only the strips around it belong to the border part
+            fast_done = true;
+            fy0 = u.y0 + 2 * cb;
+            fy1 = u.y0 + 2 * ce;
+        } else if (ce > cb) {
             UpArgs a;
             memset(&a, 0, sizeof(a));
             a.pl = pl;
@@ -501,6 +506,8 @@ int launch_typed(jinc_ctx* ctx, const jinc_table* t, float peak, const PlanePtrs
     } else {
         rects[n_rects++] = Rect{0, y_begin, W, y_end};
     }
+    if (!(parts & JINC_PART_BORDER))
+        return JINC_OK;
     return launch_general<T>(t, ga, rects, n_rects, n_planes, st, launches);
 }
 
@@ -508,7 +515,8 @@ int launch_typed(jinc_ctx* ctx, const jinc_table* t, float peak, const PlanePtrs
 
 int jinc_launch_resize_planes(jinc_ctx* ctx, const jinc_table* t, int sample_bytes, float peak, int n_planes,
                               const void* const* d_src, const ptrdiff_t* src_pitch, void* const* d_dst,
-                              const ptrdiff_t* dst_pitch, int y_begin, int y_end, cudaStream_t stream, int* launches)
+                              const ptrdiff_t* dst_pitch, int y_begin, int y_end, cudaStream_t stream, int* launches,
+                              int parts)
 {
     if (n_planes < 1 || n_planes > JINC_MAX_PLANES)
         return jinc_fail(JINC_E_INVALID, "resize: n_planes must be 1..4");
@@ -534,9 +542,9 @@ int jinc_launch_resize_planes(jinc_ctx* ctx, const jinc_table* t, int sample_byt
     if (!launches)
         launches = &dummy;
     switch (sample_bytes) {
-    case 1: return launch_typed<uint8_t>(ctx, t, peak, pl, n_planes, y_begin, y_end, stream, launches);
-    case 2: return launch_typed<uint16_t>(ctx, t, peak, pl, n_planes, y_begin, y_end, stream, launches);
-    case 4: return launch_typed<float>(ctx, t, peak, pl, n_planes, y_begin, y_end, stream, launches);
+    case 1: return launch_typed<uint8_t>(ctx, t, peak, pl, n_planes, y_begin, y_end, stream, launches, parts);
+    case 2: return launch_typed<uint16_t>(ctx, t, peak, pl, n_planes, y_begin, y_end, stream, launches, parts);
+    case 4: return launch_typed<float>(ctx, t, peak, pl, n_planes, y_begin, y_end, stream, launches, parts);
     default: return jinc_fail(JINC_E_INVALID, "resize: sample_bytes must be 1, 2 or 4");
     }
 }

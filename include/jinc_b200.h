@@ -170,6 +170,14 @@ JINC_API int jinc_filter_wait(jinc_filter* f, int64_t ticket);
 /* Row-band split of ONE frame across all of the filter's GPUs (each GPU gets a band of output rows plus
  * the source rows its windows reach; no GPU<->GPU traffic). */
 JINC_API int jinc_filter_process_split(jinc_filter* f, const jinc_frame* frame);
+/* Device-resident frame: the kernels of jinc_filter_process without staging or PCIe copies.  `frame` holds DEVICE
+ * pointers on the filter's GPU `device_index` (destination planes 16-byte aligned, pitch multiple of 16).
+ * table_mask selects which tables run (bit 0: luma/shared table, bit 1: subsampled-chroma table); parts selects the
+ * kernels (JINC_PART_*), which lets a profiler or bench bracket the interior kernel alone.  Asynchronous on
+ * `stream` (a cudaStream_t; NULL = the context's stream). */
+enum { JINC_PART_INTERIOR = 1, JINC_PART_BORDER = 2, JINC_PART_ALL = 3 };
+JINC_API int jinc_filter_process_device(jinc_filter* f, int device_index, const jinc_frame* frame, int table_mask,
+                                        int parts, void* stream);
 /* kernels launched so far by this filter (all devices) */
 JINC_API int64_t jinc_filter_kernel_launches(const jinc_filter* f);
 

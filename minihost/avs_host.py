@@ -1,4 +1,4 @@
-"""ctypes driver for the in-process AviSynth+ C-API stand-in (minihost/).
+"""ctypes driver for the in-process AviSynth+ C-API stand-in (minihost/minihost.cpp).
 
 Used by tests and bench.py to drive C plugins -- the unmodified reference build
 (oracle/_ref/libjincresize_ref.so) and the B200 plugin -- through the same
@@ -14,7 +14,8 @@ from dataclasses import dataclass
 
 import numpy as np
 
-from . import paths
+MINIHOST_LIB = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libavs_minihost.so")
+
 
 # ---- pixel types (mirror minihost/include/avisynth_c.h) -------------------
 CS_YUVA = 1 << 27
@@ -112,7 +113,7 @@ class _Lib:
     @classmethod
     def get(cls):
         if cls._inst is None:
-            path = paths.minihost_lib()
+            path = MINIHOST_LIB
             if not os.path.exists(path):
                 raise RuntimeError(f"{path} is missing: run `make host` (or __graft_entry__.build())")
             lib = C.CDLL(path, mode=C.RTLD_GLOBAL)  # plugins resolve avs_* against it
@@ -296,36 +297,3 @@ class Env:
     def live_objects():
         lib = _Lib.get()
         return lib.mh_live_frames(), lib.mh_live_clips()
-
-
-class RefTables:
-    """Reads the reference's own tables out of a filter built by oracle/_ref (via oracle/ref_shim.cpp)."""
-
-    def __init__(self, ref_lib_path: str):
-        self.lib = C.CDLL(ref_lib_path)
-        self.lib.ref_table_count.restype = C.c_int
-        self.lib.ref_table_count.argtypes = [C.c_void_p]
-        self.lib.ref_table_view.restype = C.c_int
-        self.lib.ref_table_view.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
-                                            C.POINTER(C.POINTER(C.c_int)), C.POINTER(C.POINTER(C.c_float))]
-        self.lib.ref_lut.restype = C.POINTER(C.c_double)
-        self.lib.ref_lut.argtypes = [C.c_void_p]
-
-    def count(self, clip: Clip) -> int:
-        return self.lib.ref_table_count(clip.filter_info)
-
-    def lut(self, clip: Clip) -> np.ndarray:
-        p = self.lib.ref_lut(clip.filter_info)
-        return np.ctypeslib.as_array(p, shape=(1024,)).copy()
-
-    def table(self, clip: Clip, k: int, dst_w: int, dst_h: int):
-        """Returns (filter_size, coeff_stride, meta[h,w,3] int32, factor float32 flat)."""
-        fs, cs = C.c_int(), C.c_int()
-        meta, factor = C.POINTER(C.c_int)(), C.POINTER(C.c_float)()
-        rc = self.lib.ref_table_view(clip.filter_info, k, C.byref(fs), C.byref(cs), C.byref(meta), C.byref(factor))
-        if rc != 0:
-            raise IndexError(k)
-        m = np.ctypeslib.as_array(meta, shape=(dst_h, dst_w, 3)).copy()
-        nfl = int(m[..., 2].max()) + fs.value * cs.value
-        f = np.ctypeslib.as_array(factor, shape=(nfl,)).copy()
-        return fs.value, cs.value, m, f

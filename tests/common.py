@@ -3,7 +3,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from jinc_b200 import avs_host as ah
+from minihost import avs_host as ah
 
 
 def make_planes(fmt: ah.Format, width: int, height: int, kind: str = "noise", seed: int = 0):

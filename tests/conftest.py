@@ -25,6 +25,6 @@ def native_built():
 
 @pytest.fixture(scope="session")
 def have_ref(native_built):
-    from jinc_b200 import paths
+    from oracle import ref as oref
 
-    return os.path.exists(paths.ref_plugin())
+    return oref.available()

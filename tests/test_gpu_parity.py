@@ -134,7 +134,7 @@ def test_row_band_split_equals_whole_frame(capi):
 
 
 def test_window_larger_than_plane_is_rejected(capi):
-    from jinc_b200 import avs_host as ah
+    from minihost import avs_host as ah
 
     with pytest.raises(capi.JincError, match="larger than"):
         make_filter(ah.Format("y", 8), 8, 8, 4, 4, tap=8)
@@ -143,7 +143,7 @@ def test_window_larger_than_plane_is_rejected(capi):
 def test_full_size_properties(capi):
     """Size-independent checks at a BASELINE size (config 2, 1080p -> 2160p): constant in -> constant out
     (weights sum to 1), linearity in the input, and agreement with the oracle on sampled row bands."""
-    from jinc_b200 import avs_host as ah
+    from minihost import avs_host as ah
 
     fmt, w, h, tw, th, kw = ah.YUV420P8, 1920, 1080, 3840, 2160, dict(tap=3, cplace="MPEG2")
     flt = make_filter(fmt, w, h, tw, th, **kw)
