@@ -101,6 +101,11 @@ struct Slot {
 struct DeviceState {
     jinc_ctx* ctx = nullptr;
     jinc_table* tables[2] = {nullptr, nullptr};
+    // ring of small device buffers holding the plane-pointer records of batched launches
+    static constexpr int kRing = 8;
+    unsigned char* batch_ptrs[kRing] = {};
+    size_t batch_cap[kRing] = {};
+    int batch_next = 0;
 };
 
 bool is_pinned_host(const void* p)
@@ -395,6 +400,10 @@ extern "C" void jinc_filter_destroy(jinc_filter* f)
             cudaStreamDestroy(s->stream);
     }
     for (DeviceState& d : f->devs) {
+        if (d.ctx)
+            cudaSetDevice(d.ctx->device);
+        for (unsigned char* b : d.batch_ptrs)
+            cudaFree(b);
         jinc_table_destroy(d.tables[0]);
         jinc_table_destroy(d.tables[1]);
         jinc_ctx_destroy(d.ctx);
@@ -543,6 +552,69 @@ extern "C" int jinc_filter_process_device(jinc_filter* f, int device_index, cons
         int launched = 0;
         const int rc = jinc_launch_resize_planes(d.ctx, d.tables[k], f->p.sample_bytes, f->peak, n, src, sp, dst, dp, 0,
                                                  d.tables[k]->sc.dst_h, st, &launched, parts);
+        f->launches.fetch_add(launched);
+        if (rc != JINC_OK)
+            return rc;
+    }
+    return JINC_OK;
+}
+
+extern "C" int jinc_filter_process_device_batch(jinc_filter* f, int device_index, const jinc_frame* frames, int n_frames,
+                                                int table_mask, int parts, void* stream)
+{
+    if (!f || !frames || n_frames < 1)
+        return jinc_fail(JINC_E_INVALID, "jinc_filter_process_device_batch: bad argument");
+    if (device_index < 0 || device_index >= static_cast<int>(f->devs.size()))
+        return jinc_fail(JINC_E_INVALID, "jinc_filter_process_device_batch: bad device index %d", device_index);
+    DeviceState& d = f->devs[device_index];
+    JINC_CUDA(cudaSetDevice(d.ctx->device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : d.ctx->stream;
+    const size_t rec = jinc_plane_ptrs_size();
+    for (int k = 0; k < f->n_tables; ++k) {
+        if (!(table_mask & (1 << k)))
+            continue;
+        std::vector<unsigned char> host(rec * n_frames);
+        int n = 0;
+        for (int fi = 0; fi < n_frames; ++fi) {
+            const void* src[JINC_MAX_PLANES];
+            void* dst[JINC_MAX_PLANES];
+            ptrdiff_t sp[JINC_MAX_PLANES], dp[JINC_MAX_PLANES];
+            n = 0;
+            for (int i = 0; i < f->p.n_planes; ++i) {
+                if (f->planes[i].table != k)
+                    continue;
+                src[n] = frames[fi].src[i];
+                dst[n] = frames[fi].dst[i];
+                sp[n] = frames[fi].src_pitch[i];
+                dp[n] = frames[fi].dst_pitch[i];
+                ++n;
+            }
+            if (n == 0)
+                break;
+            if (int rc = jinc_pack_plane_ptrs(host.data() + rec * fi, f->p.sample_bytes, n, src, sp, dst, dp))
+                return rc;
+        }
+        if (n == 0)
+            continue;
+        unsigned char* dbuf;
+        {
+            std::lock_guard<std::mutex> lk(f->mu);
+            const int slot = d.batch_next;
+            d.batch_next = (d.batch_next + 1) % DeviceState::kRing;
+            if (d.batch_cap[slot] < host.size()) {
+                cudaFree(d.batch_ptrs[slot]);
+                d.batch_ptrs[slot] = nullptr;
+                d.batch_cap[slot] = 0;
+                if (cudaMalloc(reinterpret_cast<void**>(&d.batch_ptrs[slot]), host.size()) != cudaSuccess)
+                    return jinc_fail(JINC_E_NOMEM, "jinc_filter_process_device_batch: cudaMalloc(%zu) failed", host.size());
+                d.batch_cap[slot] = host.size();
+            }
+            dbuf = d.batch_ptrs[slot];
+        }
+        // pageable source: staged by the runtime before the call returns, ordered before the kernel on `st`
+        JINC_CUDA(cudaMemcpyAsync(dbuf, host.data(), host.size(), cudaMemcpyHostToDevice, st));
+        int launched = 0;
+        const int rc = jinc_launch_resize_batch(d.ctx, d.tables[k], f->p.sample_bytes, f->peak, n, dbuf, n_frames, st, &launched, parts);
         f->launches.fetch_add(launched);
         if (rc != JINC_OK)
             return rc;

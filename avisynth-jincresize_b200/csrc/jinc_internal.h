@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "jinc_b200.h"
+#include "jinc_border.h"
 
 // ---------------------------------------------------------------- errors
 void jinc_set_error(const char* fmt, ...) __attribute__((format(printf, 1, 2)));
@@ -88,6 +89,9 @@ struct jinc_table {
     float* d_lut = nullptr;      // JINC_LUT_SAMPLES floats (Lut::GetFactor values)
     float* d_weights = nullptr;  // [n_rank_y][n_rank_x][fs*fs] normalised phase blocks
     std::vector<float> h_weights; // host copy (kernel parameters for the fast paths)
+    BorderGeom bgeom{};          // strips of border pixels
+    float* d_border_sum = nullptr; // [bgeom.total] per-border-pixel normaliser
+    float* d_border_w = nullptr;   // [fs*fs][bgeom.total] resident per-pixel border weights (null: rebuilt on the fly)
     // host mirrors of the small per-axis arrays (for planning and introspection)
     std::vector<int32_t> h_start[2], h_phase[2], h_rank[2], h_qint[2];
     std::vector<uint8_t> h_border[2];
@@ -113,6 +117,12 @@ int jinc_launch_resize_planes(jinc_ctx* ctx, const jinc_table* t, int sample_byt
                               const void* const* d_src, const ptrdiff_t* src_pitch, void* const* d_dst,
                               const ptrdiff_t* dst_pitch, int y_begin, int y_end, cudaStream_t stream, int* launches,
                               int parts = JINC_PART_ALL);
+// batched: d_frame_ptrs is a DEVICE array of n_frames packed plane-pointer records (jinc_pack_plane_ptrs)
+size_t jinc_plane_ptrs_size();
+int jinc_pack_plane_ptrs(void* out, int sample_bytes, int n_planes, const void* const* d_src, const ptrdiff_t* src_pitch,
+                         void* const* d_dst, const ptrdiff_t* dst_pitch);
+int jinc_launch_resize_batch(jinc_ctx* ctx, const jinc_table* t, int sample_bytes, float peak, int n_planes,
+                             const void* d_frame_ptrs, int n_frames, cudaStream_t stream, int* launches, int parts);
 int jinc_debug_pixel_weights(const jinc_table* t, int x, int y, float* out);
 
 #endif

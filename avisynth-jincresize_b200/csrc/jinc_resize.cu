@@ -4,18 +4,20 @@
 // its inner loop.  Every output sample is  sum_{ly,lx} src[start_y+ly][start_x+lx] * w[ly][lx]  over an fs x fs
 // window, followed for integer formats by clamp to [0,peak] and round-half-even (:581-582); float is raw (:583-584).
 //
-// Kernels
-//   resample_up2x     exact 2x upscale (all "JincNNResize(2w,2h)" uses).  The table has 2x2 phase classes; a thread
-//                     owns TX=4 source-aligned cells x 2 cell rows = 8x4 output samples and keeps them in 16 float2
-//                     accumulators.  Source rows live in shared memory as VERTICAL PAIRS {S[r][c], S[r+1][c]} so that
-//                     one packed FFMA2 (fma.rn.f32x2, new on sm_100) updates the same phase of two cell rows with a
-//                     single scalar weight.  Weights arrive as kernel parameters (constant bank) and are fed to the
-//                     FMA pipe through uniform registers (LDCU.128 -> FFMA2 R, R, UR, R): no shared-memory or
-//                     register-file traffic for weights at all.
-//   resample_general  one thread per output sample; interior samples gather their phase block from the L2-resident
-//                     table, border samples build their window weights on the fly from the LUT exactly as the
-//                     reference does per border pixel (:443-514).  Runs the border strips around a fast-path interior
-//                     and whole planes whose geometry has no fast path.
+// One launch covers ALL planes that share a coefficient table, for a whole BATCH of frames, interior and border
+// together; blocks take one of two roles:
+//
+//   interior tile (exact 2x upscale, every "JincNNResize(2w,2h)" use)
+//       The table has 2x2 phase classes.  A thread owns TX=4 source-aligned cells x 2 cell rows = 8x4 output samples in
+//       16 float2 accumulators.  The source tile lives in shared memory as VERTICAL PAIRS {S[r][c], S[r+1][c]} so one
+//       packed FFMA2 (fma.rn.f32x2, new on sm_100) updates the same phase of two cell rows with a single scalar
+//       weight.  Weights arrive as kernel parameters (constant bank) and reach the FMA pipe through uniform registers
+//       (LDCU -> FFMA2 R, R, UR, R): weights cost no shared-memory or register-file bandwidth.  Pair columns are
+//       de-interleaved by (c & 3) so a warp's LDS.64 is bank-conflict free.
+//   strip chunk (256 output samples of the border strips, or of the whole plane when the table has no fast path)
+//       One thread per output sample, all planes of the table in one pass.  Samples whose window was clamped get the
+//       reference's per-pixel weights on the fly: exact LUT index per tap, divided by the per-pixel normaliser that
+//       the table build stored (:443-514); other samples gather their shared phase block from the L2-resident table.
 #include <algorithm>
 #include <cstring>
 
@@ -24,11 +26,24 @@
 
 namespace {
 
-// ------------------------------------------------------------------------------------------ store helpers
+// ------------------------------------------------------------------------------------------ sample conversion
+
+// clamp to [0, peak] and round half to even (lrintf) in one saturating convert; NaN -> 0
+__device__ __forceinline__ uint32_t finish_u8(float v, float peak)
+{
+    uint32_t r;
+    asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(r) : "f"(fminf(v, peak)));
+    return r;
+}
+__device__ __forceinline__ uint32_t finish_u16(float v, float peak)
+{
+    uint32_t r;
+    asm("cvt.rni.sat.u16.f32 %0, %1;" : "=r"(r) : "f"(fminf(v, peak)));
+    return r;
+}
 
 template <typename T>
 __device__ __forceinline__ T finish(float v, float peak);
-
 template <>
 __device__ __forceinline__ float finish<float>(float v, float)
 {
@@ -37,16 +52,12 @@ __device__ __forceinline__ float finish<float>(float v, float)
 template <>
 __device__ __forceinline__ uint8_t finish<uint8_t>(float v, float peak)
 {
-    v = v > peak ? peak : v; // upper bound first (avs/minmax.h clamp)
-    v = v < 0.f ? 0.f : v;
-    return (uint8_t)__float2int_rn(v); // lrintf: round half to even
+    return (uint8_t)finish_u8(v, peak);
 }
 template <>
 __device__ __forceinline__ uint16_t finish<uint16_t>(float v, float peak)
 {
-    v = v > peak ? peak : v;
-    v = v < 0.f ? 0.f : v;
-    return (uint16_t)__float2int_rn(v);
+    return (uint16_t)finish_u16(v, peak);
 }
 
 template <typename T>
@@ -55,186 +66,8 @@ __device__ __forceinline__ float load_sample(const T* p)
     return (float)__ldg(p);
 }
 
-// ------------------------------------------------------------------------------------------ general kernel
-
-struct Rect {
-    int x0, y0, x1, y1;
-};
-
-struct PlanePtrs {
-    const void* src[JINC_MAX_PLANES];
-    void* dst[JINC_MAX_PLANES];
-    long long src_pitch[JINC_MAX_PLANES]; // in elements
-    long long dst_pitch[JINC_MAX_PLANES];
-};
-
-struct GeneralArgs {
-    PlanePtrs pl;
-    const int32_t* start_x;
-    const int32_t* start_y;
-    const int32_t* rank_x;
-    const int32_t* rank_y;
-    const float* pos_x;
-    const float* pos_y;
-    const float* weights;
-    const float* lut;
-    int fs, n_rank_x, src_w, src_h;
-    double step_x, step_y, radius2, idx_scale;
-    float peak;
-    Rect rect[4];
-    int block_begin[5]; // prefix sum of 32x8 blocks per rect
-    int blocks_x[4];
-};
-
-constexpr int GB_X = 32, GB_Y = 8;
-
-template <typename T>
-__global__ void __launch_bounds__(GB_X* GB_Y) resample_general(const __grid_constant__ GeneralArgs a)
-{
-    const int b = blockIdx.x;
-    int r = 0;
-#pragma unroll
-    for (int k = 1; k < 4; ++k)
-        r += b >= a.block_begin[k];
-    const int lb = b - a.block_begin[r];
-    const int by = lb / a.blocks_x[r], bx = lb - by * a.blocks_x[r];
-    const int x = a.rect[r].x0 + bx * GB_X + threadIdx.x;
-    const int y = a.rect[r].y0 + by * GB_Y + threadIdx.y;
-    if (x >= a.rect[r].x1 || y >= a.rect[r].y1)
-        return;
-
-    const int plane = blockIdx.y;
-    const T* __restrict__ src = static_cast<const T*>(a.pl.src[plane]);
-    T* __restrict__ dst = static_cast<T*>(a.pl.dst[plane]);
-    const long long sp = a.pl.src_pitch[plane];
-    const int fs = a.fs;
-    const int sx = a.start_x[x], sy = a.start_y[y];
-    const int rx = a.rank_x[x], ry = a.rank_y[y];
-    const T* s = src + (long long)sy * sp + sx;
-    float acc = 0.f;
-
-    if (rx >= 0 && ry >= 0) {
-        // interior: shared phase block (:431-435)
-        const float* __restrict__ w = a.weights + (size_t)(ry * a.n_rank_x + rx) * fs * fs;
-        for (int ly = 0; ly < fs; ++ly) {
-            for (int lx = 0; lx < fs; ++lx)
-                acc = fmaf(load_sample(s + lx), __ldg(w + lx), acc);
-            w += fs;
-            s += sp;
-        }
-    } else {
-        // border: per-pixel weights from the UNquantised position and the clamped window (:443-514)
-        const float px = a.pos_x[x], py = a.pos_y[y];
-        float sum = 0.f;
-        for (int ly = 0; ly < fs; ++ly) {
-            const double dy2 = jinc_tap_dist2(py, a.src_h, sy + ly, a.step_y);
-            for (int lx = 0; lx < fs; ++lx) {
-                const double dx2 = jinc_tap_dist2(px, a.src_w, sx + lx, a.step_x);
-                sum = __fadd_rn(sum, jinc_lut_weight(a.lut, __dadd_rn(dx2, dy2), a.radius2, a.idx_scale));
-            }
-        }
-        for (int ly = 0; ly < fs; ++ly) {
-            const double dy2 = jinc_tap_dist2(py, a.src_h, sy + ly, a.step_y);
-            for (int lx = 0; lx < fs; ++lx) {
-                const double dx2 = jinc_tap_dist2(px, a.src_w, sx + lx, a.step_x);
-                const float f = jinc_lut_weight(a.lut, __dadd_rn(dx2, dy2), a.radius2, a.idx_scale);
-                acc = fmaf(load_sample(s + lx), __fdiv_rn(f, sum), acc);
-            }
-            s += sp;
-        }
-    }
-    dst[(long long)y * a.pl.dst_pitch[plane] + x] = finish<T>(acc, a.peak);
-}
-
-// weights of one output pixel exactly as resample_general applies them (introspection for parity tests)
-__global__ void pixel_weights_kernel(GeneralArgs a, int x, int y, float* out)
-{
-    const int fs = a.fs;
-    const int rx = a.rank_x[x], ry = a.rank_y[y];
-    if (rx >= 0 && ry >= 0) {
-        const float* w = a.weights + (size_t)(ry * a.n_rank_x + rx) * fs * fs;
-        for (int t = threadIdx.x; t < fs * fs; t += blockDim.x)
-            out[t] = w[t];
-        return;
-    }
-    if (threadIdx.x != 0)
-        return;
-    const int sx = a.start_x[x], sy = a.start_y[y];
-    const float px = a.pos_x[x], py = a.pos_y[y];
-    float sum = 0.f;
-    for (int ly = 0; ly < fs; ++ly) {
-        const double dy2 = jinc_tap_dist2(py, a.src_h, sy + ly, a.step_y);
-        for (int lx = 0; lx < fs; ++lx) {
-            const double dx2 = jinc_tap_dist2(px, a.src_w, sx + lx, a.step_x);
-            const float f = jinc_lut_weight(a.lut, __dadd_rn(dx2, dy2), a.radius2, a.idx_scale);
-            out[ly * fs + lx] = f;
-            sum = __fadd_rn(sum, f);
-        }
-    }
-    for (int t = 0; t < fs * fs; ++t)
-        out[t] = __fdiv_rn(out[t], sum);
-}
-
-void fill_general_args(const jinc_table* t, GeneralArgs& a, float peak)
-{
-    memset(&a, 0, sizeof(a));
-    a.start_x = t->ax[0].start;
-    a.start_y = t->ax[1].start;
-    a.rank_x = t->ax[0].rank;
-    a.rank_y = t->ax[1].rank;
-    a.pos_x = t->ax[0].pos;
-    a.pos_y = t->ax[1].pos;
-    a.weights = t->d_weights;
-    a.lut = t->d_lut;
-    a.fs = t->sc.fs;
-    a.n_rank_x = t->ax[0].n_rank;
-    a.src_w = t->sc.src_w;
-    a.src_h = t->sc.src_h;
-    a.step_x = t->sc.filt_step[0];
-    a.step_y = t->sc.filt_step[1];
-    a.radius2 = t->sc.radius2;
-    a.idx_scale = t->sc.idx_scale;
-    a.peak = peak;
-}
-
-// ------------------------------------------------------------------------------------------ exact-2x kernel
-
-constexpr int UP_TX = 4;                  // cells per thread along x
-constexpr int UP_WARPS = 8;
-constexpr int UP_THREADS = UP_WARPS * 32;
-constexpr int UP_CW = 32 * UP_TX;         // cells per tile row (128 -> 256 output samples)
-constexpr int UP_RPW = 2;                 // cell-row pairs per warp
-constexpr int UP_CH = 2 * UP_WARPS * UP_RPW; // cell rows per tile (32 -> 64 output rows)
-
-template <int FS>
-struct UpGeom {
-    static constexpr int FSP = (FS + 3) & ~3;         // weight row stride (16-byte rows for LDCU.128)
-    static constexpr int NSEG = UP_TX + 1 + FS - 1;   // pair columns a thread reads per row (ox1 <= 1)
-    static constexpr int NC = UP_CW + FS;             // pair columns per tile row (CW + ox1 + FS - 1)
-    static constexpr int NCP = (NC + 3) & ~3;
-    static constexpr int SUB = NCP / 4;               // columns are de-interleaved by (c & 3): 4 sub-rows of SUB
-    static constexpr int NR = UP_CH + 1 + FS - 1;     // pair rows per tile (CH + oy1 + FS - 1)
-    static constexpr size_t SMEM = (size_t)NR * NCP * sizeof(float2);
-};
-
-template <int FS>
-struct alignas(16) UpWeights {
-    float w[2][2][FS][UpGeom<FS>::FSP]; // [py][px][ly][lx]
-};
-
-struct UpArgs {
-    PlanePtrs pl;
-    int src_w, src_h;
-    int x0, y0, ncx, ncy; // output origin of the periodic interior, cells per axis
-    int sx0, sy0;         // window origin of cell (0,0), phase (0,0)
-    int oy1;              // window-origin offset of phase row 1 (0 or 1)
-    int cy_begin, cy_end; // cell rows to produce (row-band split)
-    float peak;
-};
-
 template <typename T>
 __device__ __forceinline__ void store8(T* p, const float (&v)[8], float peak);
-
 template <>
 __device__ __forceinline__ void store8<float>(float* p, const float (&v)[8], float)
 {
@@ -247,7 +80,7 @@ __device__ __forceinline__ void store8<uint16_t>(uint16_t* p, const float (&v)[8
     uint32_t q[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k)
-        q[k] = (uint32_t)finish<uint16_t>(v[2 * k], peak) | ((uint32_t)finish<uint16_t>(v[2 * k + 1], peak) << 16);
+        q[k] = finish_u16(v[2 * k], peak) | (finish_u16(v[2 * k + 1], peak) << 16);
     *reinterpret_cast<uint4*>(p) = make_uint4(q[0], q[1], q[2], q[3]);
 }
 template <>
@@ -256,44 +89,316 @@ __device__ __forceinline__ void store8<uint8_t>(uint8_t* p, const float (&v)[8],
     uint32_t q[2];
 #pragma unroll
     for (int k = 0; k < 2; ++k)
-        q[k] = (uint32_t)finish<uint8_t>(v[4 * k], peak) | ((uint32_t)finish<uint8_t>(v[4 * k + 1], peak) << 8) |
-               ((uint32_t)finish<uint8_t>(v[4 * k + 2], peak) << 16) | ((uint32_t)finish<uint8_t>(v[4 * k + 3], peak) << 24);
+        q[k] = finish_u8(v[4 * k], peak) | (finish_u8(v[4 * k + 1], peak) << 8) | (finish_u8(v[4 * k + 2], peak) << 16) |
+               (finish_u8(v[4 * k + 3], peak) << 24);
     *reinterpret_cast<uint2*>(p) = make_uint2(q[0], q[1]);
 }
 
-template <typename T, int FS, int OX1>
-__global__ void __launch_bounds__(UP_THREADS, 2)
+// ------------------------------------------------------------------------------------------ shared argument blocks
+
+struct Rect {
+    int x0, y0, x1, y1;
+};
+
+// planes of ONE frame that share the table being run (device pointers, pitches in elements)
+struct PlanePtrs {
+    const void* src[JINC_MAX_PLANES];
+    void* dst[JINC_MAX_PLANES];
+    long long src_pitch[JINC_MAX_PLANES];
+    long long dst_pitch[JINC_MAX_PLANES];
+};
+
+// strips: up to four rectangles of output samples, enumerated row-major rect after rect, 256 per block
+struct StripArgs {
+    const int32_t* start_x;
+    const int32_t* start_y;
+    const int32_t* rank_x;
+    const int32_t* rank_y;
+    const float* pos_x;
+    const float* pos_y;
+    const float* weights;
+    const float* lut;
+    const float* border_sum;
+    const float* border_w; // resident per-pixel border weights [tap][slot], or null
+    BorderGeom bg;
+    int fs, n_rank_x, src_w, src_h;
+    double step_x, step_y, radius2, idx_scale;
+    Rect rect[4];
+    long long count_begin[5]; // prefix sums of samples per rect
+};
+
+struct FrameSet {
+    PlanePtrs one;           // used when frames == nullptr
+    const PlanePtrs* frames; // device array [grid.y] for batched launches
+    int n_planes;
+    float peak;
+};
+
+__device__ __forceinline__ const PlanePtrs& frame_ptrs(const FrameSet& fs)
+{
+    return fs.frames ? fs.frames[blockIdx.y] : fs.one;
+}
+
+constexpr int STRIP_THREADS = 256;
+
+// One output sample of a strip, for every plane of the table.
+template <typename T>
+__device__ __forceinline__ void strip_sample(const StripArgs& a, const FrameSet& fsx, long long g)
+{
+    int r = 0;
+#pragma unroll
+    for (int k = 1; k < 4; ++k)
+        r += g >= a.count_begin[k];
+    const long long li = g - a.count_begin[r];
+    const int rw = a.rect[r].x1 - a.rect[r].x0;
+    const int ry_ = (int)(li / rw);
+    const int x = a.rect[r].x0 + (int)(li - (long long)ry_ * rw);
+    const int y = a.rect[r].y0 + ry_;
+
+    const PlanePtrs& pp = frame_ptrs(fsx);
+    const int np = fsx.n_planes;
+    const int fs = a.fs;
+    const int sx = a.start_x[x], sy = a.start_y[y];
+    const int rx = a.rank_x[x], ry = a.rank_y[y];
+    float acc[JINC_MAX_PLANES] = {0.f, 0.f, 0.f, 0.f};
+    const T* s[JINC_MAX_PLANES];
+#pragma unroll
+    for (int p = 0; p < JINC_MAX_PLANES; ++p)
+        s[p] = static_cast<const T*>(pp.src[p]) + (long long)sy * pp.src_pitch[p] + sx; // unused planes: never dereferenced
+
+    const bool shared_block = rx >= 0 && ry >= 0;
+    if (shared_block || a.border_w) {
+        // weights are resident: the shared phase block (:431-435), or this border pixel's own block (tap-major)
+        const float* __restrict__ w;
+        long long wstride;
+        if (shared_block) {
+            w = a.weights + (size_t)(ry * a.n_rank_x + rx) * fs * fs;
+            wstride = 1;
+        } else {
+            w = a.border_w + jinc_border_slot(a.bg, x, y);
+            wstride = a.bg.total;
+        }
+        for (int ly = 0; ly < fs; ++ly) {
+            for (int lx = 0; lx < fs; ++lx) {
+                const float wv = __ldg(w);
+                w += wstride;
+#pragma unroll
+                for (int p = 0; p < JINC_MAX_PLANES; ++p)
+                    if (p < np)
+                        acc[p] = fmaf(load_sample(s[p] + lx), wv, acc[p]);
+            }
+#pragma unroll
+            for (int p = 0; p < JINC_MAX_PLANES; ++p)
+                s[p] += pp.src_pitch[p];
+        }
+    } else {
+        // border weights did not fit the residency budget: rebuild them per sample from the UNquantised position
+        // (:443-514), exact LUT index per tap, factor / divider
+        const float px = a.pos_x[x], py = a.pos_y[y];
+        const float sum = a.border_sum[jinc_border_slot(a.bg, x, y)];
+        for (int ly = 0; ly < fs; ++ly) {
+            const double dy2 = jinc_tap_dist2(py, a.src_h, sy + ly, a.step_y);
+            for (int lx = 0; lx < fs; ++lx) {
+                const double dx2 = jinc_tap_dist2(px, a.src_w, sx + lx, a.step_x);
+                const float f = jinc_lut_weight(a.lut, __dadd_rn(dx2, dy2), a.radius2, a.idx_scale);
+                const float wv = __fdiv_rn(f, sum);
+#pragma unroll
+                for (int p = 0; p < JINC_MAX_PLANES; ++p)
+                    if (p < np)
+                        acc[p] = fmaf(load_sample(s[p] + lx), wv, acc[p]);
+            }
+#pragma unroll
+            for (int p = 0; p < JINC_MAX_PLANES; ++p)
+                s[p] += pp.src_pitch[p];
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < JINC_MAX_PLANES; ++p)
+        if (p < np)
+            static_cast<T*>(pp.dst[p])[(long long)y * pp.dst_pitch[p] + x] = finish<T>(acc[p], fsx.peak);
+}
+
+struct GeneralArgs {
+    FrameSet fr;
+    StripArgs st;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(STRIP_THREADS) resample_strips(const __grid_constant__ GeneralArgs a)
+{
+    const long long g = (long long)blockIdx.x * STRIP_THREADS + threadIdx.x;
+    if (g < a.st.count_begin[4])
+        strip_sample<T>(a.st, a.fr, g);
+}
+
+// weights of one output pixel exactly as the reference defines them (introspection for parity tests)
+__global__ void pixel_weights_kernel(StripArgs a, int x, int y, float* out)
+{
+    const int fs = a.fs;
+    const int rx = a.rank_x[x], ry = a.rank_y[y];
+    if (rx >= 0 && ry >= 0) {
+        const float* w = a.weights + (size_t)(ry * a.n_rank_x + rx) * fs * fs;
+        for (int t = threadIdx.x; t < fs * fs; t += blockDim.x)
+            out[t] = w[t];
+        return;
+    }
+    const int sx = a.start_x[x], sy = a.start_y[y];
+    const float px = a.pos_x[x], py = a.pos_y[y];
+    const float sum = a.border_sum[jinc_border_slot(a.bg, x, y)];
+    for (int t = threadIdx.x; t < fs * fs; t += blockDim.x) {
+        const int ly = t / fs, lx = t - ly * fs;
+        const double dy2 = jinc_tap_dist2(py, a.src_h, sy + ly, a.step_y);
+        const double dx2 = jinc_tap_dist2(px, a.src_w, sx + lx, a.step_x);
+        out[t] = __fdiv_rn(jinc_lut_weight(a.lut, __dadd_rn(dx2, dy2), a.radius2, a.idx_scale), sum);
+    }
+}
+
+void fill_strip_args(const jinc_table* t, StripArgs& a)
+{
+    memset(&a, 0, sizeof(a));
+    a.start_x = t->ax[0].start;
+    a.start_y = t->ax[1].start;
+    a.rank_x = t->ax[0].rank;
+    a.rank_y = t->ax[1].rank;
+    a.pos_x = t->ax[0].pos;
+    a.pos_y = t->ax[1].pos;
+    a.weights = t->d_weights;
+    a.lut = t->d_lut;
+    a.border_sum = t->d_border_sum;
+    a.border_w = t->d_border_w;
+    a.bg = t->bgeom;
+    a.fs = t->sc.fs;
+    a.n_rank_x = t->ax[0].n_rank;
+    a.src_w = t->sc.src_w;
+    a.src_h = t->sc.src_h;
+    a.step_x = t->sc.filt_step[0];
+    a.step_y = t->sc.filt_step[1];
+    a.radius2 = t->sc.radius2;
+    a.idx_scale = t->sc.idx_scale;
+}
+
+// returns the number of 256-sample blocks
+long long set_strip_rects(StripArgs& a, const Rect* rects, int n_rects)
+{
+    long long total = 0;
+    int k = 0;
+    for (int r = 0; r < n_rects; ++r) {
+        const long long w = rects[r].x1 - rects[r].x0, h = rects[r].y1 - rects[r].y0;
+        if (w <= 0 || h <= 0)
+            continue;
+        a.rect[k] = rects[r];
+        a.count_begin[k] = total;
+        total += w * h;
+        ++k;
+    }
+    for (int j = k; j < 4; ++j) {
+        a.rect[j] = Rect{0, 0, 1, 1};
+        a.count_begin[j] = total;
+    }
+    a.count_begin[4] = total;
+    return (total + STRIP_THREADS - 1) / STRIP_THREADS;
+}
+
+// ------------------------------------------------------------------------------------------ exact-2x kernel
+
+constexpr int UP_TX = 4;                     // cells per thread along x
+constexpr int UP_WARPS = 8;
+constexpr int UP_THREADS = UP_WARPS * 32;
+constexpr int UP_CW = 32 * UP_TX;            // cells per tile row (128 -> 256 output samples)
+constexpr int UP_RPW = 2;                    // cell-row pairs per warp
+constexpr int UP_CH = 2 * UP_WARPS * UP_RPW; // cell rows per tile (32 -> 64 output rows)
+static_assert(UP_THREADS == STRIP_THREADS, "both roles share one block size");
+
+template <int FS>
+struct UpGeom {
+    static constexpr int FSP = (FS + 3) & ~3;       // weight row stride (16-byte rows)
+    static constexpr int NSEG = UP_TX + 1 + FS - 1; // pair columns a thread reads per row (ox1 <= 1)
+    static constexpr int NC = UP_CW + FS;           // pair columns per tile row (CW + ox1 + FS - 1)
+    static constexpr int NCP = (NC + 3) & ~3;
+    static constexpr int SUB = NCP / 4;             // columns are de-interleaved by (c & 3): 4 sub-rows of SUB
+    static constexpr int NR = UP_CH + 1 + FS - 1;   // pair rows per tile (CH + oy1 + FS - 1)
+    static constexpr size_t SMEM = (size_t)NR * NCP * sizeof(float2);
+};
+
+template <int FS>
+struct alignas(16) UpWeights {
+    float w[2][2][FS][UpGeom<FS>::FSP]; // [py][px][ly][lx]
+};
+
+struct UpArgs {
+    FrameSet fr;
+    StripArgs st;         // border strips around the interior (run by the blocks after the interior tiles)
+    int src_w, src_h;
+    int x0, y0, ncx;      // output origin of the periodic interior, cells per row
+    int sx0, sy0;         // window origin of cell (0,0), phase (0,0)
+    int cy_begin, cy_end; // cell rows to produce (row-band split)
+    int tiles_x, tiles_per_plane, interior_blocks; // interior_blocks = tiles_per_plane * n_planes
+};
+
+template <typename T, int FS, int OX1, int OY1>
+__global__ void __launch_bounds__(UP_THREADS, (FS >= 13 ? 2 : 3))
     resample_up2x(const __grid_constant__ UpArgs a, const __grid_constant__ UpWeights<FS> W)
 {
     using G = UpGeom<FS>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
+
+    if ((int)blockIdx.x >= a.interior_blocks) {
+        // ---------------- strip role
+        const long long g = (long long)(blockIdx.x - a.interior_blocks) * STRIP_THREADS + threadIdx.x;
+        if (g < a.st.count_begin[4])
+            strip_sample<T>(a.st, a.fr, g);
+        return;
+    }
+
+    // -------------------- interior tile role
     float2* tile = reinterpret_cast<float2*>(smem_raw); // [NR][4][SUB] pairs {S[r][c], S[r+1][c]}
+    const int plane = blockIdx.x / a.tiles_per_plane;
+    const int tidx = blockIdx.x - plane * a.tiles_per_plane;
+    const int tile_y = tidx / a.tiles_x, tile_x = tidx - tile_y * a.tiles_x;
+    const PlanePtrs& pp = frame_ptrs(a.fr);
+    const T* __restrict__ src = static_cast<const T*>(pp.src[plane]);
+    T* __restrict__ dst = static_cast<T*>(pp.dst[plane]);
+    const long long sp = pp.src_pitch[plane], dp = pp.dst_pitch[plane];
 
-    const int plane = blockIdx.z;
-    const T* __restrict__ src = static_cast<const T*>(a.pl.src[plane]);
-    T* __restrict__ dst = static_cast<T*>(a.pl.dst[plane]);
-    const long long sp = a.pl.src_pitch[plane], dp = a.pl.dst_pitch[plane];
-
-    const int cell_x0 = blockIdx.x * UP_CW;               // first cell of this tile
-    const int cell_y0 = a.cy_begin + blockIdx.y * UP_CH;
+    const int cell_x0 = tile_x * UP_CW; // first cell of this tile
+    const int cell_y0 = a.cy_begin + tile_y * UP_CH;
     const int tsx = a.sx0 + cell_x0, tsy = a.sy0 + cell_y0; // source coordinates of tile(0,0)
 
-    // ---- stage the source tile: each item = one pair row x 4 consecutive columns
-    for (int it = threadIdx.x; it < G::NR * G::SUB; it += UP_THREADS) {
-        const int r = it / G::SUB, q = it - r * G::SUB;
-        const int y0 = min(max(tsy + r, 0), a.src_h - 1), y1 = min(max(tsy + r + 1, 0), a.src_h - 1);
-        const T* row0 = src + (long long)y0 * sp;
-        const T* row1 = src + (long long)y1 * sp;
+    // ---- stage the source tile.  A thread owns 4 consecutive columns and walks down a segment of rows, pairing each
+    //      row with the one above it, so every source sample is loaded and converted once per segment.
+    {
+        constexpr int SEGS = UP_THREADS / G::SUB;       // row segments
+        constexpr int ROWS = (G::NR + SEGS - 1) / SEGS; // pair rows per segment
+        const int q = threadIdx.x % G::SUB, seg = threadIdx.x / G::SUB;
+        if (seg < SEGS) {
+            int xo[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int x = min(max(tsx + 4 * q + k, 0), a.src_w - 1); // out-of-plane taps only feed discarded cells
-            tile[(r * 4 + k) * G::SUB + q] = make_float2(load_sample(row0 + x), load_sample(row1 + x));
+            for (int k = 0; k < 4; ++k)
+                xo[k] = min(max(tsx + 4 * q + k, 0), a.src_w - 1); // out-of-plane taps only feed discarded cells
+            const int r0 = seg * ROWS, r1 = min(r0 + ROWS, G::NR);
+            float prev[4], cur[4];
+            {
+                const T* row = src + (long long)min(max(tsy + r0, 0), a.src_h - 1) * sp;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    prev[k] = load_sample(row + xo[k]);
+            }
+            for (int r = r0; r < r1; ++r) {
+                const T* row = src + (long long)min(max(tsy + r + 1, 0), a.src_h - 1) * sp;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    cur[k] = load_sample(row + xo[k]);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    tile[(r * 4 + k) * G::SUB + q] = make_float2(prev[k], cur[k]);
+                    prev[k] = cur[k];
+                }
+            }
         }
     }
     __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int oy1 = a.oy1;
 
 #pragma unroll 1
     for (int rp = warp; rp < UP_WARPS * UP_RPW; rp += UP_WARPS) {
@@ -311,14 +416,14 @@ __global__ void __launch_bounds__(UP_THREADS, 2)
 
         const float2* trow = tile + (size_t)(2 * rp) * G::NCP + lane;
 #pragma unroll 1
-        for (int rr = 0; rr < FS + oy1; ++rr) {
+        for (int rr = 0; rr < FS + OY1; ++rr) {
             float2 seg[G::NSEG];
 #pragma unroll
             for (int m = 0; m < G::NSEG; ++m)
                 seg[m] = trow[(m & 3) * G::SUB + (m >> 2)]; // column 4*lane + m
             trow += G::NCP;
 
-            if (rr < FS) { // phase row 0: ly = rr
+            if (OY1 == 0 || rr < FS) { // phase row 0: ly = rr
 #pragma unroll
                 for (int lx = 0; lx < FS; ++lx) {
                     const float w0 = W.w[0][0][rr][lx], w1 = W.w[0][1][rr][lx];
@@ -329,8 +434,8 @@ __global__ void __launch_bounds__(UP_THREADS, 2)
                     }
                 }
             }
-            const int ly1 = rr - oy1; // phase row 1
-            if (ly1 >= 0) {
+            const int ly1 = rr - OY1; // phase row 1
+            if (OY1 == 0 || rr >= OY1) {
 #pragma unroll
                 for (int lx = 0; lx < FS; ++lx) {
                     const float w0 = W.w[1][0][ly1][lx], w1 = W.w[1][1][ly1][lx];
@@ -362,10 +467,10 @@ __global__ void __launch_bounds__(UP_THREADS, 2)
                 }
                 T* o = dst + (long long)(a.y0 + 2 * (cy + h) + py) * dp + ox;
                 if (cx + UP_TX <= a.ncx) {
-                    store8<T>(o, v, a.peak);
+                    store8<T>(o, v, a.fr.peak);
                 } else {
                     for (int k = 0; k < 2 * (a.ncx - cx); ++k)
-                        o[k] = finish<T>(v[k], a.peak);
+                        o[k] = finish<T>(v[k], a.fr.peak);
                 }
             }
         }
@@ -373,7 +478,7 @@ __global__ void __launch_bounds__(UP_THREADS, 2)
 }
 
 template <typename T, int FS>
-int launch_up2x_fs(const jinc_table* t, const UpArgs& a, int n_planes, cudaStream_t st)
+int launch_up2x_fs(const jinc_table* t, UpArgs& a, long long strip_blocks, int n_frames, cudaStream_t st)
 {
     using G = UpGeom<FS>;
     const Up2xPlan& u = t->up2x;
@@ -386,12 +491,12 @@ int launch_up2x_fs(const jinc_table* t, const UpArgs& a, int n_planes, cudaStrea
                 for (int lx = 0; lx < FS; ++lx)
                     w.w[py][px][ly][lx] = blk[ly * FS + lx];
         }
-    const int rows = a.cy_end - a.cy_begin;
-    dim3 grid((u.ncx + UP_CW - 1) / UP_CW, (rows + UP_CH - 1) / UP_CH, n_planes);
-    auto kern = u.ox1 ? resample_up2x<T, FS, 1> : resample_up2x<T, FS, 0>;
+    auto kern = u.ox1 ? (u.oy1 ? resample_up2x<T, FS, 1, 1> : resample_up2x<T, FS, 1, 0>)
+                      : (u.oy1 ? resample_up2x<T, FS, 0, 1> : resample_up2x<T, FS, 0, 0>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
     if (e != cudaSuccess)
         return jinc_fail(JINC_E_CUDA, "cudaFuncSetAttribute(up2x smem %zu): %s", G::SMEM, cudaGetErrorString(e));
+    dim3 grid((unsigned)(a.interior_blocks + strip_blocks), n_frames, 1);
     kern<<<grid, UP_THREADS, G::SMEM, st>>>(a, w);
     e = cudaGetLastError();
     if (e != cudaSuccess)
@@ -400,14 +505,14 @@ int launch_up2x_fs(const jinc_table* t, const UpArgs& a, int n_planes, cudaStrea
 }
 
 template <typename T>
-int launch_up2x(const jinc_table* t, const UpArgs& a, int n_planes, cudaStream_t st)
+int launch_up2x(const jinc_table* t, UpArgs& a, long long strip_blocks, int n_frames, cudaStream_t st)
 {
     switch (t->sc.fs) {
-    case 7: return launch_up2x_fs<T, 7>(t, a, n_planes, st);   // tap 3  (Jinc36Resize)
-    case 9: return launch_up2x_fs<T, 9>(t, a, n_planes, st);   // tap 4  (Jinc64Resize)
-    case 13: return launch_up2x_fs<T, 13>(t, a, n_planes, st); // tap 6  (Jinc144Resize)
-    case 17: return launch_up2x_fs<T, 17>(t, a, n_planes, st); // tap 8  (Jinc256Resize)
-    default: return 1; // no specialisation: caller falls back to the general kernel
+    case 7: return launch_up2x_fs<T, 7>(t, a, strip_blocks, n_frames, st);   // tap 3  (Jinc36Resize)
+    case 9: return launch_up2x_fs<T, 9>(t, a, strip_blocks, n_frames, st);   // tap 4  (Jinc64Resize)
+    case 13: return launch_up2x_fs<T, 13>(t, a, strip_blocks, n_frames, st); // tap 6  (Jinc144Resize)
+    case 17: return launch_up2x_fs<T, 17>(t, a, strip_blocks, n_frames, st); // tap 8  (Jinc256Resize)
+    default: return 1;
     }
 }
 
@@ -416,111 +521,76 @@ bool up2x_supported(int fs) { return fs == 7 || fs == 9 || fs == 13 || fs == 17;
 // ------------------------------------------------------------------------------------------ launcher
 
 template <typename T>
-int launch_general(const jinc_table* t, GeneralArgs& a, const Rect* rects, int n_rects, int n_planes, cudaStream_t st,
-                   int* launches)
+int launch_typed(const jinc_table* t, const FrameSet& fr, int n_frames, int y_begin, int y_end, cudaStream_t st, int* launches,
+                 int parts)
 {
-    int total = 0, k = 0;
-    for (int r = 0; r < n_rects; ++r) {
-        const int w = rects[r].x1 - rects[r].x0, h = rects[r].y1 - rects[r].y0;
-        if (w <= 0 || h <= 0)
-            continue;
-        a.rect[k] = rects[r];
-        a.blocks_x[k] = (w + GB_X - 1) / GB_X;
-        a.block_begin[k] = total;
-        total += a.blocks_x[k] * ((h + GB_Y - 1) / GB_Y);
-        ++k;
-    }
-    for (int j = k; j < 5; ++j)
-        a.block_begin[j] = total; // unused rects never match
-    if (total == 0)
-        return JINC_OK;
-    for (int j = k; j < 4; ++j) {
-        a.rect[j] = Rect{0, 0, 0, 0};
-        a.blocks_x[j] = 1;
-    }
-    // block_begin[j] for j>=k equals `total`, so the rect search in the kernel stops at the last real rect
-    resample_general<T><<<dim3(total, n_planes), dim3(GB_X, GB_Y), 0, st>>>(a);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess)
-        return jinc_fail(JINC_E_CUDA, "resample_general launch failed: %s", cudaGetErrorString(e));
-    ++*launches;
-    return JINC_OK;
-}
-
-template <typename T>
-int launch_typed(jinc_ctx* ctx, const jinc_table* t, float peak, const PlanePtrs& pl, int n_planes, int y_begin, int y_end,
-                 cudaStream_t st, int* launches, int parts)
-{
-    (void)ctx;
-    GeneralArgs ga;
-    fill_general_args(t, ga, peak);
-    ga.pl = pl;
     const int W = t->sc.dst_w;
+    StripArgs sa;
+    fill_strip_args(t, sa);
     Rect rects[4];
     int n_rects = 0;
 
-    bool fast_done = false;
-    int fy0 = 0, fy1 = 0; // output rows covered by the fast path
     if (t->fast_path == JINC_PATH_UP2X && up2x_supported(t->sc.fs)) {
         const Up2xPlan& u = t->up2x;
-        // cell rows whose 2 output rows lie inside [y_begin, y_end); bands are cut on cell-pair boundaries
-        int cb = (std::max(y_begin, u.y0) - u.y0 + 1) / 2;
-        int ce = (std::min(y_end, u.y0 + 2 * u.ncy) - u.y0) / 2;
-        if (ce > cb && !(parts & JINC_PART_INTERIOR)) {
-            // interior deliberately skipped: still only the strips around it belong to the border part
-            fast_done = true;
-            fy0 = u.y0 + 2 * cb;
-            fy1 = u.y0 + 2 * ce;
-        } else if (ce > cb) {
+        // cell rows whose 2 output rows lie inside [y_begin, y_end)
+        const int cb = (std::max(y_begin, u.y0) - u.y0 + 1) / 2;
+        const int ce = (std::min(y_end, u.y0 + 2 * u.ncy) - u.y0) / 2;
+        if (ce > cb) {
+            const int fy0 = u.y0 + 2 * cb, fy1 = u.y0 + 2 * ce;
+            if (parts & JINC_PART_BORDER) {
+                rects[n_rects++] = Rect{0, y_begin, W, fy0};  // top strip
+                rects[n_rects++] = Rect{0, fy1, W, y_end};    // bottom strip
+                rects[n_rects++] = Rect{0, fy0, t->ix0, fy1}; // left strip
+                rects[n_rects++] = Rect{t->ix1, fy0, W, fy1}; // right strip
+            }
             UpArgs a;
             memset(&a, 0, sizeof(a));
-            a.pl = pl;
+            a.fr = fr;
+            a.st = sa;
+            const long long strip_blocks = set_strip_rects(a.st, rects, n_rects);
             a.src_w = t->sc.src_w;
             a.src_h = t->sc.src_h;
             a.x0 = u.x0;
             a.y0 = u.y0;
             a.ncx = u.ncx;
-            a.ncy = u.ncy;
             a.sx0 = u.sx0;
             a.sy0 = u.sy0;
-            a.oy1 = u.oy1;
             a.cy_begin = cb;
             a.cy_end = ce;
-            a.peak = peak;
-            const int rc = launch_up2x<T>(t, a, n_planes, st);
-            if (rc < 0)
+            a.tiles_x = (u.ncx + UP_CW - 1) / UP_CW;
+            a.tiles_per_plane = a.tiles_x * ((ce - cb + UP_CH - 1) / UP_CH);
+            a.interior_blocks = (parts & JINC_PART_INTERIOR) ? a.tiles_per_plane * fr.n_planes : 0;
+            if (a.interior_blocks + strip_blocks == 0)
+                return JINC_OK;
+            const int rc = launch_up2x<T>(t, a, strip_blocks, n_frames, st);
+            if (rc <= 0) {
+                if (rc == 0)
+                    ++*launches;
                 return rc;
-            if (rc == 0) {
-                ++*launches;
-                fast_done = true;
-                fy0 = u.y0 + 2 * cb;
-                fy1 = u.y0 + 2 * ce;
             }
         }
     }
-    if (fast_done) {
-        rects[n_rects++] = Rect{0, y_begin, W, fy0};            // top strip
-        rects[n_rects++] = Rect{0, fy1, W, y_end};              // bottom strip
-        rects[n_rects++] = Rect{0, fy0, t->ix0, fy1};           // left strip
-        rects[n_rects++] = Rect{t->ix1, fy0, W, fy1};           // right strip
-    } else {
-        rects[n_rects++] = Rect{0, y_begin, W, y_end};
-    }
     if (!(parts & JINC_PART_BORDER))
         return JINC_OK;
-    return launch_general<T>(t, ga, rects, n_rects, n_planes, st, launches);
+    // no fast path for this geometry (or band): every sample goes through the strip role
+    GeneralArgs ga;
+    ga.fr = fr;
+    ga.st = sa;
+    rects[0] = Rect{0, y_begin, W, y_end};
+    const long long blocks = set_strip_rects(ga.st, rects, 1);
+    if (blocks == 0)
+        return JINC_OK;
+    resample_strips<T><<<dim3((unsigned)blocks, n_frames), STRIP_THREADS, 0, st>>>(ga);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess)
+        return jinc_fail(JINC_E_CUDA, "resample_strips launch failed: %s", cudaGetErrorString(e));
+    ++*launches;
+    return JINC_OK;
 }
 
-} // namespace
-
-int jinc_launch_resize_planes(jinc_ctx* ctx, const jinc_table* t, int sample_bytes, float peak, int n_planes,
-                              const void* const* d_src, const ptrdiff_t* src_pitch, void* const* d_dst,
-                              const ptrdiff_t* dst_pitch, int y_begin, int y_end, cudaStream_t stream, int* launches,
-                              int parts)
+int check_and_fill(PlanePtrs& pl, int sample_bytes, int n_planes, const void* const* d_src, const ptrdiff_t* src_pitch,
+                   void* const* d_dst, const ptrdiff_t* dst_pitch)
 {
-    if (n_planes < 1 || n_planes > JINC_MAX_PLANES)
-        return jinc_fail(JINC_E_INVALID, "resize: n_planes must be 1..4");
-    PlanePtrs pl;
     memset(&pl, 0, sizeof(pl));
     for (int i = 0; i < n_planes; ++i) {
         if (!d_src[i] || !d_dst[i])
@@ -534,19 +604,65 @@ int jinc_launch_resize_planes(jinc_ctx* ctx, const jinc_table* t, int sample_byt
         pl.src_pitch[i] = src_pitch[i] / sample_bytes;
         pl.dst_pitch[i] = dst_pitch[i] / sample_bytes;
     }
+    return JINC_OK;
+}
+
+int dispatch(const jinc_table* t, int sample_bytes, const FrameSet& fr, int n_frames, int y_begin, int y_end, cudaStream_t stream,
+             int* launches, int parts)
+{
     y_begin = std::max(y_begin, 0);
     y_end = std::min(y_end, t->sc.dst_h);
-    if (y_end <= y_begin)
+    if (y_end <= y_begin || n_frames <= 0)
         return JINC_OK;
     int dummy = 0;
     if (!launches)
         launches = &dummy;
     switch (sample_bytes) {
-    case 1: return launch_typed<uint8_t>(ctx, t, peak, pl, n_planes, y_begin, y_end, stream, launches, parts);
-    case 2: return launch_typed<uint16_t>(ctx, t, peak, pl, n_planes, y_begin, y_end, stream, launches, parts);
-    case 4: return launch_typed<float>(ctx, t, peak, pl, n_planes, y_begin, y_end, stream, launches, parts);
+    case 1: return launch_typed<uint8_t>(t, fr, n_frames, y_begin, y_end, stream, launches, parts);
+    case 2: return launch_typed<uint16_t>(t, fr, n_frames, y_begin, y_end, stream, launches, parts);
+    case 4: return launch_typed<float>(t, fr, n_frames, y_begin, y_end, stream, launches, parts);
     default: return jinc_fail(JINC_E_INVALID, "resize: sample_bytes must be 1, 2 or 4");
     }
+}
+
+} // namespace
+
+size_t jinc_plane_ptrs_size() { return sizeof(PlanePtrs); }
+
+int jinc_pack_plane_ptrs(void* out, int sample_bytes, int n_planes, const void* const* d_src, const ptrdiff_t* src_pitch,
+                         void* const* d_dst, const ptrdiff_t* dst_pitch)
+{
+    if (n_planes < 1 || n_planes > JINC_MAX_PLANES)
+        return jinc_fail(JINC_E_INVALID, "resize: n_planes must be 1..4");
+    return check_and_fill(*static_cast<PlanePtrs*>(out), sample_bytes, n_planes, d_src, src_pitch, d_dst, dst_pitch);
+}
+
+int jinc_launch_resize_planes(jinc_ctx* ctx, const jinc_table* t, int sample_bytes, float peak, int n_planes,
+                              const void* const* d_src, const ptrdiff_t* src_pitch, void* const* d_dst,
+                              const ptrdiff_t* dst_pitch, int y_begin, int y_end, cudaStream_t stream, int* launches,
+                              int parts)
+{
+    (void)ctx;
+    FrameSet fr;
+    memset(&fr, 0, sizeof(fr));
+    if (int rc = jinc_pack_plane_ptrs(&fr.one, sample_bytes, n_planes, d_src, src_pitch, d_dst, dst_pitch))
+        return rc;
+    fr.frames = nullptr;
+    fr.n_planes = n_planes;
+    fr.peak = peak;
+    return dispatch(t, sample_bytes, fr, 1, y_begin, y_end, stream, launches, parts);
+}
+
+int jinc_launch_resize_batch(jinc_ctx* ctx, const jinc_table* t, int sample_bytes, float peak, int n_planes,
+                             const void* d_frame_ptrs, int n_frames, cudaStream_t stream, int* launches, int parts)
+{
+    (void)ctx;
+    FrameSet fr;
+    memset(&fr, 0, sizeof(fr));
+    fr.frames = static_cast<const PlanePtrs*>(d_frame_ptrs);
+    fr.n_planes = n_planes;
+    fr.peak = peak;
+    return dispatch(t, sample_bytes, fr, n_frames, 0, t->sc.dst_h, stream, launches, parts);
 }
 
 int jinc_launch_resize(jinc_ctx* ctx, const jinc_table* t, int sample_bytes, float peak, const void* d_src,
@@ -554,14 +670,14 @@ int jinc_launch_resize(jinc_ctx* ctx, const jinc_table* t, int sample_bytes, flo
                        int* launches)
 {
     return jinc_launch_resize_planes(ctx, t, sample_bytes, peak, 1, &d_src, &src_pitch, &d_dst, &dst_pitch, y_begin, y_end,
-                                     stream, launches);
+                                     stream, launches, JINC_PART_ALL);
 }
 
 int jinc_debug_pixel_weights(const jinc_table* t, int x, int y, float* out)
 {
     JINC_CUDA(cudaSetDevice(t->ctx->device));
-    GeneralArgs a;
-    fill_general_args(t, a, 0.f);
+    StripArgs a;
+    fill_strip_args(t, a);
     const size_t n = (size_t)t->sc.fs * t->sc.fs;
     float* d = nullptr;
     JINC_CUDA(cudaMalloc(&d, n * sizeof(float)));
@@ -587,7 +703,5 @@ extern "C" int jinc_resize_plane_device(jinc_ctx* ctx, const jinc_table* t, int 
 
 extern "C" int jinc_table_launches_per_plane(const jinc_table* t)
 {
-    if (!t)
-        return 0;
-    return (t->fast_path == JINC_PATH_UP2X && up2x_supported(t->sc.fs)) ? 2 : 1;
+    return t ? 1 : 0; // interior tiles and border strips of all planes sharing the table go out in one launch
 }

@@ -24,6 +24,7 @@
 namespace {
 
 constexpr int kAxisThreads = 1024;
+constexpr size_t kBorderWeightBudget = (size_t)8 << 30; // resident per-pixel border weights per table
 
 struct AxisKernelArgs {
     float* pos;
@@ -47,7 +48,6 @@ __global__ void __launch_bounds__(kAxisThreads) axis_kernel(AxisKernelArgs ax0, 
     const AxisKernelArgs a = blockIdx.x == 0 ? ax0 : ax1;
     __shared__ int s_rep[256];
     __shared__ int s_rank_of[256];
-    __shared__ int s_nrank;
     const int tid = threadIdx.x;
 
     if (tid < 256)
@@ -103,7 +103,6 @@ __global__ void __launch_bounds__(kAxisThreads) axis_kernel(AxisKernelArgs ax0, 
         int c = 0;
         for (int v = 0; v < a.quant; ++v)
             c += s_rep[v] != INT_MAX;
-        s_nrank = c;
         *a.n_rank_out = c;
     }
     __syncthreads();
@@ -154,6 +153,70 @@ __global__ void __launch_bounds__(128) phase_blocks_kernel(float* __restrict__ w
     const float s = s_sum;
     for (int t = threadIdx.x; t < taps; t += blockDim.x)
         w[t] = __fdiv_rn(w[t], s); // :505-514
+}
+
+// Normaliser of every border pixel: the float running sum of its window's LUT factors in row-major tap order
+// (:439,493), from the UNquantised position and the clamped window origin (:443-451 are skipped for border pixels).
+struct BorderSumArgs {
+    BorderGeom g;
+    const float* pos_x;
+    const float* pos_y;
+    const int32_t* start_x;
+    const int32_t* start_y;
+    const float* lut;
+    float* sums;
+    float* weights; // [fs*fs][g.total] normalised per-pixel weights (tap-major so neighbouring pixels coalesce), or null
+    int fs, src_w, src_h;
+    double step_x, step_y, radius2, idx_scale;
+};
+
+__global__ void __launch_bounds__(256) border_sum_kernel(BorderSumArgs a)
+{
+    const long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= a.g.total)
+        return;
+    // invert jinc_border_slot
+    int x, y;
+    const BorderGeom& g = a.g;
+    if (slot < g.off_bottom) {
+        y = (int)(slot / g.W);
+        x = (int)(slot - (long long)y * g.W);
+    } else if (slot < g.off_left) {
+        const long long r = slot - g.off_bottom;
+        y = g.by1 + (int)(r / g.W);
+        x = (int)(r % g.W);
+    } else if (slot < g.off_right) {
+        const long long r = slot - g.off_left;
+        y = g.by0 + (int)(r / g.bx0);
+        x = (int)(r % g.bx0);
+    } else {
+        const long long r = slot - g.off_right;
+        const int w = g.W - g.bx1;
+        y = g.by0 + (int)(r / w);
+        x = g.bx1 + (int)(r % w);
+    }
+    const float px = a.pos_x[x], py = a.pos_y[y];
+    const int sx = a.start_x[x], sy = a.start_y[y];
+    float sum = 0.f;
+    for (int ly = 0; ly < a.fs; ++ly) {
+        const double dy2 = jinc_tap_dist2(py, a.src_h, sy + ly, a.step_y);
+        for (int lx = 0; lx < a.fs; ++lx) {
+            const double dx2 = jinc_tap_dist2(px, a.src_w, sx + lx, a.step_x);
+            sum = __fadd_rn(sum, jinc_lut_weight(a.lut, __dadd_rn(dx2, dy2), a.radius2, a.idx_scale));
+        }
+    }
+    a.sums[slot] = sum;
+    if (!a.weights)
+        return;
+    float* w = a.weights + slot;
+    for (int ly = 0; ly < a.fs; ++ly) {
+        const double dy2 = jinc_tap_dist2(py, a.src_h, sy + ly, a.step_y);
+        for (int lx = 0; lx < a.fs; ++lx) {
+            const double dx2 = jinc_tap_dist2(px, a.src_w, sx + lx, a.step_x);
+            *w = __fdiv_rn(jinc_lut_weight(a.lut, __dadd_rn(dx2, dy2), a.radius2, a.idx_scale), sum); // :505-514
+            w += a.g.total;
+        }
+    }
 }
 
 template <typename T>
@@ -367,6 +430,43 @@ int jinc_table_build_device(jinc_table* t, const double* lut)
                                                                h_nrank[0], s.fs, s.radius2, s.idx_scale);
         JINC_CUDA(cudaGetLastError());
     }
+    // border strips and their per-pixel normalisers
+    {
+        int ax_a[2], ax_b[2];
+        for (int k = 0; k < 2; ++k)
+            interior_run(t->h_border[k], ax_a[k], ax_b[k]);
+        BorderGeom& g = t->bgeom;
+        g.W = s.dst_w;
+        g.H = s.dst_h;
+        g.bx0 = ax_a[0];
+        g.bx1 = ax_b[0];
+        g.by0 = ax_a[1];
+        g.by1 = ax_b[1];
+        const long long core_h = g.by1 - g.by0;
+        g.off_bottom = (long long)g.by0 * g.W;
+        g.off_left = g.off_bottom + (long long)(g.H - g.by1) * g.W;
+        g.off_right = g.off_left + core_h * g.bx0;
+        g.total = g.off_right + core_h * (g.W - g.bx1);
+        if (g.total > 0) {
+            if (int rc = dev_alloc(&t->d_border_sum, (size_t)g.total))
+                return rc;
+            // Per-pixel border weights are frame-invariant: keep them resident (what the reference's table holds on the
+            // host) unless they would not fit the budget, in which case the resample kernel rebuilds them per frame.
+            const size_t bw_bytes = (size_t)g.total * s.fs * s.fs * sizeof(float);
+            size_t free_b = 0, total_b = 0;
+            cudaMemGetInfo(&free_b, &total_b);
+            if (bw_bytes <= kBorderWeightBudget && bw_bytes < free_b / 4) {
+                if (cudaMalloc(reinterpret_cast<void**>(&t->d_border_w), bw_bytes) != cudaSuccess) {
+                    cudaGetLastError();
+                    t->d_border_w = nullptr;
+                }
+            }
+            BorderSumArgs ba{g, t->ax[0].pos, t->ax[1].pos, t->ax[0].start, t->ax[1].start, t->d_lut, t->d_border_sum,
+                             t->d_border_w, s.fs, s.src_w, s.src_h, s.filt_step[0], s.filt_step[1], s.radius2, s.idx_scale};
+            border_sum_kernel<<<(unsigned)((g.total + 255) / 256), 256, 0, st>>>(ba);
+            JINC_CUDA(cudaGetLastError());
+        }
+    }
     plan_fast_paths(t);
     // the fast paths take their (few) phase blocks as kernel parameters: keep a host copy of those
     if (n_blocks > 0 && n_blocks <= 16) {
@@ -432,6 +532,8 @@ extern "C" void jinc_table_destroy(jinc_table* t)
     }
     cudaFree(t->d_lut);
     cudaFree(t->d_weights);
+    cudaFree(t->d_border_sum);
+    cudaFree(t->d_border_w);
     delete t;
 }
 

@@ -57,7 +57,7 @@ EXPORTS = [
     "jinc_table_pixel_block", "jinc_resize_plane_device", "jinc_table_launches_per_plane", "jinc_filter_create",
     "jinc_filter_destroy", "jinc_filter_table", "jinc_filter_num_tables", "jinc_filter_num_devices",
     "jinc_filter_process", "jinc_filter_submit", "jinc_filter_wait", "jinc_filter_process_split",
-    "jinc_filter_kernel_launches", "jinc_filter_process_device",
+    "jinc_filter_kernel_launches", "jinc_filter_process_device", "jinc_filter_process_device_batch",
 ]
 
 _lib = None
@@ -101,6 +101,8 @@ def lib():
         L.jinc_filter_process_split.restype, L.jinc_filter_process_split.argtypes = ci, [vp, C.POINTER(Frame)]
         L.jinc_filter_process_device.restype = ci
         L.jinc_filter_process_device.argtypes = [vp, ci, C.POINTER(Frame), ci, ci, vp]
+        L.jinc_filter_process_device_batch.restype = ci
+        L.jinc_filter_process_device_batch.argtypes = [vp, ci, C.POINTER(Frame), ci, ci, ci, vp]
         L.jinc_filter_kernel_launches.restype, L.jinc_filter_kernel_launches.argtypes = C.c_int64, [vp]
         _lib = L
     return _lib
@@ -290,6 +292,11 @@ class Filter:
         """Device-resident frame (Frame holds device pointers); asynchronous on `stream`."""
         _check(lib().jinc_filter_process_device(self.handle, device_index, C.byref(frame), table_mask, parts,
                                                 stream or None))
+
+    def process_device_batch(self, frames, device_index: int = 0, table_mask: int = 3, parts: int = 3, stream: int = 0):
+        """frames: a ctypes array (Frame * n) of device-pointer frames; one launch per table for the whole batch."""
+        _check(lib().jinc_filter_process_device_batch(self.handle, device_index, frames, len(frames), table_mask, parts,
+                                                      stream or None))
 
     def submit(self, src_planes, dst_planes) -> int:
         fr = self._frame(src_planes, dst_planes)

@@ -178,6 +178,10 @@ JINC_API int jinc_filter_process_split(jinc_filter* f, const jinc_frame* frame);
 enum { JINC_PART_INTERIOR = 1, JINC_PART_BORDER = 2, JINC_PART_ALL = 3 };
 JINC_API int jinc_filter_process_device(jinc_filter* f, int device_index, const jinc_frame* frame, int table_mask,
                                         int parts, void* stream);
+/* Same for a BATCH of device-resident frames: one launch per table covers every frame of the batch (grid.y = frame).
+ * This is the throughput path for callers that keep many frames on the GPU (bench.py's kernel-only leg). */
+JINC_API int jinc_filter_process_device_batch(jinc_filter* f, int device_index, const jinc_frame* frames, int n_frames,
+                                              int table_mask, int parts, void* stream);
 /* kernels launched so far by this filter (all devices) */
 JINC_API int64_t jinc_filter_kernel_launches(const jinc_filter* f);
 
