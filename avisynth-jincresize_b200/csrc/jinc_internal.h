@@ -91,7 +91,7 @@ struct jinc_table {
     std::vector<float> h_weights; // host copy (kernel parameters for the fast paths)
     BorderGeom bgeom{};          // strips of border pixels
     float* d_border_sum = nullptr; // [bgeom.total] per-border-pixel normaliser
-    float* d_border_w = nullptr;   // [fs*fs][bgeom.total] resident per-pixel border weights (null: rebuilt on the fly)
+    float* d_border_w = nullptr;   // [bgeom.total/32][fs*fs][32] resident per-pixel border weights (null: rebuilt on the fly)
     // host mirrors of the small per-axis arrays (for planning and introspection)
     std::vector<int32_t> h_start[2], h_phase[2], h_rank[2], h_qint[2];
     std::vector<uint8_t> h_border[2];

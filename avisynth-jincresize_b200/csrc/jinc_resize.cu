@@ -119,12 +119,13 @@ struct StripArgs {
     const float* weights;
     const float* lut;
     const float* border_sum;
-    const float* border_w; // resident per-pixel border weights [tap][slot], or null
+    const float* border_w; // resident per-pixel border weights [slot/32][tap][slot%32], or null
     BorderGeom bg;
     int fs, n_rank_x, src_w, src_h;
     double step_x, step_y, radius2, idx_scale;
     Rect rect[4];
-    long long count_begin[5]; // prefix sums of samples per rect
+    unsigned count_begin[5]; // prefix sums of samples per rect
+    unsigned blocks_per_plane; // 256-sample blocks covering count_begin[4]; the grid holds this many per plane
 };
 
 struct FrameSet {
@@ -141,55 +142,47 @@ __device__ __forceinline__ const PlanePtrs& frame_ptrs(const FrameSet& fs)
 
 constexpr int STRIP_THREADS = 256;
 
-// One output sample of a strip, for every plane of the table.
-template <typename T>
-__device__ __forceinline__ void strip_sample(const StripArgs& a, const FrameSet& fsx, long long g)
+// One output sample of a strip for ONE plane.  Lean on purpose: 32-bit indexing, constant weight strides, so a tap
+// costs LDG(weight) + LDG(sample) + convert + FFMA.  FSC > 0 fixes the window size at compile time (inner loops unroll).
+template <typename T, int FSC>
+__device__ __forceinline__ void strip_sample(const StripArgs& a, const FrameSet& fsx, unsigned g, int plane)
 {
-    int r = 0;
-#pragma unroll
-    for (int k = 1; k < 4; ++k)
-        r += g >= a.count_begin[k];
-    const long long li = g - a.count_begin[r];
-    const int rw = a.rect[r].x1 - a.rect[r].x0;
-    const int ry_ = (int)(li / rw);
-    const int x = a.rect[r].x0 + (int)(li - (long long)ry_ * rw);
-    const int y = a.rect[r].y0 + ry_;
+    const int r = (int)(g >= a.count_begin[1]) + (int)(g >= a.count_begin[2]) + (int)(g >= a.count_begin[3]);
+    const unsigned li = g - a.count_begin[r];
+    const unsigned rw = (unsigned)(a.rect[r].x1 - a.rect[r].x0);
+    const unsigned rrow = li / rw;
+    const int x = a.rect[r].x0 + (int)(li - rrow * rw);
+    const int y = a.rect[r].y0 + (int)rrow;
 
     const PlanePtrs& pp = frame_ptrs(fsx);
-    const int np = fsx.n_planes;
-    const int fs = a.fs;
+    const int fs = FSC > 0 ? FSC : a.fs;
     const int sx = a.start_x[x], sy = a.start_y[y];
     const int rx = a.rank_x[x], ry = a.rank_y[y];
-    float acc[JINC_MAX_PLANES] = {0.f, 0.f, 0.f, 0.f};
-    const T* s[JINC_MAX_PLANES];
-#pragma unroll
-    for (int p = 0; p < JINC_MAX_PLANES; ++p)
-        s[p] = static_cast<const T*>(pp.src[p]) + (long long)sy * pp.src_pitch[p] + sx; // unused planes: never dereferenced
+    const int pitch = (int)pp.src_pitch[plane];
+    const T* __restrict__ s = static_cast<const T*>(pp.src[plane]) + (long long)sy * pitch + sx;
+    float acc = 0.f;
 
-    const bool shared_block = rx >= 0 && ry >= 0;
-    if (shared_block || a.border_w) {
-        // weights are resident: the shared phase block (:431-435), or this border pixel's own block (tap-major)
-        const float* __restrict__ w;
-        long long wstride;
-        if (shared_block) {
-            w = a.weights + (size_t)(ry * a.n_rank_x + rx) * fs * fs;
-            wstride = 1;
-        } else {
-            w = a.border_w + jinc_border_slot(a.bg, x, y);
-            wstride = a.bg.total;
-        }
+    if (rx >= 0 && ry >= 0) {
+        // shared phase block (:431-435), row-major fs x fs
+        const float* __restrict__ w = a.weights + (unsigned)(ry * a.n_rank_x + rx) * (unsigned)(fs * fs);
         for (int ly = 0; ly < fs; ++ly) {
-            for (int lx = 0; lx < fs; ++lx) {
-                const float wv = __ldg(w);
-                w += wstride;
 #pragma unroll
-                for (int p = 0; p < JINC_MAX_PLANES; ++p)
-                    if (p < np)
-                        acc[p] = fmaf(load_sample(s[p] + lx), wv, acc[p]);
-            }
+            for (int lx = 0; lx < (FSC > 0 ? FSC : fs); ++lx)
+                acc = fmaf(load_sample(s + lx), __ldg(w + lx), acc);
+            w += fs;
+            s += pitch;
+        }
+    } else if (a.border_w) {
+        // this border pixel's own resident block (:443-514), stored [slot / 32][tap][slot % 32]: neighbouring pixels
+        // coalesce and the tap stride is the constant 32
+        const long long slot = jinc_border_slot(a.bg, x, y);
+        const float* __restrict__ w = a.border_w + (size_t)(slot >> 5) * (size_t)(fs * fs * 32) + (unsigned)(slot & 31);
+        for (int ly = 0; ly < fs; ++ly) {
 #pragma unroll
-            for (int p = 0; p < JINC_MAX_PLANES; ++p)
-                s[p] += pp.src_pitch[p];
+            for (int lx = 0; lx < (FSC > 0 ? FSC : fs); ++lx)
+                acc = fmaf(load_sample(s + lx), __ldg(w + lx * 32), acc);
+            w += fs * 32;
+            s += pitch;
         }
     } else {
         // border weights did not fit the residency budget: rebuild them per sample from the UNquantised position
@@ -201,21 +194,22 @@ __device__ __forceinline__ void strip_sample(const StripArgs& a, const FrameSet&
             for (int lx = 0; lx < fs; ++lx) {
                 const double dx2 = jinc_tap_dist2(px, a.src_w, sx + lx, a.step_x);
                 const float f = jinc_lut_weight(a.lut, __dadd_rn(dx2, dy2), a.radius2, a.idx_scale);
-                const float wv = __fdiv_rn(f, sum);
-#pragma unroll
-                for (int p = 0; p < JINC_MAX_PLANES; ++p)
-                    if (p < np)
-                        acc[p] = fmaf(load_sample(s[p] + lx), wv, acc[p]);
+                acc = fmaf(load_sample(s + lx), __fdiv_rn(f, sum), acc);
             }
-#pragma unroll
-            for (int p = 0; p < JINC_MAX_PLANES; ++p)
-                s[p] += pp.src_pitch[p];
+            s += pitch;
         }
     }
-#pragma unroll
-    for (int p = 0; p < JINC_MAX_PLANES; ++p)
-        if (p < np)
-            static_cast<T*>(pp.dst[p])[(long long)y * pp.dst_pitch[p] + x] = finish<T>(acc[p], fsx.peak);
+    static_cast<T*>(pp.dst[plane])[(long long)y * pp.dst_pitch[plane] + x] = finish<T>(acc, fsx.peak);
+}
+
+// strip block `sb` of the grid: planes are the slow dimension
+template <typename T, int FSC>
+__device__ __forceinline__ void strip_block(const StripArgs& a, const FrameSet& fsx, unsigned sb)
+{
+    const unsigned plane = sb / a.blocks_per_plane;
+    const unsigned g = (sb - plane * a.blocks_per_plane) * STRIP_THREADS + threadIdx.x;
+    if (g < a.count_begin[4])
+        strip_sample<T, FSC>(a, fsx, g, (int)plane);
 }
 
 struct GeneralArgs {
@@ -226,9 +220,7 @@ struct GeneralArgs {
 template <typename T>
 __global__ void __launch_bounds__(STRIP_THREADS) resample_strips(const __grid_constant__ GeneralArgs a)
 {
-    const long long g = (long long)blockIdx.x * STRIP_THREADS + threadIdx.x;
-    if (g < a.st.count_begin[4])
-        strip_sample<T>(a.st, a.fr, g);
+    strip_block<T, 0>(a.st, a.fr, blockIdx.x);
 }
 
 // weights of one output pixel exactly as the reference defines them (introspection for parity tests)
@@ -277,10 +269,10 @@ void fill_strip_args(const jinc_table* t, StripArgs& a)
     a.idx_scale = t->sc.idx_scale;
 }
 
-// returns the number of 256-sample blocks
+// returns the number of 256-sample blocks per plane
 long long set_strip_rects(StripArgs& a, const Rect* rects, int n_rects)
 {
-    long long total = 0;
+    unsigned total = 0;
     int k = 0;
     for (int r = 0; r < n_rects; ++r) {
         const long long w = rects[r].x1 - rects[r].x0, h = rects[r].y1 - rects[r].y0;
@@ -288,7 +280,7 @@ long long set_strip_rects(StripArgs& a, const Rect* rects, int n_rects)
             continue;
         a.rect[k] = rects[r];
         a.count_begin[k] = total;
-        total += w * h;
+        total += (unsigned)(w * h);
         ++k;
     }
     for (int j = k; j < 4; ++j) {
@@ -296,7 +288,8 @@ long long set_strip_rects(StripArgs& a, const Rect* rects, int n_rects)
         a.count_begin[j] = total;
     }
     a.count_begin[4] = total;
-    return (total + STRIP_THREADS - 1) / STRIP_THREADS;
+    a.blocks_per_plane = (total + STRIP_THREADS - 1) / STRIP_THREADS;
+    return a.blocks_per_plane;
 }
 
 // ------------------------------------------------------------------------------------------ exact-2x kernel
@@ -344,9 +337,7 @@ __global__ void __launch_bounds__(UP_THREADS, (FS >= 13 ? 2 : 3))
 
     if ((int)blockIdx.x >= a.interior_blocks) {
         // ---------------- strip role
-        const long long g = (long long)(blockIdx.x - a.interior_blocks) * STRIP_THREADS + threadIdx.x;
-        if (g < a.st.count_begin[4])
-            strip_sample<T>(a.st, a.fr, g);
+        strip_block<T, FS>(a.st, a.fr, blockIdx.x - a.interior_blocks);
         return;
     }
 
@@ -455,22 +446,25 @@ __global__ void __launch_bounds__(UP_THREADS, (FS >= 13 ? 2 : 3))
         const int ox = a.x0 + 2 * cx;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            if (cy + h >= a.cy_end)
-                break;
+            if (cy + h < a.cy_end) {
 #pragma unroll
-            for (int py = 0; py < 2; ++py) {
-                float v[8];
+                for (int py = 0; py < 2; ++py) {
+                    float v[8];
 #pragma unroll
-                for (int i = 0; i < UP_TX; ++i) {
-                    v[2 * i] = h ? acc[py][0][i].y : acc[py][0][i].x;
-                    v[2 * i + 1] = h ? acc[py][1][i].y : acc[py][1][i].x;
-                }
-                T* o = dst + (long long)(a.y0 + 2 * (cy + h) + py) * dp + ox;
-                if (cx + UP_TX <= a.ncx) {
-                    store8<T>(o, v, a.fr.peak);
-                } else {
-                    for (int k = 0; k < 2 * (a.ncx - cx); ++k)
-                        o[k] = finish<T>(v[k], a.fr.peak);
+                    for (int i = 0; i < UP_TX; ++i) {
+                        v[2 * i] = h ? acc[py][0][i].y : acc[py][0][i].x;
+                        v[2 * i + 1] = h ? acc[py][1][i].y : acc[py][1][i].x;
+                    }
+                    T* o = dst + (long long)(a.y0 + 2 * (cy + h) + py) * dp + ox;
+                    if (cx + UP_TX <= a.ncx) {
+                        store8<T>(o, v, a.fr.peak);
+                    } else {
+                        const int nk = 2 * (a.ncx - cx);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            if (k < nk)
+                                o[k] = finish<T>(v[k], a.fr.peak);
+                    }
                 }
             }
         }
@@ -547,7 +541,7 @@ int launch_typed(const jinc_table* t, const FrameSet& fr, int n_frames, int y_be
             memset(&a, 0, sizeof(a));
             a.fr = fr;
             a.st = sa;
-            const long long strip_blocks = set_strip_rects(a.st, rects, n_rects);
+            const long long strip_blocks = set_strip_rects(a.st, rects, n_rects) * fr.n_planes;
             a.src_w = t->sc.src_w;
             a.src_h = t->sc.src_h;
             a.x0 = u.x0;
@@ -577,7 +571,7 @@ int launch_typed(const jinc_table* t, const FrameSet& fr, int n_frames, int y_be
     ga.fr = fr;
     ga.st = sa;
     rects[0] = Rect{0, y_begin, W, y_end};
-    const long long blocks = set_strip_rects(ga.st, rects, 1);
+    const long long blocks = set_strip_rects(ga.st, rects, 1) * fr.n_planes;
     if (blocks == 0)
         return JINC_OK;
     resample_strips<T><<<dim3((unsigned)blocks, n_frames), STRIP_THREADS, 0, st>>>(ga);

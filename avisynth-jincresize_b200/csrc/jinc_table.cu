@@ -165,7 +165,7 @@ struct BorderSumArgs {
     const int32_t* start_y;
     const float* lut;
     float* sums;
-    float* weights; // [fs*fs][g.total] normalised per-pixel weights (tap-major so neighbouring pixels coalesce), or null
+    float* weights; // [g.total / 32][fs*fs][32] normalised per-pixel weights (neighbouring pixels coalesce, tap stride 32), or null
     int fs, src_w, src_h;
     double step_x, step_y, radius2, idx_scale;
 };
@@ -208,13 +208,13 @@ __global__ void __launch_bounds__(256) border_sum_kernel(BorderSumArgs a)
     a.sums[slot] = sum;
     if (!a.weights)
         return;
-    float* w = a.weights + slot;
+    float* w = a.weights + (size_t)(slot >> 5) * (size_t)(a.fs * a.fs * 32) + (slot & 31);
     for (int ly = 0; ly < a.fs; ++ly) {
         const double dy2 = jinc_tap_dist2(py, a.src_h, sy + ly, a.step_y);
         for (int lx = 0; lx < a.fs; ++lx) {
             const double dx2 = jinc_tap_dist2(px, a.src_w, sx + lx, a.step_x);
             *w = __fdiv_rn(jinc_lut_weight(a.lut, __dadd_rn(dx2, dy2), a.radius2, a.idx_scale), sum); // :505-514
-            w += a.g.total;
+            w += 32;
         }
     }
 }
@@ -452,7 +452,7 @@ int jinc_table_build_device(jinc_table* t, const double* lut)
                 return rc;
             // Per-pixel border weights are frame-invariant: keep them resident (what the reference's table holds on the
             // host) unless they would not fit the budget, in which case the resample kernel rebuilds them per frame.
-            const size_t bw_bytes = (size_t)g.total * s.fs * s.fs * sizeof(float);
+            const size_t bw_bytes = (size_t)((g.total + 31) / 32 * 32) * s.fs * s.fs * sizeof(float);
             size_t free_b = 0, total_b = 0;
             cudaMemGetInfo(&free_b, &total_b);
             if (bw_bytes <= kBorderWeightBudget && bw_bytes < free_b / 4) {

@@ -1,0 +1,6 @@
+# Quick GPU check: parity tests + kernel-only bench lines.  Usage: bash tools/gpu_quick.sh <tag> [configs...]
+TAG=${1:-quick}; shift
+CFGS=${@:-2}
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q --maxfail=10 --tb=short -p no:cacheprovider 2>&1 | tail -15 | tee gpurun_out/${TAG}_pytest_gpu.log
+for c in $CFGS; do timeout 600 python bench.py --config $c --steps 10 --warmup 3 --no-cpu 2>&1 | tail -1 | tee gpurun_out/${TAG}_bench_config$c.json; done
