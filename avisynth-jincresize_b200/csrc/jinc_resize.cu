@@ -20,6 +20,7 @@
 //       the table build stored (:443-514); other samples gather their shared phase block from the L2-resident table.
 #include <algorithm>
 #include <cstring>
+#include <type_traits>
 
 #include "jinc_internal.h"
 #include "jinc_weights.cuh"
@@ -100,6 +101,15 @@ struct Rect {
     int x0, y0, x1, y1;
 };
 
+// bits per component back from peak = (1 << bits) - 1
+inline int t_bits_from_peak(float peak)
+{
+    int bits = 0;
+    while (bits < 32 && (float)((1ll << bits) - 1) < peak)
+        ++bits;
+    return bits;
+}
+
 // planes of ONE frame that share the table being run (device pointers, pitches in elements)
 struct PlanePtrs {
     const void* src[JINC_MAX_PLANES];
@@ -120,6 +130,8 @@ struct StripArgs {
     const float* lut;
     const float* border_sum;
     const float* border_w; // resident per-pixel border weights [slot/32][tap][slot%32], or null
+    const int32_t* border_block; // slot -> class block, or null
+    const float* border_wb;      // [block][tap] class blocks
     BorderGeom bg;
     int fs, n_rank_x, src_w, src_h;
     double step_x, step_y, radius2, idx_scale;
@@ -162,9 +174,11 @@ __device__ __forceinline__ void strip_sample(const StripArgs& a, const FrameSet&
     const T* __restrict__ s = static_cast<const T*>(pp.src[plane]) + (long long)sy * pitch + sx;
     float acc = 0.f;
 
-    if (rx >= 0 && ry >= 0) {
-        // shared phase block (:431-435), row-major fs x fs
-        const float* __restrict__ w = a.weights + (unsigned)(ry * a.n_rank_x + rx) * (unsigned)(fs * fs);
+    const bool shared_block = rx >= 0 && ry >= 0;
+    if (shared_block || a.border_block) {
+        // shared phase block (:431-435), or the block of this border pixel's class; row-major fs x fs
+        const float* __restrict__ w = shared_block ? a.weights + (unsigned)(ry * a.n_rank_x + rx) * (unsigned)(fs * fs)
+                                                   : a.border_wb + (size_t)a.border_block[jinc_border_slot(a.bg, x, y)] * (unsigned)(fs * fs);
         for (int ly = 0; ly < fs; ++ly) {
 #pragma unroll
             for (int lx = 0; lx < (FSC > 0 ? FSC : fs); ++lx)
@@ -202,12 +216,12 @@ __device__ __forceinline__ void strip_sample(const StripArgs& a, const FrameSet&
     static_cast<T*>(pp.dst[plane])[(long long)y * pp.dst_pitch[plane] + x] = finish<T>(acc, fsx.peak);
 }
 
-// strip block `sb` of the grid: planes are the slow dimension
-template <typename T, int FSC>
+// strip block `sb` of the grid: planes are the slow dimension.  THREADS = block size of the launching kernel
+template <typename T, int FSC, int THREADS = STRIP_THREADS>
 __device__ __forceinline__ void strip_block(const StripArgs& a, const FrameSet& fsx, unsigned sb)
 {
     const unsigned plane = sb / a.blocks_per_plane;
-    const unsigned g = (sb - plane * a.blocks_per_plane) * STRIP_THREADS + threadIdx.x;
+    const unsigned g = (sb - plane * a.blocks_per_plane) * THREADS + threadIdx.x;
     if (g < a.count_begin[4])
         strip_sample<T, FSC>(a, fsx, g, (int)plane);
 }
@@ -258,6 +272,8 @@ void fill_strip_args(const jinc_table* t, StripArgs& a)
     a.lut = t->d_lut;
     a.border_sum = t->d_border_sum;
     a.border_w = t->d_border_w;
+    a.border_block = t->d_border_block;
+    a.border_wb = t->d_border_wb;
     a.bg = t->bgeom;
     a.fs = t->sc.fs;
     a.n_rank_x = t->ax[0].n_rank;
@@ -269,8 +285,8 @@ void fill_strip_args(const jinc_table* t, StripArgs& a)
     a.idx_scale = t->sc.idx_scale;
 }
 
-// returns the number of 256-sample blocks per plane
-long long set_strip_rects(StripArgs& a, const Rect* rects, int n_rects)
+// returns the number of `threads`-sample blocks per plane
+long long set_strip_rects(StripArgs& a, const Rect* rects, int n_rects, int threads = STRIP_THREADS)
 {
     unsigned total = 0;
     int k = 0;
@@ -288,7 +304,7 @@ long long set_strip_rects(StripArgs& a, const Rect* rects, int n_rects)
         a.count_begin[j] = total;
     }
     a.count_begin[4] = total;
-    a.blocks_per_plane = (total + STRIP_THREADS - 1) / STRIP_THREADS;
+    a.blocks_per_plane = (total + threads - 1) / threads;
     return a.blocks_per_plane;
 }
 
@@ -512,6 +528,367 @@ int launch_up2x(const jinc_table* t, UpArgs& a, long long strip_blocks, int n_fr
 
 bool up2x_supported(int fs) { return fs == 7 || fs == 9 || fs == 13 || fs == 17; }
 
+// ------------------------------------------------------------------------------------------ integer-ratio downscale kernel
+//
+// Output (x,y) of the interior reads the FS x FS window at (sx0 + Q*x, sy0 + Q*y) with ONE weight block for every
+// pixel (config 5: Q = 4, FS = 50, 2500 taps per sample).  All threads apply the same weight at the same time, so
+// weights again come from the constant bank through uniform registers.  Three ideas shape the kernel:
+//   * polyphase columns: lx = Q*m + p turns the x-sum into Q stride-1 convolutions over the de-interleaved sequences
+//     S_p[j] = S[Q*j + p]; a thread that owns NX consecutive outputs reads a span of NX+MT-1 values per (row, p) and
+//     uses each for up to NX outputs, and one weight fetch feeds NX FFMA2s;
+//   * tap pairing: one packed FFMA2 multiplies the vertical sample pair {S[r][c], S[r+1][c]} with the weight pair
+//     {w[ly][lx], w[ly+1][lx]} into the two halves of ONE output's accumulator (even-row and odd-row partial sums,
+//     added in the epilogue).  Q is even, so every output row of the thread sees the same pairing and a staged pair
+//     is reused for all NY output rows of the thread;
+//   * raw sample pairs in shared memory for integer formats (two 16-bit samples per 32-bit word; u8 is widened while
+//     staging), so a 64x32-output tile with its 302x174-sample footprint fits twice per SM.  The float value is made
+//     after the shared-memory load.  For depths up to 15 bits that costs ONE byte permute per sample: staging stores
+//     x << (15 - bits), and PRMT drops those 16 bits into mantissa bits [22:8] of 0x3F000000, i.e. f = 0.5 + x' / 65536
+//     exactly.  The kernel accumulates sum(w * f) and the epilogue removes the 0.5 * sum(w) bias (host-computed per
+//     accumulator half) and rescales by a power of two.  Precision matches a direct float sum of 15-bit samples (the
+//     accumulator's ulp relative to one input LSB is the same).  16-bit samples use I2F instead (XU pipe).
+// Columns are de-interleaved by c mod (Q*NX) so a warp's loads are bank-conflict free.
+constexpr int DN_TW = 64;  // output columns per tile
+constexpr int DN_TH = 32;  // output rows per tile (integer formats; float tiles are half as tall)
+
+enum { DN_CVT_I2F = 0, DN_CVT_PRMT = 1, DN_CVT_FLOAT = 2 };
+
+template <typename T, int FS, int Q, int NX, int NY>
+struct DownGeom {
+    static constexpr bool IS_FLOAT = sizeof(T) == 4;
+    using Word = typename std::conditional<IS_FLOAT, float2, uint32_t>::type; // {row 2k, row 2k+1}
+    static constexpr int LX = DN_TW / NX;               // lanes along x
+    static constexpr int LY = 32 / LX;                  // lanes along y
+    static constexpr int TH = IS_FLOAT ? DN_TH / 2 : DN_TH;
+    static constexpr int WARPS = TH / (LY * NY);
+    static constexpr int THREADS = 32 * WARPS;
+    static constexpr int FSE = (FS + 1) & ~1;           // window rows rounded up to whole pairs
+    static constexpr int NKW = FSE / 2;                 // weight row pairs
+    static constexpr int MT = (FS + Q - 1) / Q;         // taps per polyphase component
+    static constexpr int SPAN = NX + MT - 1;            // values a thread reads per (row pair, p)
+    static constexpr int D = Q * NX;                    // column de-interleave modulus
+    static constexpr int NCOL = Q * (DN_TW - 1) + Q * (MT - 1) + Q; // columns a tile row can be asked for
+    static constexpr int SUB = (NCOL + D - 1) / D;
+    static constexpr int NROWS = Q * (TH - 1) + FSE;
+    static constexpr int NROWP = (NROWS + 1) / 2;       // row pairs per tile
+    static constexpr int JSTEP = Q / 2;                 // row pairs between consecutive output rows
+    static constexpr int NK = NKW + JSTEP * (NY - 1);   // row pairs a thread walks
+    static constexpr int HALF = NY * JSTEP;             // row pairs between lane groups that differ in y
+    static constexpr int rs_pad()
+    {
+        for (int pad = 0; pad < 32; ++pad) // lane group g lands on banks [g*LX, g*LX + LX)
+            if (((D * SUB + pad) * HALF) % 32 == LX % 32)
+                return pad;
+        return 0;
+    }
+    static constexpr int RS = D * SUB + rs_pad();       // row-pair stride in words
+    static constexpr size_t SMEM = (size_t)NROWP * RS * sizeof(Word);
+    static_assert(Q % 2 == 0, "tap pairing needs an even ratio");
+    static_assert(TH % (LY * NY) == 0 && WARPS >= 1, "tile rows must split evenly over the warps");
+    static_assert(LX - 1 + (Q * (SPAN - 1) + Q - 1) / D < SUB, "span reaches past the tile row");
+};
+
+template <int FS, int Q>
+struct alignas(16) DownWeights {
+    static constexpr int MT = (FS + Q - 1) / Q;
+    float2 w[((FS + 1) & ~1) / 2][Q][MT]; // [ly/2][p][m] = {w[ly][Q*m+p], w[ly+1][Q*m+p]}; entries outside the window are 0
+};
+
+struct DownArgs {
+    FrameSet fr;
+    StripArgs st;
+    int src_w, src_h;
+    int x0, y0, x1, y1;  // output rectangle produced by the tiles (y0..y1 already cut to the row band)
+    int tsx0, tsy0;      // window origin of output (x0, y0)
+    int tiles_x, tiles_per_plane, interior_blocks;
+    int pre_shift;       // PRMT conversion: samples are staged as x << pre_shift
+    float bias_even, bias_odd, out_scale; // PRMT conversion: out = ((acc.x - bias_even) + (acc.y - bias_odd)) * out_scale
+};
+
+template <int CVT>
+__device__ __forceinline__ float2 down_cvt(uint32_t w)
+{
+    if (CVT == DN_CVT_PRMT)
+        return make_float2(__uint_as_float(__byte_perm(w, 0x3F000000u, 0x7104)), __uint_as_float(__byte_perm(w, 0x3F000000u, 0x7324)));
+    return make_float2((float)(w & 0xffffu), (float)(w >> 16));
+}
+template <int CVT>
+__device__ __forceinline__ float2 down_cvt(float2 w)
+{
+    return w;
+}
+
+template <typename T>
+__device__ __forceinline__ void down_pack(uint32_t& out, const T* r0, const T* r1, int sh)
+{
+    out = ((uint32_t)__ldg(r0) << sh) | ((uint32_t)__ldg(r1) << (16 + sh));
+}
+__device__ __forceinline__ void down_pack(float2& out, const float* r0, const float* r1, int)
+{
+    out = make_float2(__ldg(r0), __ldg(r1));
+}
+
+template <typename T, int N>
+__device__ __forceinline__ void store_run(T* p, const float (&v)[N], float peak)
+{
+    static_assert(N % 4 == 0, "runs are multiples of four samples");
+#pragma unroll
+    for (int q = 0; q < N; q += 4) {
+        if (sizeof(T) == 4) {
+            *reinterpret_cast<float4*>(p + q) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
+        } else if (sizeof(T) == 2) {
+            *reinterpret_cast<uint2*>(p + q) = make_uint2(finish_u16(v[q], peak) | (finish_u16(v[q + 1], peak) << 16),
+                                                          finish_u16(v[q + 2], peak) | (finish_u16(v[q + 3], peak) << 16));
+        } else {
+            *reinterpret_cast<uint32_t*>(p + q) = finish_u8(v[q], peak) | (finish_u8(v[q + 1], peak) << 8) |
+                                                  (finish_u8(v[q + 2], peak) << 16) | (finish_u8(v[q + 3], peak) << 24);
+        }
+    }
+}
+
+// one row pair of the thread's walk.  ALL: every output row of the thread is inside its window (no tests)
+template <typename G, int FS, int Q, int NX, int NY, int CVT, bool ALL>
+__device__ __forceinline__ void down_row_pair(const typename G::Word* __restrict__ trow, int k, const DownWeights<FS, Q>& W,
+                                              float2 (&acc)[NY][NX])
+{
+#pragma unroll
+    for (int p = 0; p < Q; ++p) {
+        float2 s[G::SPAN];
+#pragma unroll
+        for (int m = 0; m < G::SPAN; ++m) {
+            const int cc = Q * m + p;
+            s[m] = down_cvt<CVT>(trow[(cc % G::D) * G::SUB + cc / G::D]);
+        }
+#pragma unroll
+        for (int j = 0; j < NY; ++j) {
+            const int kk = k - j * G::JSTEP; // weight row pair of output row j
+            if (ALL || (kk >= 0 && kk < G::NKW)) {
+#pragma unroll
+                for (int m = 0; m < G::MT; ++m) {
+                    if (Q * m + p < FS) {
+                        const float2 w = W.w[kk][p][m];
+#pragma unroll
+                        for (int i = 0; i < NX; ++i)
+                            acc[j][i] = __ffma2_rn(s[i + m], w, acc[j][i]);
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <typename T, int FS, int Q, int NX, int NY, int CVT>
+__global__ void __launch_bounds__((DownGeom<T, FS, Q, NX, NY>::THREADS), 2)
+    resample_down(const __grid_constant__ DownArgs a, const __grid_constant__ DownWeights<FS, Q> W)
+{
+    using G = DownGeom<T, FS, Q, NX, NY>;
+    using Word = typename G::Word;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+
+    if ((int)blockIdx.x >= a.interior_blocks) {
+        strip_block<T, 0, G::THREADS>(a.st, a.fr, blockIdx.x - a.interior_blocks);
+        return;
+    }
+    Word* tile = reinterpret_cast<Word*>(smem_raw); // [NROWP][D][SUB] (+pad): word (k, c) at k*RS + (c%D)*SUB + c/D
+    const int plane = blockIdx.x / a.tiles_per_plane;
+    const int tidx = blockIdx.x - plane * a.tiles_per_plane;
+    const int tile_y = tidx / a.tiles_x, tile_x = tidx - tile_y * a.tiles_x;
+    const PlanePtrs& pp = frame_ptrs(a.fr);
+    const T* __restrict__ src = static_cast<const T*>(pp.src[plane]);
+    T* __restrict__ dst = static_cast<T*>(pp.dst[plane]);
+    const int sp = (int)pp.src_pitch[plane];
+    const long long dp = pp.dst_pitch[plane];
+
+    const int ox0 = a.x0 + tile_x * DN_TW, oy0 = a.y0 + tile_y * G::TH; // first output of the tile
+    const int tsx = a.tsx0 + Q * (tile_x * DN_TW), tsy = a.tsy0 + Q * (tile_y * G::TH);
+
+    // ---- stage the tile: a warp takes whole row pairs, a lane the columns lane + 32 q.  All loads of KU row pairs are
+    //      issued before the first store so ~40 global loads per thread are in flight.
+    {
+        constexpr int NCOLS = G::D * G::SUB;
+        constexpr int CQ = (NCOLS + 31) / 32;
+        constexpr int KU = 2;
+        const int sh = CVT == DN_CVT_PRMT ? a.pre_shift : 0;
+        const int lane_ = threadIdx.x & 31, warp_ = threadIdx.x >> 5;
+        int gx[CQ];
+#pragma unroll
+        for (int q = 0; q < CQ; ++q)
+            gx[q] = min(max(tsx + lane_ + 32 * q, 0), a.src_w - 1); // clamped taps only feed masked outputs or zero weights
+        for (int k0 = warp_; k0 < G::NROWP; k0 += KU * G::WARPS) {
+            Word wv[KU][CQ];
+#pragma unroll
+            for (int u = 0; u < KU; ++u) {
+                const int k = min(k0 + u * G::WARPS, G::NROWP - 1);
+                const T* r0 = src + (long long)min(max(tsy + 2 * k, 0), a.src_h - 1) * sp;
+                const T* r1 = src + (long long)min(max(tsy + 2 * k + 1, 0), a.src_h - 1) * sp;
+#pragma unroll
+                for (int q = 0; q < CQ; ++q)
+                    down_pack(wv[u][q], r0 + gx[q], r1 + gx[q], sh);
+            }
+#pragma unroll
+            for (int u = 0; u < KU; ++u) {
+                const int k = k0 + u * G::WARPS;
+                if (k < G::NROWP) {
+#pragma unroll
+                    for (int q = 0; q < CQ; ++q) {
+                        const int c = lane_ + 32 * q;
+                        if (NCOLS % 32 == 0 || c < NCOLS)
+                            tile[k * G::RS + (c % G::D) * G::SUB + c / G::D] = wv[u][q];
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lx_ = lane % G::LX, ly_ = lane / G::LX;
+    const int row0 = (warp * G::LY + ly_) * NY; // first output row of this thread inside the tile
+    const Word* __restrict__ trow = tile + (size_t)(row0 * G::JSTEP) * G::RS + lx_;
+
+    float2 acc[NY][NX];
+#pragma unroll
+    for (int j = 0; j < NY; ++j)
+#pragma unroll
+        for (int i = 0; i < NX; ++i)
+            acc[j][i] = make_float2(0.f, 0.f);
+
+    constexpr int K_ALL0 = G::JSTEP * (NY - 1); // first row pair at which every output row is inside its window
+    int k = 0;
+#pragma unroll 1
+    for (; k < K_ALL0; ++k, trow += G::RS)
+        down_row_pair<G, FS, Q, NX, NY, CVT, false>(trow, k, W, acc);
+#pragma unroll 1
+    for (; k < G::NKW; ++k, trow += G::RS)
+        down_row_pair<G, FS, Q, NX, NY, CVT, true>(trow, k, W, acc);
+#pragma unroll 1
+    for (; k < G::NK; ++k, trow += G::RS)
+        down_row_pair<G, FS, Q, NX, NY, CVT, false>(trow, k, W, acc);
+
+    // ---- epilogue: NY rows x NX consecutive samples
+    const int ox = ox0 + NX * lx_;
+    if (ox >= a.x1)
+        return;
+#pragma unroll
+    for (int j = 0; j < NY; ++j) {
+        const int oy = oy0 + row0 + j;
+        if (oy >= a.y1)
+            break;
+        float v[NX];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+            if (CVT == DN_CVT_PRMT)
+                v[i] = ((acc[j][i].x - a.bias_even) + (acc[j][i].y - a.bias_odd)) * a.out_scale;
+            else
+                v[i] = acc[j][i].x + acc[j][i].y;
+        }
+        T* o = dst + (long long)oy * dp + ox;
+        if (ox + NX <= a.x1) {
+            store_run<T, NX>(o, v, a.fr.peak);
+        } else {
+#pragma unroll
+            for (int i = 0; i < NX; ++i)
+                if (ox + i < a.x1)
+                    o[i] = finish<T>(v[i], a.fr.peak);
+        }
+    }
+}
+
+template <typename T, int FS, int Q, int NX, int NY, int CVT>
+int launch_down_cfg(DownArgs& a, const DownWeights<FS, Q>& w, long long strip_blocks_of, int n_frames, cudaStream_t st,
+                    const Rect* rects, int n_rects)
+{
+    using G = DownGeom<T, FS, Q, NX, NY>;
+    const long long strip_blocks = strip_blocks_of ? set_strip_rects(a.st, rects, n_rects, G::THREADS) * a.fr.n_planes : 0;
+    a.tiles_x = (a.x1 - a.x0 + DN_TW - 1) / DN_TW;
+    a.tiles_per_plane = a.tiles_x * ((a.y1 - a.y0 + G::TH - 1) / G::TH);
+    if (a.interior_blocks)
+        a.interior_blocks = a.tiles_per_plane * a.fr.n_planes;
+    auto kern = resample_down<T, FS, Q, NX, NY, CVT>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
+    if (e != cudaSuccess)
+        return jinc_fail(JINC_E_CUDA, "cudaFuncSetAttribute(down smem %zu): %s", G::SMEM, cudaGetErrorString(e));
+    if (a.interior_blocks + strip_blocks == 0)
+        return 2;
+    dim3 grid((unsigned)(a.interior_blocks + strip_blocks), n_frames, 1);
+    kern<<<grid, G::THREADS, G::SMEM, st>>>(a, w);
+    e = cudaGetLastError();
+    if (e != cudaSuccess)
+        return jinc_fail(JINC_E_CUDA, "resample_down launch failed: %s", cudaGetErrorString(e));
+    return JINC_OK;
+}
+
+constexpr int DN_NX = 8, DN_NY = 2; // outputs per thread
+
+template <typename T, int FS, int Q>
+int launch_down_fs(const jinc_table* t, DownArgs& a, bool want_strips, int n_frames, cudaStream_t st, const Rect* rects, int n_rects)
+{
+    static_assert(sizeof(DownWeights<FS, Q>) + sizeof(DownArgs) < 32000, "kernel parameters exceed the 32 KB limit");
+    const DownPlan& d = t->down;
+    DownWeights<FS, Q> w;
+    memset(&w, 0, sizeof(w));
+    const float* blk = t->h_weights.data() + (size_t)d.wblock * FS * FS;
+    double sum_even = 0.0, sum_odd = 0.0;
+    for (int ly = 0; ly < FS; ++ly)
+        for (int lx = 0; lx < FS; ++lx) {
+            const float v = blk[ly * FS + lx];
+            float2& e = w.w[ly >> 1][lx % Q][lx / Q];
+            if (ly & 1) {
+                e.y = v;
+                sum_odd += v;
+            } else {
+                e.x = v;
+                sum_even += v;
+            }
+        }
+    if constexpr (sizeof(T) == 4) {
+        return launch_down_cfg<T, FS, Q, DN_NX, DN_NY, DN_CVT_FLOAT>(a, w, want_strips, n_frames, st, rects, n_rects);
+    } else {
+        const int bits = t_bits_from_peak(a.fr.peak);
+        if (bits <= 15) {
+            // f = 0.5 + (x << pre_shift) / 65536  =>  sum(w f) = 0.5 sum(w) + sum(w x) * 2^(pre_shift - 16)
+            a.pre_shift = 15 - bits;
+            a.bias_even = (float)(0.5 * sum_even);
+            a.bias_odd = (float)(0.5 * sum_odd);
+            a.out_scale = (float)(1 << (16 - a.pre_shift));
+            return launch_down_cfg<T, FS, Q, DN_NX, DN_NY, DN_CVT_PRMT>(a, w, want_strips, n_frames, st, rects, n_rects);
+        }
+        if constexpr (sizeof(T) == 2)
+            return launch_down_cfg<T, FS, Q, DN_NX, DN_NY, DN_CVT_I2F>(a, w, want_strips, n_frames, st, rects, n_rects);
+        return 1;
+    }
+}
+
+// 0 launched, 2 nothing to do, 1 unsupported geometry, <0 error
+template <typename T>
+int launch_down(const jinc_table* t, DownArgs& a, bool want_strips, int n_frames, cudaStream_t st, const Rect* rects, int n_rects)
+{
+    const int key = t->down.qx * 1000 + t->sc.fs;
+    switch (key) {
+#define JINC_DOWN_CASE(Q_, FS_) \
+    case Q_ * 1000 + FS_: return launch_down_fs<T, FS_, Q_>(t, a, want_strips, n_frames, st, rects, n_rects);
+        JINC_DOWN_CASE(2, 13) // tap 3, 1/2
+        JINC_DOWN_CASE(2, 17) // tap 4, 1/2
+        JINC_DOWN_CASE(2, 25) // tap 6, 1/2
+        JINC_DOWN_CASE(2, 33) // tap 8, 1/2
+        JINC_DOWN_CASE(4, 26) // tap 3, 1/4
+        JINC_DOWN_CASE(4, 34) // tap 4, 1/4
+        JINC_DOWN_CASE(4, 50) // tap 6, 1/4
+#undef JINC_DOWN_CASE
+    default: return 1;
+    }
+}
+
+bool down_supported(const jinc_table* t)
+{
+    if (!t->down.ok || t->down.qx != t->down.qy)
+        return false;
+    switch (t->down.qx * 1000 + t->sc.fs) {
+    case 2013: case 2017: case 2025: case 2033: case 4026: case 4034: case 4050: return true;
+    default: return false;
+    }
+}
+
 // ------------------------------------------------------------------------------------------ launcher
 
 template <typename T>
@@ -562,6 +939,38 @@ int launch_typed(const jinc_table* t, const FrameSet& fr, int n_frames, int y_be
                     ++*launches;
                 return rc;
             }
+        }
+    }
+    if (t->fast_path == JINC_PATH_DOWN_INT && down_supported(t)) {
+        const DownPlan& d = t->down;
+        const int fy0 = std::max(y_begin, d.y0), fy1 = std::min(y_end, d.y0 + d.ny);
+        if (fy1 > fy0) {
+            if (parts & JINC_PART_BORDER) {
+                rects[n_rects++] = Rect{0, y_begin, W, fy0};
+                rects[n_rects++] = Rect{0, fy1, W, y_end};
+                rects[n_rects++] = Rect{0, fy0, t->ix0, fy1};
+                rects[n_rects++] = Rect{t->ix1, fy0, W, fy1};
+            }
+            DownArgs a;
+            memset(&a, 0, sizeof(a));
+            a.fr = fr;
+            a.st = sa;
+            a.src_w = t->sc.src_w;
+            a.src_h = t->sc.src_h;
+            a.x0 = d.x0;
+            a.x1 = d.x0 + d.nx;
+            a.y0 = fy0;
+            a.y1 = fy1;
+            a.tsx0 = d.sx0;
+            a.tsy0 = d.sy0 + d.qy * (fy0 - d.y0);
+            a.interior_blocks = (parts & JINC_PART_INTERIOR) ? 1 : 0; // resolved to the tile count by the launcher
+            const int rc = launch_down<T>(t, a, n_rects > 0, n_frames, st, rects, n_rects);
+            if (rc != 1) {
+                if (rc == 0)
+                    ++*launches;
+                return rc == 2 ? JINC_OK : rc;
+            }
+            n_rects = 0;
         }
     }
     if (!(parts & JINC_PART_BORDER))

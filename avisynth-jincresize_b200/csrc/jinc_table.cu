@@ -17,6 +17,7 @@
 #include <climits>
 #include <cmath>
 #include <cstring>
+#include <unordered_map>
 
 #include "jinc_internal.h"
 #include "jinc_weights.cuh"
@@ -216,6 +217,23 @@ __global__ void __launch_bounds__(256) border_sum_kernel(BorderSumArgs a)
             *w = __fdiv_rn(jinc_lut_weight(a.lut, __dadd_rn(dx2, dy2), a.radius2, a.idx_scale), sum); // :505-514
             w += 32;
         }
+    }
+}
+
+// Weight block of one border class, from its representative pixel: factor / divider (:488-514), row-major taps.
+__global__ void __launch_bounds__(128) border_class_kernel(BorderSumArgs a, const int2* __restrict__ reps, float* __restrict__ out)
+{
+    const int2 r = reps[blockIdx.x];
+    const float px = a.pos_x[r.x], py = a.pos_y[r.y];
+    const int sx = a.start_x[r.x], sy = a.start_y[r.y];
+    const float sum = a.sums[jinc_border_slot(a.g, r.x, r.y)];
+    const int taps = a.fs * a.fs;
+    float* w = out + (size_t)blockIdx.x * taps;
+    for (int t = threadIdx.x; t < taps; t += blockDim.x) {
+        const int ly = t / a.fs, lx = t - ly * a.fs;
+        const double dy2 = jinc_tap_dist2(py, a.src_h, sy + ly, a.step_y);
+        const double dx2 = jinc_tap_dist2(px, a.src_w, sx + lx, a.step_x);
+        w[t] = __fdiv_rn(jinc_lut_weight(a.lut, __dadd_rn(dx2, dy2), a.radius2, a.idx_scale), sum);
     }
 }
 
@@ -450,21 +468,86 @@ int jinc_table_build_device(jinc_table* t, const double* lut)
         if (g.total > 0) {
             if (int rc = dev_alloc(&t->d_border_sum, (size_t)g.total))
                 return rc;
-            // Per-pixel border weights are frame-invariant: keep them resident (what the reference's table holds on the
-            // host) unless they would not fit the budget, in which case the resample kernel rebuilds them per frame.
-            const size_t bw_bytes = (size_t)((g.total + 31) / 32 * 32) * s.fs * s.fs * sizeof(float);
+            // Border weights are frame-invariant: keep them resident (what the reference's table holds on the host).
+            // First try to fold the border pixels into classes of identical blocks.  A tap's distance is
+            // fl(c - (start + l)) with c the clamped position (:485-486); c - start is exactly representable
+            // (0 <= c - start <= c, a multiple of ulp(c)), so two pixels whose c - start agree on an axis have the same
+            // distances on that axis, hence -- when both axes agree -- the same factors, divider and weights.
+            std::vector<int32_t> cls[2];
+            for (int k = 0; k < 2; ++k) {
+                const int n = k == 0 ? s.dst_w : s.dst_h;
+                const float hi = static_cast<float>((k == 0 ? s.src_w : s.src_h) - 1);
+                std::unordered_map<uint32_t, int32_t> ids;
+                cls[k].resize(n);
+                for (int i = 0; i < n; ++i) {
+                    float c = t->h_pos[k][i] > hi ? hi : t->h_pos[k][i];
+                    c = c < 0.f ? 0.f : c;
+                    const float delta = c - static_cast<float>(t->h_start[k][i]);
+                    uint32_t bits;
+                    memcpy(&bits, &delta, sizeof(bits));
+                    cls[k][i] = ids.emplace(bits, static_cast<int32_t>(ids.size())).first->second;
+                }
+            }
+            std::vector<int32_t> block_of(static_cast<size_t>(g.total));
+            std::vector<int2> reps;
+            {
+                std::unordered_map<uint64_t, int32_t> blocks;
+                auto visit = [&](int x, int y) {
+                    const uint64_t key = (static_cast<uint64_t>(static_cast<uint32_t>(cls[1][y])) << 32) | static_cast<uint32_t>(cls[0][x]);
+                    auto it = blocks.find(key);
+                    if (it == blocks.end()) {
+                        it = blocks.emplace(key, static_cast<int32_t>(reps.size())).first;
+                        reps.push_back(make_int2(x, y));
+                    }
+                    block_of[static_cast<size_t>(jinc_border_slot(g, x, y))] = it->second;
+                };
+                for (int y = 0; y < g.H; ++y) {
+                    if (y < g.by0 || y >= g.by1) {
+                        for (int x = 0; x < g.W; ++x)
+                            visit(x, y);
+                    } else {
+                        for (int x = 0; x < g.bx0; ++x)
+                            visit(x, y);
+                        for (int x = g.bx1; x < g.W; ++x)
+                            visit(x, y);
+                    }
+                }
+            }
+            const size_t taps_n = static_cast<size_t>(s.fs) * s.fs;
+            const bool use_classes = reps.size() * 4 <= static_cast<size_t>(g.total) && reps.size() * taps_n * sizeof(float) <= ((size_t)256 << 20);
             size_t free_b = 0, total_b = 0;
             cudaMemGetInfo(&free_b, &total_b);
-            if (bw_bytes <= kBorderWeightBudget && bw_bytes < free_b / 4) {
-                if (cudaMalloc(reinterpret_cast<void**>(&t->d_border_w), bw_bytes) != cudaSuccess) {
-                    cudaGetLastError();
-                    t->d_border_w = nullptr;
+            if (!use_classes) {
+                const size_t bw_bytes = (size_t)((g.total + 31) / 32 * 32) * taps_n * sizeof(float);
+                if (bw_bytes <= kBorderWeightBudget && bw_bytes < free_b / 4) {
+                    if (cudaMalloc(reinterpret_cast<void**>(&t->d_border_w), bw_bytes) != cudaSuccess) {
+                        cudaGetLastError();
+                        t->d_border_w = nullptr;
+                    }
                 }
             }
             BorderSumArgs ba{g, t->ax[0].pos, t->ax[1].pos, t->ax[0].start, t->ax[1].start, t->d_lut, t->d_border_sum,
                              t->d_border_w, s.fs, s.src_w, s.src_h, s.filt_step[0], s.filt_step[1], s.radius2, s.idx_scale};
             border_sum_kernel<<<(unsigned)((g.total + 255) / 256), 256, 0, st>>>(ba);
             JINC_CUDA(cudaGetLastError());
+            if (use_classes) {
+                int2* d_reps = nullptr;
+                if (int rc = dev_alloc(&d_reps, reps.size()))
+                    return rc;
+                int rc = dev_alloc(&t->d_border_block, static_cast<size_t>(g.total));
+                rc = rc ? rc : dev_alloc(&t->d_border_wb, reps.size() * taps_n);
+                if (rc) {
+                    cudaFree(d_reps);
+                    return rc;
+                }
+                t->n_border_blocks = static_cast<int>(reps.size());
+                JINC_CUDA(cudaMemcpyAsync(d_reps, reps.data(), reps.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
+                JINC_CUDA(cudaMemcpyAsync(t->d_border_block, block_of.data(), block_of.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+                border_class_kernel<<<(unsigned)reps.size(), 128, 0, st>>>(ba, d_reps, t->d_border_wb);
+                JINC_CUDA(cudaGetLastError());
+                JINC_CUDA(cudaStreamSynchronize(st)); // reps / block_of are host temporaries
+                cudaFree(d_reps);
+            }
         }
     }
     plan_fast_paths(t);
@@ -534,6 +617,8 @@ extern "C" void jinc_table_destroy(jinc_table* t)
     cudaFree(t->d_weights);
     cudaFree(t->d_border_sum);
     cudaFree(t->d_border_w);
+    cudaFree(t->d_border_block);
+    cudaFree(t->d_border_wb);
     delete t;
 }
 

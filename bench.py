@@ -301,13 +301,13 @@ def run_b200(args, cfg):
             e0 = torch.cuda.Event(enable_timing=True)
             e1 = torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            flt.process_device_batch(frames_arr, 0, 1, 3, sh_)
+            flt.process_device_batch(frames_arr, 0, 1, args.parts, sh_)
             e1.record(stream)
             pairs.append((e0, e1))
         else:
-            flt.process_device_batch(frames_arr, 0, 1, 3, sh_)
+            flt.process_device_batch(frames_arr, 0, 1, args.parts, sh_)
         if n_tables > 1:
-            flt.process_device_batch(frames_arr, 0, 2, 3, sh_)
+            flt.process_device_batch(frames_arr, 0, 2, args.parts, sh_)
 
     def barrier():
         torch.cuda.synchronize()
@@ -394,7 +394,7 @@ def run_b200(args, cfg):
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": cfg["name"], "config_id": args.config, "frames_per_step": F,
-                       "sample_type": f"{fmt.family}{fmt.bits}", "filter_size": fs_l,
+                       "sample_type": f"{fmt.family}{fmt.bits}", "filter_size": fs_l, **({"parts": args.parts, "INVALID": "diagnostic run, part of the frame skipped"} if args.parts != 3 else {}),
                        "l2": "inputs larger than L2: every step walks %d distinct frames (%.0f MB of planes)" % (F, F * byts / 1e6),
                        "partition": "frame-parallel, one process per GPU, no collective"},
             "e2e": {"value": e2e_value, "unit": "Mpixel/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -403,7 +403,7 @@ def run_b200(args, cfg):
                     "pcie_gbs": (h2d + d2h) * args.steps / e2e_s / 1e9},
             "gpu_launches": gpu_launches,
             "clocks": clocks,
-            "roofline": {"bound": "fp32_fma", "kernel": ("resample_up2x" if i0.fast_path == 1 else "resample_strips") + " (luma-table planes of all %d frames: interior tiles + border strips)" % F,
+            "roofline": {"bound": "fp32_fma", "kernel": {1: "resample_up2x", 2: "resample_down"}.get(i0.fast_path, "resample_strips") + " (luma-table planes of all %d frames: interior tiles + border strips)" % F,
                          "achieved": achieved_tf, "peak": fma_peak, "unit": "TFLOP/s", "frac": achieved_tf / fma_peak,
                          "peak_source": fma_how, "traffic": None, "launch_ms": dom_avg_ms,
                          "algorithmic_flop_per_launch": dom_flop, "share_of_step": sum(dom_ms) / ms_total},
@@ -428,6 +428,8 @@ def main():
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--parts", type=int, default=3, choices=[1, 2, 3],
+                    help="diagnosis only: 1 = interior tiles, 2 = border strips, 3 = both (the only valid bench setting)")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     rank = int(os.environ.get("RANK", "0"))

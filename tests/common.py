@@ -70,6 +70,17 @@ SMALL_CASES = [
     ("yuva420_14bit_2x", ah.Format("yuva420", 14), 128, 72, 256, 144, dict(tap=3, cplace="topleft")),
     ("f32_444_3x_tap16", ah.Format("444", 32), 96, 64, 288, 192, dict(tap=16)),
     ("same_size_shift", ah.Format("y", 16), 160, 90, 160, 90, dict(tap=3, src_left=0.37, src_top=-0.21)),
+    # integer-ratio downscales (polyphase kernel): every instantiated (ratio, filter size) and sample type
+    ("half_tap3_yv12", ah.YV12, 640, 360, 320, 180, dict(tap=3)),
+    ("half_tap4_f32_444", ah.Format("444", 32), 288, 160, 144, 80, dict(tap=4)),
+    ("half_tap6_y16", ah.Format("y", 16), 400, 240, 200, 120, dict(tap=6)),
+    ("half_tap8_rgbp10", ah.Format("rgbp", 10), 320, 200, 160, 100, dict(tap=8, blur=1.1)),
+    ("quarter_tap3_y8", ah.Format("y", 8), 800, 480, 200, 120, dict(tap=3)),
+    ("quarter_tap4_422p12", ah.Format("422", 12), 1024, 512, 256, 128, dict(tap=4)),
+    ("quarter_tap6_f32_y", ah.Format("y", 32), 640, 400, 160, 100, dict(tap=6)),
+    # exact 2x with the remaining alias taps and a third-size / 3x ratio (general kernel)
+    ("up2x_tap6_420p8", ah.YUV420P8, 200, 120, 400, 240, dict(tap=6, cplace="mpeg1")),
+    ("third_tap3_y8", ah.Format("y", 8), 600, 360, 200, 120, dict(tap=3)),
 ]
 
 

@@ -2,5 +2,8 @@
 TAG=${1:-quick}; shift
 CFGS=${@:-2}
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q --maxfail=10 --tb=short -p no:cacheprovider 2>&1 | tail -15 | tee gpurun_out/${TAG}_pytest_gpu.log
-for c in $CFGS; do timeout 600 python bench.py --config $c --steps 10 --warmup 3 --no-cpu 2>&1 | tail -1 | tee gpurun_out/${TAG}_bench_config$c.json; done
+timeout 900 python -m pytest tests -m gpu -q --maxfail=10 --tb=short -p no:cacheprovider 2>&1 | tail -25 | tee gpurun_out/${TAG}_pytest_gpu.log
+for c in $CFGS; do
+  timeout 600 python bench.py --config $c --steps 10 --warmup 3 --no-cpu 2>&1 | tail -1 | tee gpurun_out/${TAG}_bench_config$c.json
+  for p in 1 2; do timeout 600 python bench.py --config $c --steps 10 --warmup 3 --no-cpu --parts $p 2>&1 | tail -1 | tee gpurun_out/${TAG}_bench_config${c}_parts$p.json; done
+done
