@@ -95,7 +95,7 @@ struct jinc_table {
     // Border pixels whose clamped position sits at the same offset from its window origin on both axes have identical
     // weight blocks; when that folds the border into few classes the blocks are kept once, [block][fs*fs], plus a map
     int32_t* d_border_block = nullptr; // [bgeom.total] slot -> class block (null: per-slot weights above)
-    float* d_border_wb = nullptr;      // [n_border_blocks][fs*fs]
+    float* d_border_wb = nullptr;      // [n_border_blocks][fs][fsp], fsp = fs rounded up to 4 (16-byte rows, pad = 0)
     int n_border_blocks = 0;
     // host mirrors of the small per-axis arrays (for planning and introspection)
     std::vector<int32_t> h_start[2], h_phase[2], h_rank[2], h_qint[2];

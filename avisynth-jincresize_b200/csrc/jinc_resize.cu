@@ -61,10 +61,27 @@ __device__ __forceinline__ uint16_t finish<uint16_t>(float v, float peak)
     return (uint16_t)finish_u16(v, peak);
 }
 
+// Integer samples become floats without the (quarter-rate) I2F: drop the bits into the mantissa of 2^23 and subtract
+// 2^23 again -- exact for any value below 2^23.
 template <typename T>
 __device__ __forceinline__ float load_sample(const T* p)
 {
-    return (float)__ldg(p);
+    return __uint_as_float(0x4B000000u | (uint32_t)__ldg(p)) - 8388608.f;
+}
+template <>
+__device__ __forceinline__ float load_sample<float>(const float* p)
+{
+    return __ldg(p);
+}
+template <typename T>
+__device__ __forceinline__ float sample_to_float(T v)
+{
+    return __uint_as_float(0x4B000000u | (uint32_t)v) - 8388608.f;
+}
+template <>
+__device__ __forceinline__ float sample_to_float<float>(float v)
+{
+    return v;
 }
 
 template <typename T>
@@ -118,7 +135,7 @@ struct PlanePtrs {
     long long dst_pitch[JINC_MAX_PLANES];
 };
 
-// strips: up to four rectangles of output samples, enumerated row-major rect after rect, 256 per block
+// strips: up to four rectangles of output samples, each cut into patches of PW x PH outputs; one block per patch
 struct StripArgs {
     const int32_t* start_x;
     const int32_t* start_y;
@@ -131,13 +148,16 @@ struct StripArgs {
     const float* border_sum;
     const float* border_w; // resident per-pixel border weights [slot/32][tap][slot%32], or null
     const int32_t* border_block; // slot -> class block, or null
-    const float* border_wb;      // [block][tap] class blocks
+    const float* border_wb;      // [block][fs][fsp] class blocks, fsp = fs rounded up to 4
     BorderGeom bg;
     int fs, n_rank_x, src_w, src_h;
     double step_x, step_y, radius2, idx_scale;
     Rect rect[4];
-    unsigned count_begin[5]; // prefix sums of samples per rect
-    unsigned blocks_per_plane; // 256-sample blocks covering count_begin[4]; the grid holds this many per plane
+    unsigned patch_begin[5];   // prefix sums of patches per rect
+    unsigned patches_x[4];     // patches per row of patches
+    int pw_log2[4];            // log2 of the patch width (patch height = outputs per block / width)
+    unsigned blocks_per_plane; // = patch_begin[4]; the grid holds this many strip blocks per plane
+    unsigned smem_floats;      // shared memory a strip block may use to stage its source footprint (0: none)
 };
 
 struct FrameSet {
@@ -152,20 +172,106 @@ __device__ __forceinline__ const PlanePtrs& frame_ptrs(const FrameSet& fs)
     return fs.frames ? fs.frames[blockIdx.y] : fs.one;
 }
 
+// Window rows as aligned 32-bit words (the plane base and pitch are 4-byte aligned), converted later: the words are
+// funnel-shifted into place and every sample is dropped into the mantissa of 2^23 by one byte permute.
+template <typename T, int FS>
+struct RowWords {
+    static constexpr int SB = (int)sizeof(T);
+    static constexpr int NA = (FS * SB + 3) / 4;      // aligned words that hold the row
+    static constexpr int NW = SB == 4 ? FS : NA + 1;  // words loaded (one more when the row starts inside a word)
+    // rows whose loads are issued together (the strips are latency-bound: most sample rows miss L2), about 24 registers
+    static constexpr int GROUP = (24 / NW) < 1 ? 1 : ((24 / NW) > FS ? FS : (24 / NW));
+};
+
+template <typename T, int FS>
+__device__ __forceinline__ void load_row_words(const T* __restrict__ s, uint32_t (&w)[RowWords<T, FS>::NW])
+{
+    using R = RowWords<T, FS>;
+    if constexpr (R::SB == 4) {
+#pragma unroll
+        for (int i = 0; i < FS; ++i)
+            w[i] = __ldg(reinterpret_cast<const uint32_t*>(s) + i);
+    } else {
+        const uintptr_t addr = reinterpret_cast<uintptr_t>(s);
+        const uint32_t* __restrict__ p4 = reinterpret_cast<const uint32_t*>(addr & ~(uintptr_t)3);
+#pragma unroll
+        for (int j = 0; j < R::NA; ++j)
+            w[j] = __ldg(p4 + j);
+        w[R::NA] = ((unsigned)(addr & 3) + FS * R::SB > 4 * R::NA) ? __ldg(p4 + R::NA) : 0u; // never touch a word the row does not reach
+    }
+}
+
+template <typename T, int FS>
+__device__ __forceinline__ void row_words_to_float(const uint32_t (&w)[RowWords<T, FS>::NW], unsigned off, float (&v)[FS])
+{
+    using R = RowWords<T, FS>;
+    if constexpr (R::SB == 4) {
+#pragma unroll
+        for (int i = 0; i < FS; ++i)
+            v[i] = __uint_as_float(w[i]);
+    } else {
+        uint32_t al[R::NA];
+#pragma unroll
+        for (int j = 0; j < R::NA; ++j)
+            al[j] = __funnelshift_r(w[j], w[j + 1], off * 8);
+#pragma unroll
+        for (int i = 0; i < FS; ++i) {
+            uint32_t bits;
+            if (R::SB == 1)
+                bits = __byte_perm(al[i >> 2], 0x4B000000u, 0x7440 | (i & 3));
+            else
+                bits = __byte_perm(al[i >> 1], 0x4B000000u, (i & 1) ? 0x7432 : 0x7410);
+            v[i] = __uint_as_float(bits) - 8388608.f;
+        }
+    }
+}
+
+// sum over an FS x FS window with a weight block whose rows are padded to 16 bytes
+template <typename T, int FS>
+__device__ __forceinline__ float dot_rows_vec(const T* __restrict__ s, int pitch, const float* __restrict__ w)
+{
+    using R = RowWords<T, FS>;
+    constexpr int FSP = (FS + 3) & ~3;
+    const unsigned off = (unsigned)(reinterpret_cast<uintptr_t>(s) & 3); // the pitch keeps it the same on every row
+    float acc = 0.f;
+#pragma unroll 1
+    for (int ly0 = 0; ly0 < FS; ly0 += R::GROUP) {
+        uint32_t words[R::GROUP][R::NW];
+#pragma unroll
+        for (int g = 0; g < R::GROUP; ++g) {
+            const int ly = min(ly0 + g, FS - 1); // the last group may be short: re-read the last row, skipped below
+            load_row_words<T, FS>(s + (long long)ly * pitch, words[g]);
+        }
+#pragma unroll
+        for (int g = 0; g < R::GROUP; ++g) {
+            if (FS % R::GROUP != 0 && ly0 + g >= FS)
+                break;
+            float wr[FSP], v[FS];
+            const float4* __restrict__ w4 = reinterpret_cast<const float4*>(w + (ly0 + g) * FSP);
+#pragma unroll
+            for (int q = 0; q < FSP / 4; ++q) {
+                const float4 t = __ldg(w4 + q);
+                wr[4 * q] = t.x;
+                wr[4 * q + 1] = t.y;
+                wr[4 * q + 2] = t.z;
+                wr[4 * q + 3] = t.w;
+            }
+            row_words_to_float<T, FS>(words[g], off, v);
+#pragma unroll
+            for (int lx = 0; lx < FS; ++lx)
+                acc = fmaf(v[lx], wr[lx], acc);
+        }
+    }
+    return acc;
+}
+
 constexpr int STRIP_THREADS = 256;
 
-// One output sample of a strip for ONE plane.  Lean on purpose: 32-bit indexing, constant weight strides, so a tap
-// costs LDG(weight) + LDG(sample) + convert + FFMA.  FSC > 0 fixes the window size at compile time (inner loops unroll).
+// One output sample of a strip for ONE plane, read straight from global memory.  Lean on purpose: 32-bit indexing,
+// constant weight strides.  FSC > 0 fixes the window size at compile time (inner loops unroll).
 template <typename T, int FSC>
-__device__ __forceinline__ void strip_sample(const StripArgs& a, const FrameSet& fsx, unsigned g, int plane)
+__device__ __forceinline__ void strip_sample(const StripArgs& a, const FrameSet& fsx, int x, int y, int plane)
 {
-    const int r = (int)(g >= a.count_begin[1]) + (int)(g >= a.count_begin[2]) + (int)(g >= a.count_begin[3]);
-    const unsigned li = g - a.count_begin[r];
-    const unsigned rw = (unsigned)(a.rect[r].x1 - a.rect[r].x0);
-    const unsigned rrow = li / rw;
-    const int x = a.rect[r].x0 + (int)(li - rrow * rw);
-    const int y = a.rect[r].y0 + (int)rrow;
-
     const PlanePtrs& pp = frame_ptrs(fsx);
     const int fs = FSC > 0 ? FSC : a.fs;
     const int sx = a.start_x[x], sy = a.start_y[y];
@@ -175,10 +281,24 @@ __device__ __forceinline__ void strip_sample(const StripArgs& a, const FrameSet&
     float acc = 0.f;
 
     const bool shared_block = rx >= 0 && ry >= 0;
-    if (shared_block || a.border_block) {
-        // shared phase block (:431-435), or the block of this border pixel's class; row-major fs x fs
-        const float* __restrict__ w = shared_block ? a.weights + (unsigned)(ry * a.n_rank_x + rx) * (unsigned)(fs * fs)
-                                                   : a.border_wb + (size_t)a.border_block[jinc_border_slot(a.bg, x, y)] * (unsigned)(fs * fs);
+    if (!shared_block && a.border_block) {
+        // the block of this border pixel's class, rows padded to 16 bytes
+        const int fsp = (fs + 3) & ~3;
+        const float* __restrict__ w = a.border_wb + (size_t)a.border_block[jinc_border_slot(a.bg, x, y)] * (unsigned)(fs * fsp);
+        if (FSC > 0 && ((reinterpret_cast<uintptr_t>(pp.src[plane]) | (uintptr_t)(pitch * (int)sizeof(T))) & 3) == 0) {
+            acc = dot_rows_vec<T, (FSC > 0 ? FSC : 4)>(s, pitch, w);
+        } else {
+            for (int ly = 0; ly < fs; ++ly) {
+#pragma unroll
+                for (int lx = 0; lx < (FSC > 0 ? FSC : fs); ++lx)
+                    acc = fmaf(load_sample(s + lx), __ldg(w + lx), acc);
+                w += fsp;
+                s += pitch;
+            }
+        }
+    } else if (shared_block) {
+        // shared phase block (:431-435), row-major fs x fs
+        const float* __restrict__ w = a.weights + (unsigned)(ry * a.n_rank_x + rx) * (unsigned)(fs * fs);
         for (int ly = 0; ly < fs; ++ly) {
 #pragma unroll
             for (int lx = 0; lx < (FSC > 0 ? FSC : fs); ++lx)
@@ -216,14 +336,213 @@ __device__ __forceinline__ void strip_sample(const StripArgs& a, const FrameSet&
     static_cast<T*>(pp.dst[plane])[(long long)y * pp.dst_pitch[plane] + x] = finish<T>(acc, fsx.peak);
 }
 
-// strip block `sb` of the grid: planes are the slow dimension.  THREADS = block size of the launching kernel
-template <typename T, int FSC, int THREADS = STRIP_THREADS>
-__device__ __forceinline__ void strip_block(const StripArgs& a, const FrameSet& fsx, unsigned sb)
+// What a strip sample needs besides its source window: gathered for all of a thread's samples before any is used, so
+// the table loads of the SPT samples are in flight together.
+struct StripMeta {
+    int x, y;       // output sample (x < 0: none)
+    int sx, sy;     // window origin
+    const float* w; // weight block: [fs][wstride]
+    int wstride;    // fs for a shared phase block, fs rounded up to 4 for a border class block; 0 = neither (slow kinds)
+};
+
+template <int FSC>
+__device__ __forceinline__ StripMeta strip_meta(const StripArgs& a, int x, int y)
 {
+    const int fs = FSC > 0 ? FSC : a.fs;
+    StripMeta m;
+    m.x = x;
+    m.y = y;
+    m.sx = a.start_x[x];
+    m.sy = a.start_y[y];
+    const bool border = x < a.bg.bx0 || x >= a.bg.bx1 || y < a.bg.by0 || y >= a.bg.by1; // no table load needed to know
+    if (!border) {
+        m.w = a.weights + (unsigned)(a.rank_y[y] * a.n_rank_x + a.rank_x[x]) * (unsigned)(fs * fs);
+        m.wstride = fs;
+    } else if (a.border_block) {
+        const int fsp = (fs + 3) & ~3;
+        m.w = a.border_wb + (size_t)a.border_block[jinc_border_slot(a.bg, x, y)] * (unsigned)(fs * fsp);
+        m.wstride = fsp;
+    } else {
+        m.w = nullptr;
+        m.wstride = 0;
+    }
+    return m;
+}
+
+// One sample from a staged footprint: `tile` holds the source rectangle [sy_lo, ..) x [sx_lo, sx_lo + fw) as floats.
+template <typename T, int FSC>
+__device__ __forceinline__ void strip_sample_staged(const StripArgs& a, const FrameSet& fsx, const StripMeta& m, int plane,
+                                                    const float* __restrict__ tile, int fw, int sx_lo, int sy_lo)
+{
+    const int fs = FSC > 0 ? FSC : a.fs;
+    const float* __restrict__ s = tile + (m.sy - sy_lo) * fw + (m.sx - sx_lo);
+    float acc = 0.f;
+    if (m.wstride == fs) {
+        const float* __restrict__ w = m.w;
+        for (int ly = 0; ly < fs; ++ly) {
+#pragma unroll
+            for (int lx = 0; lx < (FSC > 0 ? FSC : fs); ++lx)
+                acc = fmaf(s[lx], __ldg(w + lx), acc);
+            w += fs;
+            s += fw;
+        }
+    } else {
+        const float4* __restrict__ w4 = reinterpret_cast<const float4*>(m.w); // rows padded to 16 bytes
+        for (int ly = 0; ly < fs; ++ly) {
+#pragma unroll
+            for (int q = 0; q < (FSC > 0 ? (FSC + 3) / 4 : m.wstride / 4); ++q) {
+                const float4 t = __ldg(w4 + q);
+                const int lx = 4 * q;
+                acc = fmaf(s[lx], t.x, acc);
+                if (lx + 1 < fs)
+                    acc = fmaf(s[lx + 1], t.y, acc);
+                if (lx + 2 < fs)
+                    acc = fmaf(s[lx + 2], t.z, acc);
+                if (lx + 3 < fs)
+                    acc = fmaf(s[lx + 3], t.w, acc);
+            }
+            w4 += m.wstride / 4;
+            s += fw;
+        }
+    }
+    const PlanePtrs& pp = frame_ptrs(fsx);
+    static_cast<T*>(pp.dst[plane])[(long long)m.y * pp.dst_pitch[plane] + m.x] = finish<T>(acc, fsx.peak);
+}
+
+// SPT samples of one thread that share ONE class block (the usual case in the strips of the periodic geometries: a
+// thread's samples lie in the same border row or column, a multiple of the phase period apart): the weights are loaded
+// once and feed SPT independent accumulators.
+template <typename T, int FSC, int SPT>
+__device__ __forceinline__ void strip_samples_fused(const StripArgs& a, const FrameSet& fsx, const StripMeta (&m)[SPT], int plane,
+                                                    const float* __restrict__ tile, int fw, int sx_lo, int sy_lo)
+{
+    const int fs = FSC > 0 ? FSC : a.fs;
+    const float* __restrict__ s[SPT];
+    float acc[SPT];
+#pragma unroll
+    for (int k = 0; k < SPT; ++k) {
+        s[k] = tile + (m[k].sy - sy_lo) * fw + (m[k].sx - sx_lo);
+        acc[k] = 0.f;
+    }
+    const float4* __restrict__ w4 = reinterpret_cast<const float4*>(m[0].w); // rows padded to 16 bytes
+    const int wq = m[0].wstride / 4;
+    for (int ly = 0; ly < fs; ++ly) {
+#pragma unroll
+        for (int q = 0; q < (FSC > 0 ? (FSC + 3) / 4 : wq); ++q) {
+            const float4 t = __ldg(w4 + q);
+            const int lx = 4 * q;
+#pragma unroll
+            for (int k = 0; k < SPT; ++k) {
+                acc[k] = fmaf(s[k][lx], t.x, acc[k]);
+                if (lx + 1 < fs)
+                    acc[k] = fmaf(s[k][lx + 1], t.y, acc[k]);
+                if (lx + 2 < fs)
+                    acc[k] = fmaf(s[k][lx + 2], t.z, acc[k]);
+                if (lx + 3 < fs)
+                    acc[k] = fmaf(s[k][lx + 3], t.w, acc[k]);
+            }
+        }
+        w4 += wq;
+#pragma unroll
+        for (int k = 0; k < SPT; ++k)
+            s[k] += fw;
+    }
+    const PlanePtrs& pp = frame_ptrs(fsx);
+    T* __restrict__ dst = static_cast<T*>(pp.dst[plane]);
+    const long long dp = pp.dst_pitch[plane];
+#pragma unroll
+    for (int k = 0; k < SPT; ++k)
+        dst[(long long)m[k].y * dp + m[k].x] = finish<T>(acc[k], fsx.peak);
+}
+
+// Strip block `sb` of the grid (planes are the slow dimension): one patch of PW x PH outputs, SPT per thread.  The
+// source rectangle the patch reads (window origins are monotonic along both axes) is staged into shared memory as
+// floats when it fits, so the global loads are coalesced, converted once and every window row is read from shared
+// memory; otherwise every sample reads global memory directly.
+template <typename T, int FSC, int THREADS = STRIP_THREADS, int SPT = 1>
+__device__ __forceinline__ void strip_block(const StripArgs& a, const FrameSet& fsx, unsigned sb, float* __restrict__ tile)
+{
+    const int fs = FSC > 0 ? FSC : a.fs;
     const unsigned plane = sb / a.blocks_per_plane;
-    const unsigned g = (sb - plane * a.blocks_per_plane) * THREADS + threadIdx.x;
-    if (g < a.count_begin[4])
-        strip_sample<T, FSC>(a, fsx, g, (int)plane);
+    const unsigned pid = sb - plane * a.blocks_per_plane;
+    const int r = (int)(pid >= a.patch_begin[1]) + (int)(pid >= a.patch_begin[2]) + (int)(pid >= a.patch_begin[3]);
+    const unsigned lp = pid - a.patch_begin[r];
+    const unsigned pyi = lp / a.patches_x[r], pxi = lp - pyi * a.patches_x[r];
+    const int pwl = a.pw_log2[r];
+    const int ox0 = a.rect[r].x0 + (int)(pxi << pwl), oy0 = a.rect[r].y0 + (int)pyi * ((THREADS * SPT) >> pwl);
+    const int nx = min(1 << pwl, a.rect[r].x1 - ox0), ny = min((THREADS * SPT) >> pwl, a.rect[r].y1 - oy0);
+
+    // footprint corners and the tables of this thread's samples: one round of loads
+    const int sx_lo = a.start_x[ox0], sy_lo = a.start_y[oy0];
+    const int fw = a.start_x[ox0 + nx - 1] + fs - sx_lo, fh = a.start_y[oy0 + ny - 1] + fs - sy_lo;
+    StripMeta meta[SPT];
+#pragma unroll
+    for (int k = 0; k < SPT; ++k) {
+        const int o = (int)threadIdx.x + k * THREADS;
+        const int lx = o & ((1 << pwl) - 1), ly = o >> pwl;
+        if (lx < nx && ly < ny) {
+            meta[k] = strip_meta<FSC>(a, ox0 + lx, oy0 + ly);
+        } else {
+            meta[k].x = -1;
+            meta[k].wstride = 0;
+        }
+    }
+    const unsigned n = (unsigned)(fw * fh);
+    const bool staged = tile != nullptr && n <= a.smem_floats; // the same for the whole block
+    if (staged) {
+        const PlanePtrs& pp = frame_ptrs(fsx);
+        const int pitch = (int)pp.src_pitch[plane];
+        const T* __restrict__ src = static_cast<const T*>(pp.src[plane]) + (long long)sy_lo * pitch + sx_lo;
+        const float inv_fw = 1.f / (float)fw;
+        for (unsigned e0 = threadIdx.x; e0 < n; e0 += 4 * THREADS) {
+            T v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { // all four loads are issued before the first conversion
+                const unsigned e = min(e0 + u * THREADS, n - 1);
+                unsigned row = (unsigned)__float2int_rd(((float)e + 0.5f) * inv_fw);
+                row -= (row * (unsigned)fw > e);
+                row += ((row + 1) * (unsigned)fw <= e);
+                v[u] = __ldg(src + (long long)row * pitch + (e - row * (unsigned)fw));
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (e0 + u * THREADS < n)
+                    tile[e0 + u * THREADS] = sample_to_float(v[u]);
+        }
+        __syncthreads();
+    }
+    if (SPT > 1 && staged) {
+        bool same = true;
+        const int fsp = (fs + 3) & ~3;
+#pragma unroll
+        for (int k = 0; k < SPT; ++k)
+            same = same && meta[k].x >= 0 && meta[k].w == meta[0].w && meta[k].wstride == fsp;
+        if (same) {
+            strip_samples_fused<T, FSC, SPT>(a, fsx, meta, (int)plane, tile, fw, sx_lo, sy_lo);
+            return;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < SPT; ++k) {
+        if (meta[k].x < 0)
+            continue;
+        if (staged && meta[k].wstride)
+            strip_sample_staged<T, FSC>(a, fsx, meta[k], (int)plane, tile, fw, sx_lo, sy_lo);
+        else
+            strip_sample<T, FSC>(a, fsx, meta[k].x, meta[k].y, (int)plane);
+    }
+}
+
+// Role of block b in a merged grid of `interior` tile blocks and `strips` strip blocks: the strip blocks are spread
+// evenly through the grid (their latency-bound work then hides under the FMA-bound tiles sharing the SM) instead of
+// trailing it.  Returns true for a strip block and its index in `id`, else the tile index.
+__device__ __forceinline__ bool block_role(unsigned b, unsigned interior, unsigned strips, unsigned& id)
+{
+    const unsigned long long total = (unsigned long long)interior + strips;
+    const unsigned s0 = (unsigned)((unsigned long long)b * strips / total);
+    const unsigned s1 = (unsigned)((unsigned long long)(b + 1) * strips / total);
+    id = s1 > s0 ? s0 : b - s0;
+    return s1 > s0;
 }
 
 struct GeneralArgs {
@@ -231,10 +550,15 @@ struct GeneralArgs {
     StripArgs st;
 };
 
+constexpr int GEN_SPT = 4;                  // outputs per thread of the general kernel
+constexpr int GEN_MAX_PW = 64;              // its patches are 64 x 16 outputs
+constexpr size_t GEN_SMEM = (size_t)96 << 10; // staging space (two blocks per SM)
+
 template <typename T>
 __global__ void __launch_bounds__(STRIP_THREADS) resample_strips(const __grid_constant__ GeneralArgs a)
 {
-    strip_block<T, 0>(a.st, a.fr, blockIdx.x);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    strip_block<T, 0, STRIP_THREADS, GEN_SPT>(a.st, a.fr, blockIdx.x, reinterpret_cast<float*>(smem_raw));
 }
 
 // weights of one output pixel exactly as the reference defines them (introspection for parity tests)
@@ -246,6 +570,14 @@ __global__ void pixel_weights_kernel(StripArgs a, int x, int y, float* out)
         const float* w = a.weights + (size_t)(ry * a.n_rank_x + rx) * fs * fs;
         for (int t = threadIdx.x; t < fs * fs; t += blockDim.x)
             out[t] = w[t];
+        return;
+    }
+    if (a.border_block) {
+        // what the resample kernels apply: the block of this border pixel's class
+        const int fsp = (fs + 3) & ~3;
+        const float* w = a.border_wb + (size_t)a.border_block[jinc_border_slot(a.bg, x, y)] * (unsigned)(fs * fsp);
+        for (int t = threadIdx.x; t < fs * fs; t += blockDim.x)
+            out[t] = w[(t / fs) * fsp + t % fs];
         return;
     }
     const int sx = a.start_x[x], sy = a.start_y[y];
@@ -285,27 +617,38 @@ void fill_strip_args(const jinc_table* t, StripArgs& a)
     a.idx_scale = t->sc.idx_scale;
 }
 
-// returns the number of `threads`-sample blocks per plane
-long long set_strip_rects(StripArgs& a, const Rect* rects, int n_rects, int threads = STRIP_THREADS)
+// Cuts the rectangles into patches of `outputs` samples (one strip block each), at most `max_pw` wide; returns the
+// number of strip blocks per plane.
+long long set_strip_rects(StripArgs& a, const Rect* rects, int n_rects, int outputs, int max_pw, size_t smem_bytes)
 {
     unsigned total = 0;
     int k = 0;
+    max_pw = std::min(max_pw, outputs);
     for (int r = 0; r < n_rects; ++r) {
         const long long w = rects[r].x1 - rects[r].x0, h = rects[r].y1 - rects[r].y0;
         if (w <= 0 || h <= 0)
             continue;
+        int pwl = 3; // patches are at least 8 wide
+        while ((1 << pwl) < w && (1 << pwl) < max_pw)
+            ++pwl;
+        const long long pw = 1ll << pwl, ph = outputs / pw;
         a.rect[k] = rects[r];
-        a.count_begin[k] = total;
-        total += (unsigned)(w * h);
+        a.pw_log2[k] = pwl;
+        a.patches_x[k] = (unsigned)((w + pw - 1) / pw);
+        a.patch_begin[k] = total;
+        total += a.patches_x[k] * (unsigned)((h + ph - 1) / ph);
         ++k;
     }
     for (int j = k; j < 4; ++j) {
         a.rect[j] = Rect{0, 0, 1, 1};
-        a.count_begin[j] = total;
+        a.pw_log2[j] = 3;
+        a.patches_x[j] = 1;
+        a.patch_begin[j] = total;
     }
-    a.count_begin[4] = total;
-    a.blocks_per_plane = (total + threads - 1) / threads;
-    return a.blocks_per_plane;
+    a.patch_begin[4] = total;
+    a.blocks_per_plane = total;
+    a.smem_floats = (unsigned)(smem_bytes / sizeof(float));
+    return total;
 }
 
 // ------------------------------------------------------------------------------------------ exact-2x kernel
@@ -316,7 +659,8 @@ constexpr int UP_THREADS = UP_WARPS * 32;
 constexpr int UP_CW = 32 * UP_TX;            // cells per tile row (128 -> 256 output samples)
 constexpr int UP_RPW = 2;                    // cell-row pairs per warp
 constexpr int UP_CH = 2 * UP_WARPS * UP_RPW; // cell rows per tile (32 -> 64 output rows)
-static_assert(UP_THREADS == STRIP_THREADS, "both roles share one block size");
+constexpr int UP_STRIP_SPT = 4;              // strip role: outputs per thread (patches of 1024 outputs, up to 256 wide)
+constexpr int UP_STRIP_MAX_PW = 1024;            // a thread's four samples share a border row: x, x + 256, ...
 
 template <int FS>
 struct UpGeom {
@@ -342,6 +686,7 @@ struct UpArgs {
     int sx0, sy0;         // window origin of cell (0,0), phase (0,0)
     int cy_begin, cy_end; // cell rows to produce (row-band split)
     int tiles_x, tiles_per_plane, interior_blocks; // interior_blocks = tiles_per_plane * n_planes
+    int strip_blocks;
 };
 
 template <typename T, int FS, int OX1, int OY1>
@@ -351,16 +696,17 @@ __global__ void __launch_bounds__(UP_THREADS, (FS >= 13 ? 2 : 3))
     using G = UpGeom<FS>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
 
-    if ((int)blockIdx.x >= a.interior_blocks) {
+    unsigned role_id;
+    if (block_role(blockIdx.x, a.interior_blocks, a.strip_blocks, role_id)) {
         // ---------------- strip role
-        strip_block<T, FS>(a.st, a.fr, blockIdx.x - a.interior_blocks);
+        strip_block<T, FS, UP_THREADS, UP_STRIP_SPT>(a.st, a.fr, role_id, reinterpret_cast<float*>(smem_raw));
         return;
     }
 
     // -------------------- interior tile role
     float2* tile = reinterpret_cast<float2*>(smem_raw); // [NR][4][SUB] pairs {S[r][c], S[r+1][c]}
-    const int plane = blockIdx.x / a.tiles_per_plane;
-    const int tidx = blockIdx.x - plane * a.tiles_per_plane;
+    const int plane = role_id / a.tiles_per_plane;
+    const int tidx = role_id - plane * a.tiles_per_plane;
     const int tile_y = tidx / a.tiles_x, tile_x = tidx - tile_y * a.tiles_x;
     const PlanePtrs& pp = frame_ptrs(a.fr);
     const T* __restrict__ src = static_cast<const T*>(pp.src[plane]);
@@ -506,6 +852,7 @@ int launch_up2x_fs(const jinc_table* t, UpArgs& a, long long strip_blocks, int n
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
     if (e != cudaSuccess)
         return jinc_fail(JINC_E_CUDA, "cudaFuncSetAttribute(up2x smem %zu): %s", G::SMEM, cudaGetErrorString(e));
+    a.strip_blocks = (int)strip_blocks;
     dim3 grid((unsigned)(a.interior_blocks + strip_blocks), n_frames, 1);
     kern<<<grid, UP_THREADS, G::SMEM, st>>>(a, w);
     e = cudaGetLastError();
@@ -527,6 +874,17 @@ int launch_up2x(const jinc_table* t, UpArgs& a, long long strip_blocks, int n_fr
 }
 
 bool up2x_supported(int fs) { return fs == 7 || fs == 9 || fs == 13 || fs == 17; }
+
+size_t up2x_smem_bytes(int fs)
+{
+    switch (fs) {
+    case 7: return UpGeom<7>::SMEM;
+    case 9: return UpGeom<9>::SMEM;
+    case 13: return UpGeom<13>::SMEM;
+    case 17: return UpGeom<17>::SMEM;
+    default: return 0;
+    }
+}
 
 // ------------------------------------------------------------------------------------------ integer-ratio downscale kernel
 //
@@ -550,6 +908,9 @@ bool up2x_supported(int fs) { return fs == 7 || fs == 9 || fs == 13 || fs == 17;
 // Columns are de-interleaved by c mod (Q*NX) so a warp's loads are bank-conflict free.
 constexpr int DN_TW = 64;  // output columns per tile
 constexpr int DN_TH = 32;  // output rows per tile (integer formats; float tiles are half as tall)
+
+constexpr int DN_STRIP_SPT = 2;    // strip role: outputs per thread, patches at most 64 wide (the windows are wide)
+constexpr int DN_STRIP_MAX_PW = 256;
 
 enum { DN_CVT_I2F = 0, DN_CVT_PRMT = 1, DN_CVT_FLOAT = 2 };
 
@@ -600,7 +961,7 @@ struct DownArgs {
     int src_w, src_h;
     int x0, y0, x1, y1;  // output rectangle produced by the tiles (y0..y1 already cut to the row band)
     int tsx0, tsy0;      // window origin of output (x0, y0)
-    int tiles_x, tiles_per_plane, interior_blocks;
+    int tiles_x, tiles_per_plane, interior_blocks, strip_blocks;
     int pre_shift;       // PRMT conversion: samples are staged as x << pre_shift
     float bias_even, bias_odd, out_scale; // PRMT conversion: out = ((acc.x - bias_even) + (acc.y - bias_odd)) * out_scale
 };
@@ -685,13 +1046,14 @@ __global__ void __launch_bounds__((DownGeom<T, FS, Q, NX, NY>::THREADS), 2)
     using Word = typename G::Word;
     extern __shared__ __align__(16) unsigned char smem_raw[];
 
-    if ((int)blockIdx.x >= a.interior_blocks) {
-        strip_block<T, 0, G::THREADS>(a.st, a.fr, blockIdx.x - a.interior_blocks);
+    unsigned role_id;
+    if (block_role(blockIdx.x, a.interior_blocks, a.strip_blocks, role_id)) {
+        strip_block<T, FS, G::THREADS, DN_STRIP_SPT>(a.st, a.fr, role_id, reinterpret_cast<float*>(smem_raw));
         return;
     }
     Word* tile = reinterpret_cast<Word*>(smem_raw); // [NROWP][D][SUB] (+pad): word (k, c) at k*RS + (c%D)*SUB + c/D
-    const int plane = blockIdx.x / a.tiles_per_plane;
-    const int tidx = blockIdx.x - plane * a.tiles_per_plane;
+    const int plane = role_id / a.tiles_per_plane;
+    const int tidx = role_id - plane * a.tiles_per_plane;
     const int tile_y = tidx / a.tiles_x, tile_x = tidx - tile_y * a.tiles_x;
     const PlanePtrs& pp = frame_ptrs(a.fr);
     const T* __restrict__ src = static_cast<const T*>(pp.src[plane]);
@@ -799,7 +1161,8 @@ int launch_down_cfg(DownArgs& a, const DownWeights<FS, Q>& w, long long strip_bl
                     const Rect* rects, int n_rects)
 {
     using G = DownGeom<T, FS, Q, NX, NY>;
-    const long long strip_blocks = strip_blocks_of ? set_strip_rects(a.st, rects, n_rects, G::THREADS) * a.fr.n_planes : 0;
+    const long long strip_blocks =
+        strip_blocks_of ? set_strip_rects(a.st, rects, n_rects, G::THREADS * DN_STRIP_SPT, DN_STRIP_MAX_PW, G::SMEM) * a.fr.n_planes : 0;
     a.tiles_x = (a.x1 - a.x0 + DN_TW - 1) / DN_TW;
     a.tiles_per_plane = a.tiles_x * ((a.y1 - a.y0 + G::TH - 1) / G::TH);
     if (a.interior_blocks)
@@ -810,6 +1173,7 @@ int launch_down_cfg(DownArgs& a, const DownWeights<FS, Q>& w, long long strip_bl
         return jinc_fail(JINC_E_CUDA, "cudaFuncSetAttribute(down smem %zu): %s", G::SMEM, cudaGetErrorString(e));
     if (a.interior_blocks + strip_blocks == 0)
         return 2;
+    a.strip_blocks = (int)strip_blocks;
     dim3 grid((unsigned)(a.interior_blocks + strip_blocks), n_frames, 1);
     kern<<<grid, G::THREADS, G::SMEM, st>>>(a, w);
     e = cudaGetLastError();
@@ -918,7 +1282,8 @@ int launch_typed(const jinc_table* t, const FrameSet& fr, int n_frames, int y_be
             memset(&a, 0, sizeof(a));
             a.fr = fr;
             a.st = sa;
-            const long long strip_blocks = set_strip_rects(a.st, rects, n_rects) * fr.n_planes;
+            const long long strip_blocks =
+                set_strip_rects(a.st, rects, n_rects, UP_THREADS * UP_STRIP_SPT, UP_STRIP_MAX_PW, up2x_smem_bytes(t->sc.fs)) * fr.n_planes;
             a.src_w = t->sc.src_w;
             a.src_h = t->sc.src_h;
             a.x0 = u.x0;
@@ -980,11 +1345,14 @@ int launch_typed(const jinc_table* t, const FrameSet& fr, int n_frames, int y_be
     ga.fr = fr;
     ga.st = sa;
     rects[0] = Rect{0, y_begin, W, y_end};
-    const long long blocks = set_strip_rects(ga.st, rects, 1) * fr.n_planes;
+    const long long blocks = set_strip_rects(ga.st, rects, 1, STRIP_THREADS * GEN_SPT, GEN_MAX_PW, GEN_SMEM) * fr.n_planes;
     if (blocks == 0)
         return JINC_OK;
-    resample_strips<T><<<dim3((unsigned)blocks, n_frames), STRIP_THREADS, 0, st>>>(ga);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = cudaFuncSetAttribute(resample_strips<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEN_SMEM);
+    if (e != cudaSuccess)
+        return jinc_fail(JINC_E_CUDA, "cudaFuncSetAttribute(strips smem): %s", cudaGetErrorString(e));
+    resample_strips<T><<<dim3((unsigned)blocks, n_frames), STRIP_THREADS, GEN_SMEM, st>>>(ga);
+    e = cudaGetLastError();
     if (e != cudaSuccess)
         return jinc_fail(JINC_E_CUDA, "resample_strips launch failed: %s", cudaGetErrorString(e));
     ++*launches;

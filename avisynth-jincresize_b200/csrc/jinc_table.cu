@@ -227,13 +227,13 @@ __global__ void __launch_bounds__(128) border_class_kernel(BorderSumArgs a, cons
     const float px = a.pos_x[r.x], py = a.pos_y[r.y];
     const int sx = a.start_x[r.x], sy = a.start_y[r.y];
     const float sum = a.sums[jinc_border_slot(a.g, r.x, r.y)];
-    const int taps = a.fs * a.fs;
-    float* w = out + (size_t)blockIdx.x * taps;
-    for (int t = threadIdx.x; t < taps; t += blockDim.x) {
+    const int fsp = (a.fs + 3) & ~3; // rows padded to 16 bytes (the pad stays 0 from the memset)
+    float* w = out + (size_t)blockIdx.x * a.fs * fsp;
+    for (int t = threadIdx.x; t < a.fs * a.fs; t += blockDim.x) {
         const int ly = t / a.fs, lx = t - ly * a.fs;
         const double dy2 = jinc_tap_dist2(py, a.src_h, sy + ly, a.step_y);
         const double dx2 = jinc_tap_dist2(px, a.src_w, sx + lx, a.step_x);
-        w[t] = __fdiv_rn(jinc_lut_weight(a.lut, __dadd_rn(dx2, dy2), a.radius2, a.idx_scale), sum);
+        w[ly * fsp + lx] = __fdiv_rn(jinc_lut_weight(a.lut, __dadd_rn(dx2, dy2), a.radius2, a.idx_scale), sum);
     }
 }
 
@@ -535,12 +535,14 @@ int jinc_table_build_device(jinc_table* t, const double* lut)
                 if (int rc = dev_alloc(&d_reps, reps.size()))
                     return rc;
                 int rc = dev_alloc(&t->d_border_block, static_cast<size_t>(g.total));
-                rc = rc ? rc : dev_alloc(&t->d_border_wb, reps.size() * taps_n);
+                const size_t wb_floats = reps.size() * s.fs * static_cast<size_t>((s.fs + 3) & ~3);
+                rc = rc ? rc : dev_alloc(&t->d_border_wb, wb_floats);
                 if (rc) {
                     cudaFree(d_reps);
                     return rc;
                 }
                 t->n_border_blocks = static_cast<int>(reps.size());
+                JINC_CUDA(cudaMemsetAsync(t->d_border_wb, 0, wb_floats * sizeof(float), st));
                 JINC_CUDA(cudaMemcpyAsync(d_reps, reps.data(), reps.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
                 JINC_CUDA(cudaMemcpyAsync(t->d_border_block, block_of.data(), block_of.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
                 border_class_kernel<<<(unsigned)reps.size(), 128, 0, st>>>(ba, d_reps, t->d_border_wb);

@@ -56,6 +56,9 @@ def test_table_matches_reference_table(capi, case):
         pts = [(0, 0), (W - 1, 0), (0, H - 1), (W - 1, H - 1), (W // 2, 0), (0, H // 2), (W // 2, H // 2),
                (W // 2 + 1, H // 2), (W // 2, H // 2 + 1), (W // 3, H - 2), (W - 2, H // 3)]
         pts += [(int(x), int(y)) for x, y in zip(xs[:12], ys[:12])]
+        # border strips, where pixels are folded into classes of identical blocks: walk along every edge
+        pts += [(int(x), y) for x in rng.integers(0, W, 10) for y in (0, 1, 2, H - 3, H - 2, H - 1)]
+        pts += [(x, int(y)) for y in rng.integers(0, H, 10) for x in (0, 1, 2, W - 3, W - 2, W - 1)]
         for x, y in pts:
             got = tv.pixel_weights(x, y)
             ref = ot.block(y, x)
