@@ -658,6 +658,25 @@ extern "C" int jinc_filter_wait(jinc_filter* f, int64_t ticket)
     return rc;
 }
 
+extern "C" int jinc_plan_frame_owner(int64_t frame, int n_parts)
+{
+    if (n_parts < 1 || frame < 0)
+        return jinc_fail(JINC_E_INVALID, "jinc_plan_frame_owner: bad argument");
+    return static_cast<int>(frame % n_parts);
+}
+
+extern "C" int jinc_plan_row_bands(int target_h, int n_parts, int32_t* y_begin, int32_t* y_end)
+{
+    if (target_h < 1 || n_parts < 1 || !y_begin || !y_end)
+        return jinc_fail(JINC_E_INVALID, "jinc_plan_row_bands: bad argument");
+    const int band = static_cast<int>(align_up(static_cast<size_t>((target_h + n_parts - 1) / n_parts), 16));
+    for (int i = 0; i < n_parts; ++i) {
+        y_begin[i] = std::min(target_h, i * band);
+        y_end[i] = std::min(target_h, (i + 1) * band);
+    }
+    return JINC_OK;
+}
+
 extern "C" int jinc_filter_process_split(jinc_filter* f, const jinc_frame* frame)
 {
     if (int rc = check_frame(f, frame))
@@ -687,15 +706,13 @@ extern "C" int jinc_filter_process_split(jinc_filter* f, const jinc_frame* frame
         for (Slot* s : held)
             s->busy = true;
     }
-    const int H = f->p.target_h;
-    const int band = static_cast<int>(align_up(static_cast<size_t>((H + nd - 1) / nd), 16));
-    int rc = JINC_OK;
+    std::vector<int32_t> yb(nd), ye(nd);
+    int rc = jinc_plan_row_bands(f->p.target_h, nd, yb.data(), ye.data());
     std::vector<std::pair<int, int>> ranges(nd);
     for (int di = 0; di < nd; ++di) {
-        const int y0 = std::min(H, di * band), y1 = std::min(H, (di + 1) * band);
-        ranges[di] = {y0, y1};
-        if (y1 > y0 && rc == JINC_OK)
-            rc = enqueue_frame(f, held[di], frame, y0, y1, false);
+        ranges[di] = {yb[di], ye[di]};
+        if (ye[di] > yb[di] && rc == JINC_OK)
+            rc = enqueue_frame(f, held[di], frame, yb[di], ye[di], false);
     }
     for (int di = 0; di < nd; ++di) {
         if (ranges[di].second > ranges[di].first) {

@@ -58,6 +58,7 @@ EXPORTS = [
     "jinc_filter_destroy", "jinc_filter_table", "jinc_filter_num_tables", "jinc_filter_num_devices",
     "jinc_filter_process", "jinc_filter_submit", "jinc_filter_wait", "jinc_filter_process_split",
     "jinc_filter_kernel_launches", "jinc_filter_process_device", "jinc_filter_process_device_batch",
+    "jinc_plan_frame_owner", "jinc_plan_row_bands",
 ]
 
 _lib = None
@@ -104,6 +105,9 @@ def lib():
         L.jinc_filter_process_device_batch.restype = ci
         L.jinc_filter_process_device_batch.argtypes = [vp, ci, C.POINTER(Frame), ci, ci, ci, vp]
         L.jinc_filter_kernel_launches.restype, L.jinc_filter_kernel_launches.argtypes = C.c_int64, [vp]
+        L.jinc_plan_frame_owner.restype, L.jinc_plan_frame_owner.argtypes = ci, [C.c_int64, ci]
+        L.jinc_plan_row_bands.restype = ci
+        L.jinc_plan_row_bands.argtypes = [ci, ci, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         _lib = L
     return _lib
 
@@ -115,6 +119,27 @@ def _check(rc: int):
 
 def device_count() -> int:
     return lib().jinc_device_count()
+
+
+def frame_owner(frame: int, n_parts: int) -> int:
+    """Part (GPU of a filter, or rank of a multi-process job) that frame `frame` belongs to.  Host-only."""
+    r = lib().jinc_plan_frame_owner(frame, n_parts)
+    if r < 0:
+        _check(r)
+    return r
+
+
+def frames_of(part: int, n_parts: int, n_frames: int) -> list[int]:
+    """Frames of a clip of n_frames that part `part` processes (frame-parallel partition, no exchange)."""
+    return [n for n in range(n_frames) if frame_owner(n, n_parts) == part]
+
+
+def row_bands(target_h: int, n_parts: int) -> list[tuple[int, int]]:
+    """Output-row bands [y0, y1) of the row-band split of one frame over n_parts GPUs.  Host-only."""
+    y0 = (C.c_int32 * n_parts)()
+    y1 = (C.c_int32 * n_parts)()
+    _check(lib().jinc_plan_row_bands(target_h, n_parts, y0, y1))
+    return [(int(a), int(b)) for a, b in zip(y0, y1)]
 
 
 def radius_for_tap(tap: int) -> float:

@@ -54,6 +54,13 @@ CONFIGS = {
             fn="Jinc256Resize", kw=dict(), tap=8, frames=2),
     5: dict(name="7680x4320 YUV420P10 -> 1920x1080 JincResize tap=6 blur=0.9", fmt=ah.YUV420P10, w=7680, h=4320,
             tw=1920, th=1080, fn="JincResize", kw=dict(tap=6, blur=0.9), tap=6, frames=4),
+    # not BASELINE configs: the "next" row of SURVEY.md 8(f), ratios that are not exact 2x / 1/n (general kernel)
+    6: dict(name="1280x720 YUV420P8 -> 1920x1080 Jinc36Resize (1.5x, general path)", fmt=ah.YUV420P8, w=1280, h=720, tw=1920,
+            th=1080, fn="Jinc36Resize", kw=dict(), tap=3, frames=48),
+    7: dict(name="1920x1080 YUV420P8 -> 1280x720 Jinc36Resize (2/3 downscale, general path)", fmt=ah.YUV420P8, w=1920, h=1080,
+            tw=1280, th=720, fn="Jinc36Resize", kw=dict(), tap=3, frames=48),
+    8: dict(name="1920x1080 YUV444P16 -> 2500x1400 Jinc64Resize (irregular ratio, many phases)", fmt=ah.YUV444P16, w=1920, h=1080,
+            tw=2500, th=1400, fn="Jinc64Resize", kw=dict(), tap=4, frames=12),
 }
 
 

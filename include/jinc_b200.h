@@ -167,6 +167,15 @@ JINC_API int jinc_filter_process(jinc_filter* f, const jinc_frame* frame);
  * until that frame's dst planes are complete.  src/dst memory must stay valid until wait returns. */
 JINC_API int jinc_filter_submit(jinc_filter* f, const jinc_frame* frame, int64_t* ticket);
 JINC_API int jinc_filter_wait(jinc_filter* f, int64_t ticket);
+/* The partition rules, host-only (usable without a GPU; multi-process drivers use the same rules across ranks):
+ *   frames  -- frame n of a clip belongs to part n % n_parts (what jinc_filter_submit's round-robin does);
+ *   bands   -- one frame is cut into n_parts bands of output rows, each a multiple of 16 luma rows (whole cell pairs
+ *              for luma and for 4:2:0 chroma) except the last; parts beyond the frame get empty bands.
+ * Replaces the reference's row-parallel loop (src/JincResize.cpp:594-599) and AviSynth's per-thread frame hand-out for
+ * this MT_MULTI_INSTANCE filter (:649-652) as the unit of parallelism. */
+JINC_API int jinc_plan_frame_owner(int64_t frame, int n_parts);
+JINC_API int jinc_plan_row_bands(int target_h, int n_parts, int32_t* y_begin, int32_t* y_end);
+
 /* Row-band split of ONE frame across all of the filter's GPUs (each GPU gets a band of output rows plus
  * the source rows its windows reach; no GPU<->GPU traffic). */
 JINC_API int jinc_filter_process_split(jinc_filter* f, const jinc_frame* frame);
