@@ -1,0 +1,766 @@
+// jinc_resample.cuh -- device code and argument blocks shared by the resample translation units.
+//
+// Replaces JincResize::resize_plane_c<T,thr,subsampled> (src/JincResize.cpp:536-601) and the three SIMD copies of
+// its inner loop.  Every output sample is  sum_{ly,lx} src[start_y+ly][start_x+lx] * w[ly][lx]  over an fs x fs
+// window, followed for integer formats by clamp to [0,peak] and round-half-even (:581-582); float is raw (:583-584).
+//
+// One launch covers ALL planes that share a coefficient table, for a whole BATCH of frames, interior and border
+// together; blocks take one of two roles:
+//
+//   interior tile (exact 2x upscale, every "JincNNResize(2w,2h)" use)
+//       The table has 2x2 phase classes.  A thread owns TX=4 source-aligned cells x 2 cell rows = 8x4 output samples in
+//       16 float2 accumulators.  The source tile lives in shared memory as VERTICAL PAIRS {S[r][c], S[r+1][c]} so one
+//       packed FFMA2 (fma.rn.f32x2, new on sm_100) updates the same phase of two cell rows with a single scalar
+//       weight.  Weights arrive as kernel parameters (constant bank) and reach the FMA pipe through uniform registers
+//       (LDCU -> FFMA2 R, R, UR, R): weights cost no shared-memory or register-file bandwidth.  Pair columns are
+//       de-interleaved by (c & 3) so a warp's LDS.64 is bank-conflict free.
+//   strip chunk (256 output samples of the border strips, or of the whole plane when the table has no fast path)
+//       One thread per output sample, all planes of the table in one pass.  Samples whose window was clamped get the
+//       reference's per-pixel weights on the fly: exact LUT index per tap, divided by the per-pixel normaliser that
+//       the table build stored (:443-514); other samples gather their shared phase block from the L2-resident table.
+//
+// The kernels are split over several translation units (one per sample type and kernel family) so that the build
+// runs in parallel; everything here is a template, inline, or a plain struct.
+#ifndef JINC_RESAMPLE_CUH
+#define JINC_RESAMPLE_CUH
+
+#include <algorithm>
+#include <cstring>
+#include <type_traits>
+
+#include "jinc_internal.h"
+#include "jinc_weights.cuh"
+
+namespace jinc_rs {
+
+// ------------------------------------------------------------------------------------------ sample conversion
+
+// clamp to [0, peak] and round half to even (lrintf) in one saturating convert; NaN -> 0
+// (8-bit planes always have peak = 255, which the saturating convert already enforces)
+__device__ __forceinline__ uint32_t finish_u8(float v, float)
+{
+    uint32_t r;
+    asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ uint32_t finish_u16(float v, float peak)
+{
+    uint32_t r;
+    asm("cvt.rni.sat.u16.f32 %0, %1;" : "=r"(r) : "f"(fminf(v, peak)));
+    return r;
+}
+// full-range 16-bit: saturation is the clamp
+__device__ __forceinline__ uint32_t finish_u16_full(float v)
+{
+    uint32_t r;
+    asm("cvt.rni.sat.u16.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return r;
+}
+
+template <typename T>
+__device__ __forceinline__ T finish(float v, float peak);
+template <>
+__device__ __forceinline__ float finish<float>(float v, float)
+{
+    return v;
+}
+template <>
+__device__ __forceinline__ uint8_t finish<uint8_t>(float v, float peak)
+{
+    return (uint8_t)finish_u8(v, peak);
+}
+template <>
+__device__ __forceinline__ uint16_t finish<uint16_t>(float v, float peak)
+{
+    return (uint16_t)finish_u16(v, peak);
+}
+
+// Integer samples become floats without the (quarter-rate) I2F: drop the bits into the mantissa of 2^23 and subtract
+// 2^23 again -- exact for any value below 2^23.
+template <typename T>
+__device__ __forceinline__ float load_sample(const T* p)
+{
+    return __uint_as_float(0x4B000000u | (uint32_t)__ldg(p)) - 8388608.f;
+}
+template <>
+__device__ __forceinline__ float load_sample<float>(const float* p)
+{
+    return __ldg(p);
+}
+template <typename T>
+__device__ __forceinline__ float sample_to_float(T v)
+{
+    return __uint_as_float(0x4B000000u | (uint32_t)v) - 8388608.f;
+}
+template <>
+__device__ __forceinline__ float sample_to_float<float>(float v)
+{
+    return v;
+}
+
+template <typename T>
+__device__ __forceinline__ void store8(T* p, const float (&v)[8], float peak);
+template <>
+__device__ __forceinline__ void store8<float>(float* p, const float (&v)[8], float)
+{
+    reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+template <>
+__device__ __forceinline__ void store8<uint16_t>(uint16_t* p, const float (&v)[8], float peak)
+{
+    uint32_t q[4];
+    if (peak >= 65535.f) { // uniform: 16-bit clips need no separate upper clamp
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            q[k] = finish_u16_full(v[2 * k]) | (finish_u16_full(v[2 * k + 1]) << 16);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            q[k] = finish_u16(v[2 * k], peak) | (finish_u16(v[2 * k + 1], peak) << 16);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(q[0], q[1], q[2], q[3]);
+}
+template <>
+__device__ __forceinline__ void store8<uint8_t>(uint8_t* p, const float (&v)[8], float peak)
+{
+    uint32_t q[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+        q[k] = finish_u8(v[4 * k], peak) | (finish_u8(v[4 * k + 1], peak) << 8) | (finish_u8(v[4 * k + 2], peak) << 16) |
+               (finish_u8(v[4 * k + 3], peak) << 24);
+    *reinterpret_cast<uint2*>(p) = make_uint2(q[0], q[1]);
+}
+
+// ------------------------------------------------------------------------------------------ shared argument blocks
+
+struct Rect {
+    int x0, y0, x1, y1;
+};
+
+// bits per component back from peak = (1 << bits) - 1
+inline int t_bits_from_peak(float peak)
+{
+    int bits = 0;
+    while (bits < 32 && (float)((1ll << bits) - 1) < peak)
+        ++bits;
+    return bits;
+}
+
+// planes of ONE frame that share the table being run (device pointers, pitches in elements)
+struct PlanePtrs {
+    const void* src[JINC_MAX_PLANES];
+    void* dst[JINC_MAX_PLANES];
+    long long src_pitch[JINC_MAX_PLANES];
+    long long dst_pitch[JINC_MAX_PLANES];
+};
+
+// strips: up to four rectangles of output samples, each cut into patches of PW x PH outputs; one block per patch
+struct StripArgs {
+    const int32_t* start_x;
+    const int32_t* start_y;
+    const int32_t* rank_x;
+    const int32_t* rank_y;
+    const float* pos_x;
+    const float* pos_y;
+    const float* weights;
+    const float* lut;
+    const float* border_sum;
+    const float* border_w; // resident per-pixel border weights [slot/32][tap][slot%32], or null
+    const int32_t* border_block; // slot -> class block, or null
+    const float* border_wb;      // [block][fs][fsp] class blocks, fsp = fs rounded up to 4
+    BorderGeom bg;
+    int fs, n_rank_x, src_w, src_h;
+    double step_x, step_y, radius2, idx_scale;
+    Rect rect[4];
+    unsigned patch_begin[5];   // prefix sums of patches per rect
+    unsigned patches_x[4];     // patches per row of patches
+    int pw_log2[4];            // log2 of the patch width (patch height = outputs per block / width)
+    unsigned blocks_per_plane; // = patch_begin[4]; the grid holds this many strip blocks per plane
+    unsigned smem_floats;      // shared memory a strip block may use to stage its source footprint (0: none)
+};
+
+struct FrameSet {
+    PlanePtrs one;           // used when frames == nullptr
+    const PlanePtrs* frames; // device array [grid.y] for batched launches
+    int n_planes;
+    float peak;
+};
+
+__device__ __forceinline__ const PlanePtrs& frame_ptrs(const FrameSet& fs)
+{
+    return fs.frames ? fs.frames[blockIdx.y] : fs.one;
+}
+
+// Window rows as aligned 32-bit words (the plane base and pitch are 4-byte aligned), converted later: the words are
+// funnel-shifted into place and every sample is dropped into the mantissa of 2^23 by one byte permute.
+template <typename T, int FS>
+struct RowWords {
+    static constexpr int SB = (int)sizeof(T);
+    static constexpr int NA = (FS * SB + 3) / 4;      // aligned words that hold the row
+    static constexpr int NW = SB == 4 ? FS : NA + 1;  // words loaded (one more when the row starts inside a word)
+    // rows whose loads are issued together (the strips are latency-bound: most sample rows miss L2), about 24 registers
+    static constexpr int GROUP = (24 / NW) < 1 ? 1 : ((24 / NW) > FS ? FS : (24 / NW));
+};
+
+template <typename T, int FS>
+__device__ __forceinline__ void load_row_words(const T* __restrict__ s, uint32_t (&w)[RowWords<T, FS>::NW])
+{
+    using R = RowWords<T, FS>;
+    if constexpr (R::SB == 4) {
+#pragma unroll
+        for (int i = 0; i < FS; ++i)
+            w[i] = __ldg(reinterpret_cast<const uint32_t*>(s) + i);
+    } else {
+        const uintptr_t addr = reinterpret_cast<uintptr_t>(s);
+        const uint32_t* __restrict__ p4 = reinterpret_cast<const uint32_t*>(addr & ~(uintptr_t)3);
+#pragma unroll
+        for (int j = 0; j < R::NA; ++j)
+            w[j] = __ldg(p4 + j);
+        w[R::NA] = ((unsigned)(addr & 3) + FS * R::SB > 4 * R::NA) ? __ldg(p4 + R::NA) : 0u; // never touch a word the row does not reach
+    }
+}
+
+template <typename T, int FS>
+__device__ __forceinline__ void row_words_to_float(const uint32_t (&w)[RowWords<T, FS>::NW], unsigned off, float (&v)[FS])
+{
+    using R = RowWords<T, FS>;
+    if constexpr (R::SB == 4) {
+#pragma unroll
+        for (int i = 0; i < FS; ++i)
+            v[i] = __uint_as_float(w[i]);
+    } else {
+        uint32_t al[R::NA];
+#pragma unroll
+        for (int j = 0; j < R::NA; ++j)
+            al[j] = __funnelshift_r(w[j], w[j + 1], off * 8);
+#pragma unroll
+        for (int i = 0; i < FS; ++i) {
+            uint32_t bits;
+            if (R::SB == 1)
+                bits = __byte_perm(al[i >> 2], 0x4B000000u, 0x7440 | (i & 3));
+            else
+                bits = __byte_perm(al[i >> 1], 0x4B000000u, (i & 1) ? 0x7432 : 0x7410);
+            v[i] = __uint_as_float(bits) - 8388608.f;
+        }
+    }
+}
+
+// sum over an FS x FS window with a weight block whose rows are padded to 16 bytes
+template <typename T, int FS>
+__device__ __forceinline__ float dot_rows_vec(const T* __restrict__ s, int pitch, const float* __restrict__ w)
+{
+    using R = RowWords<T, FS>;
+    constexpr int FSP = (FS + 3) & ~3;
+    const unsigned off = (unsigned)(reinterpret_cast<uintptr_t>(s) & 3); // the pitch keeps it the same on every row
+    float acc = 0.f;
+#pragma unroll 1
+    for (int ly0 = 0; ly0 < FS; ly0 += R::GROUP) {
+        uint32_t words[R::GROUP][R::NW];
+#pragma unroll
+        for (int g = 0; g < R::GROUP; ++g) {
+            const int ly = min(ly0 + g, FS - 1); // the last group may be short: re-read the last row, skipped below
+            load_row_words<T, FS>(s + (long long)ly * pitch, words[g]);
+        }
+#pragma unroll
+        for (int g = 0; g < R::GROUP; ++g) {
+            if (FS % R::GROUP != 0 && ly0 + g >= FS)
+                break;
+            float wr[FSP], v[FS];
+            const float4* __restrict__ w4 = reinterpret_cast<const float4*>(w + (ly0 + g) * FSP);
+#pragma unroll
+            for (int q = 0; q < FSP / 4; ++q) {
+                const float4 t = __ldg(w4 + q);
+                wr[4 * q] = t.x;
+                wr[4 * q + 1] = t.y;
+                wr[4 * q + 2] = t.z;
+                wr[4 * q + 3] = t.w;
+            }
+            row_words_to_float<T, FS>(words[g], off, v);
+#pragma unroll
+            for (int lx = 0; lx < FS; ++lx)
+                acc = fmaf(v[lx], wr[lx], acc);
+        }
+    }
+    return acc;
+}
+
+constexpr int STRIP_THREADS = 256;
+
+// One output sample of a strip for ONE plane, read straight from global memory.  Lean on purpose: 32-bit indexing,
+// constant weight strides.  FSC > 0 fixes the window size at compile time (inner loops unroll).
+template <typename T, int FSC>
+__device__ __forceinline__ void strip_sample(const StripArgs& a, const FrameSet& fsx, int x, int y, int plane)
+{
+    const PlanePtrs& pp = frame_ptrs(fsx);
+    const int fs = FSC > 0 ? FSC : a.fs;
+    const int sx = a.start_x[x], sy = a.start_y[y];
+    const int rx = a.rank_x[x], ry = a.rank_y[y];
+    const int pitch = (int)pp.src_pitch[plane];
+    const T* __restrict__ s = static_cast<const T*>(pp.src[plane]) + (long long)sy * pitch + sx;
+    float acc = 0.f;
+
+    const bool shared_block = rx >= 0 && ry >= 0;
+    if (!shared_block && a.border_block) {
+        // the block of this border pixel's class, rows padded to 16 bytes
+        const int fsp = (fs + 3) & ~3;
+        const float* __restrict__ w = a.border_wb + (size_t)a.border_block[jinc_border_slot(a.bg, x, y)] * (unsigned)(fs * fsp);
+        if (FSC > 0 && ((reinterpret_cast<uintptr_t>(pp.src[plane]) | (uintptr_t)(pitch * (int)sizeof(T))) & 3) == 0) {
+            acc = dot_rows_vec<T, (FSC > 0 ? FSC : 4)>(s, pitch, w);
+        } else {
+            for (int ly = 0; ly < fs; ++ly) {
+#pragma unroll
+                for (int lx = 0; lx < (FSC > 0 ? FSC : fs); ++lx)
+                    acc = fmaf(load_sample(s + lx), __ldg(w + lx), acc);
+                w += fsp;
+                s += pitch;
+            }
+        }
+    } else if (shared_block) {
+        // shared phase block (:431-435), row-major fs x fs
+        const float* __restrict__ w = a.weights + (unsigned)(ry * a.n_rank_x + rx) * (unsigned)(fs * fs);
+        for (int ly = 0; ly < fs; ++ly) {
+#pragma unroll
+            for (int lx = 0; lx < (FSC > 0 ? FSC : fs); ++lx)
+                acc = fmaf(load_sample(s + lx), __ldg(w + lx), acc);
+            w += fs;
+            s += pitch;
+        }
+    } else if (a.border_w) {
+        // this border pixel's own resident block (:443-514), stored [slot / 32][tap][slot % 32]: neighbouring pixels
+        // coalesce and the tap stride is the constant 32
+        const long long slot = jinc_border_slot(a.bg, x, y);
+        const float* __restrict__ w = a.border_w + (size_t)(slot >> 5) * (size_t)(fs * fs * 32) + (unsigned)(slot & 31);
+        for (int ly = 0; ly < fs; ++ly) {
+#pragma unroll
+            for (int lx = 0; lx < (FSC > 0 ? FSC : fs); ++lx)
+                acc = fmaf(load_sample(s + lx), __ldg(w + lx * 32), acc);
+            w += fs * 32;
+            s += pitch;
+        }
+    } else {
+        // border weights did not fit the residency budget: rebuild them per sample from the UNquantised position
+        // (:443-514), exact LUT index per tap, factor / divider
+        const float px = a.pos_x[x], py = a.pos_y[y];
+        const float sum = a.border_sum[jinc_border_slot(a.bg, x, y)];
+        for (int ly = 0; ly < fs; ++ly) {
+            const double dy2 = jinc_tap_dist2(py, a.src_h, sy + ly, a.step_y);
+            for (int lx = 0; lx < fs; ++lx) {
+                const double dx2 = jinc_tap_dist2(px, a.src_w, sx + lx, a.step_x);
+                const float f = jinc_lut_weight(a.lut, __dadd_rn(dx2, dy2), a.radius2, a.idx_scale);
+                acc = fmaf(load_sample(s + lx), __fdiv_rn(f, sum), acc);
+            }
+            s += pitch;
+        }
+    }
+    static_cast<T*>(pp.dst[plane])[(long long)y * pp.dst_pitch[plane] + x] = finish<T>(acc, fsx.peak);
+}
+
+// What a strip sample needs besides its source window: gathered for all of a thread's samples before any is used, so
+// the table loads of the SPT samples are in flight together.
+struct StripMeta {
+    int x, y;       // output sample (x < 0: none)
+    int sx, sy;     // window origin
+    const float* w; // weight block: [fs][wstride]
+    int wstride;    // fs for a shared phase block, fs rounded up to 4 for a border class block; 0 = neither (slow kinds)
+};
+
+template <int FSC>
+__device__ __forceinline__ StripMeta strip_meta(const StripArgs& a, int x, int y)
+{
+    const int fs = FSC > 0 ? FSC : a.fs;
+    StripMeta m;
+    m.x = x;
+    m.y = y;
+    m.sx = a.start_x[x];
+    m.sy = a.start_y[y];
+    const bool border = x < a.bg.bx0 || x >= a.bg.bx1 || y < a.bg.by0 || y >= a.bg.by1; // no table load needed to know
+    if (!border) {
+        m.w = a.weights + (unsigned)(a.rank_y[y] * a.n_rank_x + a.rank_x[x]) * (unsigned)(fs * fs);
+        m.wstride = fs;
+    } else if (a.border_block) {
+        const int fsp = (fs + 3) & ~3;
+        m.w = a.border_wb + (size_t)a.border_block[jinc_border_slot(a.bg, x, y)] * (unsigned)(fs * fsp);
+        m.wstride = fsp;
+    } else {
+        m.w = nullptr;
+        m.wstride = 0;
+    }
+    return m;
+}
+
+// One sample from a staged footprint: `tile` holds the source rectangle [sy_lo, ..) x [sx_lo, sx_lo + fw) as floats.
+template <typename T, int FSC>
+__device__ __forceinline__ void strip_sample_staged(const StripArgs& a, const FrameSet& fsx, const StripMeta& m, int plane,
+                                                    const float* __restrict__ tile, int fw, int sx_lo, int sy_lo)
+{
+    const int fs = FSC > 0 ? FSC : a.fs;
+    const float* __restrict__ s = tile + (m.sy - sy_lo) * fw + (m.sx - sx_lo);
+    float acc = 0.f;
+    if (m.wstride == fs) {
+        const float* __restrict__ w = m.w;
+        for (int ly = 0; ly < fs; ++ly) {
+#pragma unroll
+            for (int lx = 0; lx < (FSC > 0 ? FSC : fs); ++lx)
+                acc = fmaf(s[lx], __ldg(w + lx), acc);
+            w += fs;
+            s += fw;
+        }
+    } else {
+        const float4* __restrict__ w4 = reinterpret_cast<const float4*>(m.w); // rows padded to 16 bytes
+        for (int ly = 0; ly < fs; ++ly) {
+#pragma unroll
+            for (int q = 0; q < (FSC > 0 ? (FSC + 3) / 4 : m.wstride / 4); ++q) {
+                const float4 t = __ldg(w4 + q);
+                const int lx = 4 * q;
+                acc = fmaf(s[lx], t.x, acc);
+                if (lx + 1 < fs)
+                    acc = fmaf(s[lx + 1], t.y, acc);
+                if (lx + 2 < fs)
+                    acc = fmaf(s[lx + 2], t.z, acc);
+                if (lx + 3 < fs)
+                    acc = fmaf(s[lx + 3], t.w, acc);
+            }
+            w4 += m.wstride / 4;
+            s += fw;
+        }
+    }
+    const PlanePtrs& pp = frame_ptrs(fsx);
+    static_cast<T*>(pp.dst[plane])[(long long)m.y * pp.dst_pitch[plane] + m.x] = finish<T>(acc, fsx.peak);
+}
+
+// SPT samples of one thread that share ONE class block (the usual case in the strips of the periodic geometries: a
+// thread's samples lie in the same border row or column, a multiple of the phase period apart): the weights are loaded
+// once and feed SPT independent accumulators.
+template <typename T, int FSC, int SPT>
+__device__ __forceinline__ void strip_samples_fused(const StripArgs& a, const FrameSet& fsx, const StripMeta (&m)[SPT], int plane,
+                                                    const float* __restrict__ tile, int fw, int sx_lo, int sy_lo)
+{
+    const int fs = FSC > 0 ? FSC : a.fs;
+    const float* __restrict__ s[SPT];
+    float acc[SPT];
+#pragma unroll
+    for (int k = 0; k < SPT; ++k) {
+        s[k] = tile + (m[k].sy - sy_lo) * fw + (m[k].sx - sx_lo);
+        acc[k] = 0.f;
+    }
+    const float4* __restrict__ w4 = reinterpret_cast<const float4*>(m[0].w); // rows padded to 16 bytes
+    const int wq = m[0].wstride / 4;
+    for (int ly = 0; ly < fs; ++ly) {
+#pragma unroll
+        for (int q = 0; q < (FSC > 0 ? (FSC + 3) / 4 : wq); ++q) {
+            const float4 t = __ldg(w4 + q);
+            const int lx = 4 * q;
+#pragma unroll
+            for (int k = 0; k < SPT; ++k) {
+                acc[k] = fmaf(s[k][lx], t.x, acc[k]);
+                if (lx + 1 < fs)
+                    acc[k] = fmaf(s[k][lx + 1], t.y, acc[k]);
+                if (lx + 2 < fs)
+                    acc[k] = fmaf(s[k][lx + 2], t.z, acc[k]);
+                if (lx + 3 < fs)
+                    acc[k] = fmaf(s[k][lx + 3], t.w, acc[k]);
+            }
+        }
+        w4 += wq;
+#pragma unroll
+        for (int k = 0; k < SPT; ++k)
+            s[k] += fw;
+    }
+    const PlanePtrs& pp = frame_ptrs(fsx);
+    T* __restrict__ dst = static_cast<T*>(pp.dst[plane]);
+    const long long dp = pp.dst_pitch[plane];
+#pragma unroll
+    for (int k = 0; k < SPT; ++k)
+        dst[(long long)m[k].y * dp + m[k].x] = finish<T>(acc[k], fsx.peak);
+}
+
+// Strip block `sb` of the grid (planes are the slow dimension): one patch of PW x PH outputs, SPT per thread.  The
+// source rectangle the patch reads (window origins are monotonic along both axes) is staged into shared memory as
+// floats when it fits, so the global loads are coalesced, converted once and every window row is read from shared
+// memory; otherwise every sample reads global memory directly.
+template <typename T, int FSC, int THREADS = STRIP_THREADS, int SPT = 1>
+__device__ __forceinline__ void strip_block(const StripArgs& a, const FrameSet& fsx, unsigned sb, float* __restrict__ tile)
+{
+    const int fs = FSC > 0 ? FSC : a.fs;
+    const unsigned plane = sb / a.blocks_per_plane;
+    const unsigned pid = sb - plane * a.blocks_per_plane;
+    const int r = (int)(pid >= a.patch_begin[1]) + (int)(pid >= a.patch_begin[2]) + (int)(pid >= a.patch_begin[3]);
+    const unsigned lp = pid - a.patch_begin[r];
+    const unsigned pyi = lp / a.patches_x[r], pxi = lp - pyi * a.patches_x[r];
+    const int pwl = a.pw_log2[r];
+    const int ox0 = a.rect[r].x0 + (int)(pxi << pwl), oy0 = a.rect[r].y0 + (int)pyi * ((THREADS * SPT) >> pwl);
+    const int nx = min(1 << pwl, a.rect[r].x1 - ox0), ny = min((THREADS * SPT) >> pwl, a.rect[r].y1 - oy0);
+
+    // footprint corners and the tables of this thread's samples: one round of loads
+    const int sx_lo = a.start_x[ox0], sy_lo = a.start_y[oy0];
+    const int fw = a.start_x[ox0 + nx - 1] + fs - sx_lo, fh = a.start_y[oy0 + ny - 1] + fs - sy_lo;
+    StripMeta meta[SPT];
+#pragma unroll
+    for (int k = 0; k < SPT; ++k) {
+        const int o = (int)threadIdx.x + k * THREADS;
+        const int lx = o & ((1 << pwl) - 1), ly = o >> pwl;
+        if (lx < nx && ly < ny) {
+            meta[k] = strip_meta<FSC>(a, ox0 + lx, oy0 + ly);
+        } else {
+            meta[k].x = -1;
+            meta[k].wstride = 0;
+        }
+    }
+    const unsigned n = (unsigned)(fw * fh);
+    const bool staged = tile != nullptr && n <= a.smem_floats; // the same for the whole block
+    if (staged) {
+        const PlanePtrs& pp = frame_ptrs(fsx);
+        const int pitch = (int)pp.src_pitch[plane];
+        const T* __restrict__ src = static_cast<const T*>(pp.src[plane]) + (long long)sy_lo * pitch + sx_lo;
+        const float inv_fw = 1.f / (float)fw;
+        for (unsigned e0 = threadIdx.x; e0 < n; e0 += 4 * THREADS) {
+            T v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { // all four loads are issued before the first conversion
+                const unsigned e = min(e0 + u * THREADS, n - 1);
+                unsigned row = (unsigned)__float2int_rd(((float)e + 0.5f) * inv_fw);
+                row -= (row * (unsigned)fw > e);
+                row += ((row + 1) * (unsigned)fw <= e);
+                v[u] = __ldg(src + (long long)row * pitch + (e - row * (unsigned)fw));
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (e0 + u * THREADS < n)
+                    tile[e0 + u * THREADS] = sample_to_float(v[u]);
+        }
+        __syncthreads();
+    }
+    if (SPT > 1 && staged) {
+        bool same = true;
+        const int fsp = (fs + 3) & ~3;
+#pragma unroll
+        for (int k = 0; k < SPT; ++k)
+            same = same && meta[k].x >= 0 && meta[k].w == meta[0].w && meta[k].wstride == fsp;
+        if (same) {
+            strip_samples_fused<T, FSC, SPT>(a, fsx, meta, (int)plane, tile, fw, sx_lo, sy_lo);
+            return;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < SPT; ++k) {
+        if (meta[k].x < 0)
+            continue;
+        if (staged && meta[k].wstride)
+            strip_sample_staged<T, FSC>(a, fsx, meta[k], (int)plane, tile, fw, sx_lo, sy_lo);
+        else
+            strip_sample<T, FSC>(a, fsx, meta[k].x, meta[k].y, (int)plane);
+    }
+}
+
+// Role of block b in a merged grid of interior tile blocks and `strips` strip blocks: strip block k sits at grid
+// position k << shift (their latency-bound work then hides under the FMA-bound tiles sharing the SM) instead of
+// trailing the grid.  Returns true for a strip block and its index in `id`, else the tile index.  32-bit shifts only:
+// this runs in every block's prologue.
+__device__ __forceinline__ bool block_role(unsigned b, unsigned strips, int shift, unsigned& id)
+{
+    const unsigned k = b >> shift;
+    if ((b & ((1u << shift) - 1u)) == 0u && k < strips) {
+        id = k;
+        return true;
+    }
+    id = b - min(k + 1u, strips);
+    return false;
+}
+
+// largest shift with (strips - 1) << shift < interior + strips, i.e. every strip block has a grid position
+inline int strip_role_shift(long long interior, long long strips)
+{
+    int shift = 0;
+    if (strips > 0)
+        while (shift < 30 && (strips << (shift + 1)) <= interior + strips)
+            ++shift;
+    return shift;
+}
+
+// Cuts the rectangles into patches of `outputs` samples (one strip block each), at most `max_pw` wide; returns the
+// number of strip blocks per plane.
+inline long long set_strip_rects(StripArgs& a, const Rect* rects, int n_rects, int outputs, int max_pw, size_t smem_bytes)
+{
+    unsigned total = 0;
+    int k = 0;
+    max_pw = std::min(max_pw, outputs);
+    for (int r = 0; r < n_rects; ++r) {
+        const long long w = rects[r].x1 - rects[r].x0, h = rects[r].y1 - rects[r].y0;
+        if (w <= 0 || h <= 0)
+            continue;
+        int pwl = 3; // patches are at least 8 wide
+        while ((1 << pwl) < w && (1 << pwl) < max_pw)
+            ++pwl;
+        const long long pw = 1ll << pwl, ph = outputs / pw;
+        a.rect[k] = rects[r];
+        a.pw_log2[k] = pwl;
+        a.patches_x[k] = (unsigned)((w + pw - 1) / pw);
+        a.patch_begin[k] = total;
+        total += a.patches_x[k] * (unsigned)((h + ph - 1) / ph);
+        ++k;
+    }
+    for (int j = k; j < 4; ++j) {
+        a.rect[j] = Rect{0, 0, 1, 1};
+        a.pw_log2[j] = 3;
+        a.patches_x[j] = 1;
+        a.patch_begin[j] = total;
+    }
+    a.patch_begin[4] = total;
+    a.blocks_per_plane = total;
+    a.smem_floats = (unsigned)(smem_bytes / sizeof(float));
+    return total;
+}
+
+// ------------------------------------------------------------------------------------------ exact-2x kernel
+
+constexpr int UP_TX = 4;                     // cells per thread along x
+constexpr int UP_WARPS = 8;
+constexpr int UP_THREADS = UP_WARPS * 32;
+constexpr int UP_CW = 32 * UP_TX;            // cells per tile row (128 -> 256 output samples)
+constexpr int UP_RPW = 2;                    // cell-row pairs per warp
+constexpr int UP_CH = 2 * UP_WARPS * UP_RPW; // cell rows per tile (32 -> 64 output rows)
+constexpr int UP_STRIP_SPT = 4;              // strip role: outputs per thread (patches of 1024 outputs, up to 256 wide)
+constexpr int UP_STRIP_MAX_PW = 1024;            // a thread's four samples share a border row: x, x + 256, ...
+
+template <int FS>
+struct UpGeom {
+    static constexpr int FSP = (FS + 3) & ~3;       // weight row stride (16-byte rows)
+    static constexpr int NSEG = UP_TX + 1 + FS - 1; // pair columns a thread reads per row (ox1 <= 1)
+    static constexpr int NC = UP_CW + FS;           // pair columns per tile row (CW + ox1 + FS - 1)
+    static constexpr int NCP = (NC + 3) & ~3;
+    static constexpr int SUB = NCP / 4;             // columns are de-interleaved by (c & 3): 4 sub-rows of SUB
+    static constexpr int NR = UP_CH + 1 + FS - 1;   // pair rows per tile (CH + oy1 + FS - 1)
+    static constexpr size_t SMEM = (size_t)NR * NCP * sizeof(float2);
+};
+
+template <int FS>
+struct alignas(16) UpWeights {
+    float w[2][2][FS][UpGeom<FS>::FSP]; // [py][px][ly][lx]
+};
+
+struct UpArgs {
+    FrameSet fr;
+    StripArgs st;         // border strips around the interior (run by the blocks after the interior tiles)
+    int src_w, src_h;
+    int x0, y0, ncx;      // output origin of the periodic interior, cells per row
+    int sx0, sy0;         // window origin of cell (0,0), phase (0,0)
+    int cy_begin, cy_end; // cell rows to produce (row-band split)
+    int tiles_x, tiles_per_plane, interior_blocks; // interior_blocks = tiles_per_plane * n_planes
+    int strip_blocks, strip_shift;
+};
+
+inline bool up2x_supported(int fs) { return fs == 7 || fs == 9 || fs == 13 || fs == 17; }
+
+inline size_t up2x_smem_bytes(int fs)
+{
+    switch (fs) {
+    case 7: return UpGeom<7>::SMEM;
+    case 9: return UpGeom<9>::SMEM;
+    case 13: return UpGeom<13>::SMEM;
+    case 17: return UpGeom<17>::SMEM;
+    default: return 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ integer-ratio downscale kernel
+//
+// Output (x,y) of the interior reads the FS x FS window at (sx0 + Q*x, sy0 + Q*y) with ONE weight block for every
+// pixel (config 5: Q = 4, FS = 50, 2500 taps per sample).  All threads apply the same weight at the same time, so
+// weights again come from the constant bank through uniform registers.  Three ideas shape the kernel:
+//   * polyphase columns: lx = Q*m + p turns the x-sum into Q stride-1 convolutions over the de-interleaved sequences
+//     S_p[j] = S[Q*j + p]; a thread that owns NX consecutive outputs reads a span of NX+MT-1 values per (row, p) and
+//     uses each for up to NX outputs, and one weight fetch feeds NX FFMA2s;
+//   * tap pairing: one packed FFMA2 multiplies the vertical sample pair {S[r][c], S[r+1][c]} with the weight pair
+//     {w[ly][lx], w[ly+1][lx]} into the two halves of ONE output's accumulator (even-row and odd-row partial sums,
+//     added in the epilogue).  Q is even, so every output row of the thread sees the same pairing and a staged pair
+//     is reused for all NY output rows of the thread;
+//   * raw sample pairs in shared memory for integer formats (two 16-bit samples per 32-bit word; u8 is widened while
+//     staging), so a 64x32-output tile with its 302x174-sample footprint fits twice per SM.  The float value is made
+//     after the shared-memory load.  For depths up to 15 bits that costs ONE byte permute per sample: staging stores
+//     x << (15 - bits), and PRMT drops those 16 bits into mantissa bits [22:8] of 0x3F000000, i.e. f = 0.5 + x' / 65536
+//     exactly.  The kernel accumulates sum(w * f) and the epilogue removes the 0.5 * sum(w) bias (host-computed per
+//     accumulator half) and rescales by a power of two.  Precision matches a direct float sum of 15-bit samples (the
+//     accumulator's ulp relative to one input LSB is the same).  16-bit samples use I2F instead (XU pipe).
+// Columns are de-interleaved by c mod (Q*NX) so a warp's loads are bank-conflict free.
+constexpr int DN_TW = 64;  // output columns per tile
+constexpr int DN_TH = 32;  // output rows per tile (integer formats; float tiles are half as tall)
+
+constexpr int DN_STRIP_SPT = 2;    // strip role: outputs per thread, patches at most 64 wide (the windows are wide)
+constexpr int DN_STRIP_MAX_PW = 256;
+
+enum { DN_CVT_I2F = 0, DN_CVT_PRMT = 1, DN_CVT_FLOAT = 2 };
+
+template <typename T, int FS, int Q, int NX, int NY>
+struct DownGeom {
+    static constexpr bool IS_FLOAT = sizeof(T) == 4;
+    using Word = typename std::conditional<IS_FLOAT, float2, uint32_t>::type; // {row 2k, row 2k+1}
+    static constexpr int LX = DN_TW / NX;               // lanes along x
+    static constexpr int LY = 32 / LX;                  // lanes along y
+    static constexpr int TH = IS_FLOAT ? DN_TH / 2 : DN_TH;
+    static constexpr int WARPS = TH / (LY * NY);
+    static constexpr int THREADS = 32 * WARPS;
+    static constexpr int FSE = (FS + 1) & ~1;           // window rows rounded up to whole pairs
+    static constexpr int NKW = FSE / 2;                 // weight row pairs
+    static constexpr int MT = (FS + Q - 1) / Q;         // taps per polyphase component
+    static constexpr int SPAN = NX + MT - 1;            // values a thread reads per (row pair, p)
+    static constexpr int D = Q * NX;                    // column de-interleave modulus
+    static constexpr int NCOL = Q * (DN_TW - 1) + Q * (MT - 1) + Q; // columns a tile row can be asked for
+    static constexpr int SUB = (NCOL + D - 1) / D;
+    static constexpr int NROWS = Q * (TH - 1) + FSE;
+    static constexpr int NROWP = (NROWS + 1) / 2;       // row pairs per tile
+    static constexpr int JSTEP = Q / 2;                 // row pairs between consecutive output rows
+    static constexpr int NK = NKW + JSTEP * (NY - 1);   // row pairs a thread walks
+    static constexpr int HALF = NY * JSTEP;             // row pairs between lane groups that differ in y
+    static constexpr int rs_pad()
+    {
+        for (int pad = 0; pad < 32; ++pad) // lane group g lands on banks [g*LX, g*LX + LX)
+            if (((D * SUB + pad) * HALF) % 32 == LX % 32)
+                return pad;
+        return 0;
+    }
+    static constexpr int RS = D * SUB + rs_pad();       // row-pair stride in words
+    static constexpr size_t SMEM = (size_t)NROWP * RS * sizeof(Word);
+    static_assert(Q % 2 == 0, "tap pairing needs an even ratio");
+    static_assert(TH % (LY * NY) == 0 && WARPS >= 1, "tile rows must split evenly over the warps");
+    static_assert(LX - 1 + (Q * (SPAN - 1) + Q - 1) / D < SUB, "span reaches past the tile row");
+};
+
+template <int FS, int Q>
+struct alignas(16) DownWeights {
+    static constexpr int MT = (FS + Q - 1) / Q;
+    float2 w[((FS + 1) & ~1) / 2][Q][MT]; // [ly/2][p][m] = {w[ly][Q*m+p], w[ly+1][Q*m+p]}; entries outside the window are 0
+};
+
+struct DownArgs {
+    FrameSet fr;
+    StripArgs st;
+    int src_w, src_h;
+    int x0, y0, x1, y1;  // output rectangle produced by the tiles (y0..y1 already cut to the row band)
+    int tsx0, tsy0;      // window origin of output (x0, y0)
+    int tiles_x, tiles_per_plane, interior_blocks, strip_blocks, strip_shift;
+    int pre_shift;       // PRMT conversion: samples are staged as x << pre_shift
+    float bias_even, bias_odd, out_scale; // PRMT conversion: out = ((acc.x - bias_even) + (acc.y - bias_odd)) * out_scale
+};
+
+// ---- launch entry points, one explicit instantiation per sample type (jinc_up2x_*.cu, jinc_down_*.cu)
+// 0 launched, 1 unsupported filter size, <0 error
+template <typename T>
+int launch_up2x(const jinc_table* t, UpArgs& a, long long strip_blocks, int n_frames, cudaStream_t st);
+// 0 launched, 2 nothing to do, 1 unsupported geometry, <0 error
+template <typename T>
+int launch_down(const jinc_table* t, DownArgs& a, bool want_strips, int n_frames, cudaStream_t st, const Rect* rects, int n_rects);
+
+inline bool down_supported(const jinc_table* t)
+{
+    if (!t->down.ok || t->down.qx != t->down.qy)
+        return false;
+    switch (t->down.qx * 1000 + t->sc.fs) {
+    case 2013: case 2017: case 2025: case 2033: case 4026: case 4034: case 4050: return true;
+    default: return false;
+    }
+}
+
+} // namespace jinc_rs
+
+#endif

@@ -1,0 +1,214 @@
+// jinc_up2x.cuh -- exact-2x interior kernel (see jinc_resample.cuh for the layout); included by jinc_up2x_<type>.cu,
+// which instantiates launch_up2x for one sample type.
+#ifndef JINC_UP2X_CUH
+#define JINC_UP2X_CUH
+
+#include "jinc_resample.cuh"
+
+namespace jinc_rs {
+
+constexpr int UP_UNROLL_MAX_FS = 9; // windows up to this size get a fully unrolled row loop
+
+// One pair row of the tile applied to the thread's 16 accumulators: phase row 0 uses weight row rr, phase row 1 uses
+// weight row rr - OY1.
+template <int FS, int OX1, int OY1>
+__device__ __forceinline__ void up_row(const float2* __restrict__ trow, int rr, const UpWeights<FS>& W, float2 (&acc)[2][2][UP_TX])
+{
+    using G = UpGeom<FS>;
+    float2 seg[G::NSEG];
+#pragma unroll
+    for (int m = 0; m < G::NSEG; ++m)
+        seg[m] = trow[(m & 3) * G::SUB + (m >> 2)]; // column 4*lane + m
+
+    if (OY1 == 0 || rr < FS) { // phase row 0: ly = rr
+#pragma unroll
+        for (int lx = 0; lx < FS; ++lx) {
+            const float w0 = W.w[0][0][rr][lx], w1 = W.w[0][1][rr][lx];
+#pragma unroll
+            for (int i = 0; i < UP_TX; ++i) {
+                acc[0][0][i] = __ffma2_rn(seg[i + lx], make_float2(w0, w0), acc[0][0][i]);
+                acc[0][1][i] = __ffma2_rn(seg[i + OX1 + lx], make_float2(w1, w1), acc[0][1][i]);
+            }
+        }
+    }
+    const int ly1 = rr - OY1; // phase row 1
+    if (OY1 == 0 || rr >= OY1) {
+#pragma unroll
+        for (int lx = 0; lx < FS; ++lx) {
+            const float w0 = W.w[1][0][ly1][lx], w1 = W.w[1][1][ly1][lx];
+#pragma unroll
+            for (int i = 0; i < UP_TX; ++i) {
+                acc[1][0][i] = __ffma2_rn(seg[i + lx], make_float2(w0, w0), acc[1][0][i]);
+                acc[1][1][i] = __ffma2_rn(seg[i + OX1 + lx], make_float2(w1, w1), acc[1][1][i]);
+            }
+        }
+    }
+}
+
+template <typename T, int FS, int OX1, int OY1>
+__global__ void __launch_bounds__(UP_THREADS, (FS >= 13 ? 2 : 3))
+    resample_up2x(const __grid_constant__ UpArgs a, const __grid_constant__ UpWeights<FS> W)
+{
+    using G = UpGeom<FS>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+
+    unsigned role_id;
+    if (block_role(blockIdx.x, (unsigned)a.strip_blocks, a.strip_shift, role_id)) {
+        // ---------------- strip role
+        strip_block<T, FS, UP_THREADS, UP_STRIP_SPT>(a.st, a.fr, role_id, reinterpret_cast<float*>(smem_raw));
+        return;
+    }
+
+    // -------------------- interior tile role
+    float2* tile = reinterpret_cast<float2*>(smem_raw); // [NR][4][SUB] pairs {S[r][c], S[r+1][c]}
+    const int plane = role_id / a.tiles_per_plane;
+    const int tidx = role_id - plane * a.tiles_per_plane;
+    const int tile_y = tidx / a.tiles_x, tile_x = tidx - tile_y * a.tiles_x;
+    const PlanePtrs& pp = frame_ptrs(a.fr);
+    const T* __restrict__ src = static_cast<const T*>(pp.src[plane]);
+    T* __restrict__ dst = static_cast<T*>(pp.dst[plane]);
+    const long long sp = pp.src_pitch[plane], dp = pp.dst_pitch[plane];
+
+    const int cell_x0 = tile_x * UP_CW; // first cell of this tile
+    const int cell_y0 = a.cy_begin + tile_y * UP_CH;
+    const int tsx = a.sx0 + cell_x0, tsy = a.sy0 + cell_y0; // source coordinates of tile(0,0)
+
+    // ---- stage the source tile.  A thread owns 4 consecutive columns and walks down a segment of rows, pairing each
+    //      row with the one above it, so every source sample is loaded and converted once per segment.
+    {
+        constexpr int SEGS = UP_THREADS / G::SUB;       // row segments
+        constexpr int ROWS = (G::NR + SEGS - 1) / SEGS; // pair rows per segment
+        const int q = threadIdx.x % G::SUB, seg = threadIdx.x / G::SUB;
+        if (seg < SEGS) {
+            int xo[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                xo[k] = min(max(tsx + 4 * q + k, 0), a.src_w - 1); // out-of-plane taps only feed discarded cells
+            const int r0 = seg * ROWS, r1 = min(r0 + ROWS, G::NR);
+            float prev[4], cur[4];
+            {
+                const T* row = src + (long long)min(max(tsy + r0, 0), a.src_h - 1) * sp;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    prev[k] = load_sample(row + xo[k]);
+            }
+            for (int r = r0; r < r1; ++r) {
+                const T* row = src + (long long)min(max(tsy + r + 1, 0), a.src_h - 1) * sp;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    cur[k] = load_sample(row + xo[k]);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    tile[(r * 4 + k) * G::SUB + q] = make_float2(prev[k], cur[k]);
+                    prev[k] = cur[k];
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+#pragma unroll 1
+    for (int rp = warp; rp < UP_WARPS * UP_RPW; rp += UP_WARPS) {
+        const int cy = cell_y0 + 2 * rp; // first cell row of the pair
+        if (cy >= a.cy_end)
+            break;
+        float2 acc[2][2][UP_TX];
+#pragma unroll
+        for (int py = 0; py < 2; ++py)
+#pragma unroll
+            for (int px = 0; px < 2; ++px)
+#pragma unroll
+                for (int i = 0; i < UP_TX; ++i)
+                    acc[py][px][i] = make_float2(0.f, 0.f);
+
+        const float2* trow = tile + (size_t)(2 * rp) * G::NCP + lane;
+        if constexpr (FS <= UP_UNROLL_MAX_FS) {
+            // small windows: the row loop is unrolled completely, so every weight has a fixed constant-bank address
+            // and there is no loop control between the FFMA2 runs
+#pragma unroll
+            for (int rr = 0; rr < FS + OY1; ++rr)
+                up_row<FS, OX1, OY1>(trow + rr * G::NCP, rr, W, acc);
+        } else {
+#pragma unroll 1
+            for (int rr = 0; rr < FS + OY1; ++rr, trow += G::NCP)
+                up_row<FS, OX1, OY1>(trow, rr, W, acc);
+        }
+
+        // ---- epilogue: 4 output rows x 8 consecutive samples per thread
+        const int cx = cell_x0 + UP_TX * lane;
+        if (cx >= a.ncx)
+            continue;
+        const int ox = a.x0 + 2 * cx;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            if (cy + h < a.cy_end) {
+#pragma unroll
+                for (int py = 0; py < 2; ++py) {
+                    float v[8];
+#pragma unroll
+                    for (int i = 0; i < UP_TX; ++i) {
+                        v[2 * i] = h ? acc[py][0][i].y : acc[py][0][i].x;
+                        v[2 * i + 1] = h ? acc[py][1][i].y : acc[py][1][i].x;
+                    }
+                    T* o = dst + (long long)(a.y0 + 2 * (cy + h) + py) * dp + ox;
+                    if (cx + UP_TX <= a.ncx) {
+                        store8<T>(o, v, a.fr.peak);
+                    } else {
+                        const int nk = 2 * (a.ncx - cx);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            if (k < nk)
+                                o[k] = finish<T>(v[k], a.fr.peak);
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <typename T, int FS>
+int launch_up2x_fs(const jinc_table* t, UpArgs& a, long long strip_blocks, int n_frames, cudaStream_t st)
+{
+    using G = UpGeom<FS>;
+    const Up2xPlan& u = t->up2x;
+    UpWeights<FS> w;
+    memset(&w, 0, sizeof(w));
+    for (int py = 0; py < 2; ++py)
+        for (int px = 0; px < 2; ++px) {
+            const float* blk = t->h_weights.data() + (size_t)u.wblock[py][px] * FS * FS;
+            for (int ly = 0; ly < FS; ++ly)
+                for (int lx = 0; lx < FS; ++lx)
+                    w.w[py][px][ly][lx] = blk[ly * FS + lx];
+        }
+    auto kern = u.ox1 ? (u.oy1 ? resample_up2x<T, FS, 1, 1> : resample_up2x<T, FS, 1, 0>)
+                      : (u.oy1 ? resample_up2x<T, FS, 0, 1> : resample_up2x<T, FS, 0, 0>);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
+    if (e != cudaSuccess)
+        return jinc_fail(JINC_E_CUDA, "cudaFuncSetAttribute(up2x smem %zu): %s", G::SMEM, cudaGetErrorString(e));
+    a.strip_blocks = (int)strip_blocks;
+    a.strip_shift = strip_role_shift(a.interior_blocks, strip_blocks);
+    dim3 grid((unsigned)(a.interior_blocks + strip_blocks), n_frames, 1);
+    kern<<<grid, UP_THREADS, G::SMEM, st>>>(a, w);
+    e = cudaGetLastError();
+    if (e != cudaSuccess)
+        return jinc_fail(JINC_E_CUDA, "resample_up2x launch failed: %s", cudaGetErrorString(e));
+    return JINC_OK;
+}
+
+template <typename T>
+int launch_up2x(const jinc_table* t, UpArgs& a, long long strip_blocks, int n_frames, cudaStream_t st)
+{
+    switch (t->sc.fs) {
+    case 7: return launch_up2x_fs<T, 7>(t, a, strip_blocks, n_frames, st);   // tap 3  (Jinc36Resize)
+    case 9: return launch_up2x_fs<T, 9>(t, a, strip_blocks, n_frames, st);   // tap 4  (Jinc64Resize)
+    case 13: return launch_up2x_fs<T, 13>(t, a, strip_blocks, n_frames, st); // tap 6  (Jinc144Resize)
+    case 17: return launch_up2x_fs<T, 17>(t, a, strip_blocks, n_frames, st); // tap 8  (Jinc256Resize)
+    default: return 1;
+    }
+}
+
+} // namespace jinc_rs
+
+#endif
