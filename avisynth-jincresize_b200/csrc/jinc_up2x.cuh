@@ -73,8 +73,9 @@ __global__ void __launch_bounds__(UP_THREADS, (FS >= 13 ? 2 : 3))
     const int cell_y0 = a.cy_begin + tile_y * UP_CH;
     const int tsx = a.sx0 + cell_x0, tsy = a.sy0 + cell_y0; // source coordinates of tile(0,0)
 
-    // ---- stage the source tile.  A thread owns 4 consecutive columns and walks down a segment of rows, pairing each
-    //      row with the one above it, so every source sample is loaded and converted once per segment.
+    // ---- stage the source tile.  A thread owns 4 consecutive columns and a segment of rows; ALL its loads are issued
+    //      before the first conversion (one memory round trip per tile instead of one per row), then every row is paired
+    //      with the one below it.
     {
         constexpr int SEGS = UP_THREADS / G::SUB;       // row segments
         constexpr int ROWS = (G::NR + SEGS - 1) / SEGS; // pair rows per segment
@@ -84,23 +85,21 @@ __global__ void __launch_bounds__(UP_THREADS, (FS >= 13 ? 2 : 3))
 #pragma unroll
             for (int k = 0; k < 4; ++k)
                 xo[k] = min(max(tsx + 4 * q + k, 0), a.src_w - 1); // out-of-plane taps only feed discarded cells
-            const int r0 = seg * ROWS, r1 = min(r0 + ROWS, G::NR);
-            float prev[4], cur[4];
-            {
-                const T* row = src + (long long)min(max(tsy + r0, 0), a.src_h - 1) * sp;
+            const int r0 = seg * ROWS;
+            T raw[ROWS + 1][4];
+#pragma unroll
+            for (int j = 0; j <= ROWS; ++j) {
+                const T* row = src + (long long)min(max(tsy + r0 + j, 0), a.src_h - 1) * sp;
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                    prev[k] = load_sample(row + xo[k]);
+                    raw[j][k] = __ldg(row + xo[k]);
             }
-            for (int r = r0; r < r1; ++r) {
-                const T* row = src + (long long)min(max(tsy + r + 1, 0), a.src_h - 1) * sp;
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    cur[k] = load_sample(row + xo[k]);
+            for (int j = 0; j < ROWS; ++j) {
+                if (r0 + j < G::NR) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    tile[(r * 4 + k) * G::SUB + q] = make_float2(prev[k], cur[k]);
-                    prev[k] = cur[k];
+                    for (int k = 0; k < 4; ++k)
+                        tile[((r0 + j) * 4 + k) * G::SUB + q] = make_float2(sample_to_float(raw[j][k]), sample_to_float(raw[j + 1][k]));
                 }
             }
         }
