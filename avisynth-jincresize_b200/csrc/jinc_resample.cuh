@@ -98,6 +98,41 @@ __device__ __forceinline__ float sample_to_float<float>(float v)
     return v;
 }
 
+// four consecutive samples as one aligned vector load
+template <typename T>
+struct Vec4Of;
+template <>
+struct Vec4Of<uint8_t> {
+    using type = uint32_t;
+};
+template <>
+struct Vec4Of<uint16_t> {
+    using type = uint2;
+};
+template <>
+struct Vec4Of<float> {
+    using type = float4;
+};
+// sample k (0..3, a constant after unrolling) of such a group as float: integer samples are dropped into the mantissa
+// of 2^23 by one byte permute, then 2^23 is subtracted
+template <typename T>
+__device__ __forceinline__ float vec4_sample(const typename Vec4Of<T>::type& v, int k);
+template <>
+__device__ __forceinline__ float vec4_sample<uint8_t>(const uint32_t& v, int k)
+{
+    return __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7440u | (unsigned)k)) - 8388608.f;
+}
+template <>
+__device__ __forceinline__ float vec4_sample<uint16_t>(const uint2& v, int k)
+{
+    return __uint_as_float(__byte_perm((k & 2) ? v.y : v.x, 0x4B000000u, (k & 1) ? 0x7432u : 0x7410u)) - 8388608.f;
+}
+template <>
+__device__ __forceinline__ float vec4_sample<float>(const float4& v, int k)
+{
+    return k == 0 ? v.x : k == 1 ? v.y : k == 2 ? v.z : v.w;
+}
+
 template <typename T>
 __device__ __forceinline__ void store8(T* p, const float (&v)[8], float peak);
 template <>
@@ -615,7 +650,7 @@ inline long long set_strip_rects(StripArgs& a, const Rect* rects, int n_rects, i
 // ------------------------------------------------------------------------------------------ exact-2x kernel
 
 constexpr int UP_TX = 4;                     // cells per thread along x
-constexpr int UP_WARPS = 8;
+constexpr int UP_WARPS = 4;
 constexpr int UP_THREADS = UP_WARPS * 32;
 constexpr int UP_CW = 32 * UP_TX;            // cells per tile row (128 -> 256 output samples)
 constexpr int UP_RPW = 2;                    // cell-row pairs per warp

@@ -46,7 +46,7 @@ __device__ __forceinline__ void up_row(const float2* __restrict__ trow, int rr, 
 }
 
 template <typename T, int FS, int OX1, int OY1>
-__global__ void __launch_bounds__(UP_THREADS, (FS >= 13 ? 2 : 3))
+__global__ void __launch_bounds__(UP_THREADS, (FS >= 13 ? 4 : 6))
     resample_up2x(const __grid_constant__ UpArgs a, const __grid_constant__ UpWeights<FS> W)
 {
     using G = UpGeom<FS>;
@@ -73,10 +73,45 @@ __global__ void __launch_bounds__(UP_THREADS, (FS >= 13 ? 2 : 3))
     const int cell_y0 = a.cy_begin + tile_y * UP_CH;
     const int tsx = a.sx0 + cell_x0, tsy = a.sy0 + cell_y0; // source coordinates of tile(0,0)
 
-    // ---- stage the source tile.  A thread owns 4 consecutive columns and a segment of rows; ALL its loads are issued
-    //      before the first conversion (one memory round trip per tile instead of one per row), then every row is paired
-    //      with the one below it.
-    {
+    // ---- stage the source tile: every row is paired with the one below it and converted to float once.  A thread owns
+    //      one 4-sample group per row over a segment of rows and issues ALL its loads before the first conversion (one
+    //      memory round trip per tile).  When the plane base and pitch allow it the groups are aligned vector loads
+    //      (4 samples per LDG); the tile columns then start d = tsx & 3 samples into the first group.
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)(sp * (long long)sizeof(T))) & (4 * sizeof(T) - 1)) == 0;
+    if (vec_ok) {
+        using V = typename Vec4Of<T>::type;
+        constexpr int GRP = G::SUB + 1;                 // groups per row (one more: the row starts inside a group)
+        constexpr int SEGS = UP_THREADS / GRP;          // row segments
+        constexpr int ROWS = (G::NR + SEGS - 1) / SEGS; // pair rows per segment
+        const int q = threadIdx.x % GRP, seg = threadIdx.x / GRP;
+        if (seg < SEGS) {
+            const int d = tsx & 3;
+            const int g = min(max((tsx >> 2) + q, 0), (a.src_w - 1) >> 2); // groups outside the plane only feed discarded cells
+            const int r0 = seg * ROWS;
+            V raw[ROWS + 1];
+#pragma unroll
+            for (int j = 0; j <= ROWS; ++j) {
+                const T* row = src + (long long)min(max(tsy + r0 + j, 0), a.src_h - 1) * sp;
+                raw[j] = __ldg(reinterpret_cast<const V*>(row) + g);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int cc = k - d;                      // tile column of sample k is 4 q + cc
+                const int idx = q + (cc >> 2);
+                if (idx >= 0 && idx < G::SUB) {
+                    float2* out = tile + (r0 * 4 + (cc & 3)) * G::SUB + idx;
+                    float prev = vec4_sample<T>(raw[0], k);
+#pragma unroll
+                    for (int j = 0; j < ROWS; ++j) {
+                        const float cur = vec4_sample<T>(raw[j + 1], k);
+                        if (r0 + j < G::NR)
+                            out[j * 4 * G::SUB] = make_float2(prev, cur);
+                        prev = cur;
+                    }
+                }
+            }
+        }
+    } else {
         constexpr int SEGS = UP_THREADS / G::SUB;       // row segments
         constexpr int ROWS = (G::NR + SEGS - 1) / SEGS; // pair rows per segment
         const int q = threadIdx.x % G::SUB, seg = threadIdx.x / G::SUB;
