@@ -199,6 +199,7 @@ struct StripArgs {
     const float* pos_x;
     const float* pos_y;
     const float* weights;
+    const float* weights_p; // the phase blocks again with rows padded to 16 bytes [block][fs][fsp], or null (many phases)
     const float* lut;
     const float* border_sum;
     const float* border_w; // resident per-pixel border weights [slot/32][tap][slot%32], or null
@@ -211,6 +212,7 @@ struct StripArgs {
     unsigned patch_begin[5];   // prefix sums of patches per rect
     unsigned patches_x[4];     // patches per row of patches
     int pw_log2[4];            // log2 of the patch width (patch height = outputs per block / width)
+    int row_mode[4];           // 1: a thread's samples lie in one output row (top/bottom strips), 0: in one column
     unsigned blocks_per_plane; // = patch_begin[4]; the grid holds this many strip blocks per plane
     unsigned smem_floats;      // shared memory a strip block may use to stage its source footprint (0: none)
 };
@@ -400,10 +402,23 @@ struct StripMeta {
     int wstride;    // fs for a shared phase block, fs rounded up to 4 for a border class block; 0 = neither (slow kinds)
 };
 
+// 32-bit form of jinc_border_slot for the kernels (the table build rejects geometries with 2^31 or more border pixels)
+__device__ __forceinline__ int border_slot32(const BorderGeom& g, int x, int y)
+{
+    if (y < g.by0)
+        return y * g.W + x;
+    if (y >= g.by1)
+        return (int)g.off_bottom + (y - g.by1) * g.W + x;
+    if (x < g.bx0)
+        return (int)g.off_left + (y - g.by0) * g.bx0 + x;
+    return (int)g.off_right + (y - g.by0) * (g.W - g.bx1) + (x - g.bx1);
+}
+
 template <int FSC>
 __device__ __forceinline__ StripMeta strip_meta(const StripArgs& a, int x, int y)
 {
     const int fs = FSC > 0 ? FSC : a.fs;
+    const int fsp = (fs + 3) & ~3;
     StripMeta m;
     m.x = x;
     m.y = y;
@@ -411,11 +426,16 @@ __device__ __forceinline__ StripMeta strip_meta(const StripArgs& a, int x, int y
     m.sy = a.start_y[y];
     const bool border = x < a.bg.bx0 || x >= a.bg.bx1 || y < a.bg.by0 || y >= a.bg.by1; // no table load needed to know
     if (!border) {
-        m.w = a.weights + (unsigned)(a.rank_y[y] * a.n_rank_x + a.rank_x[x]) * (unsigned)(fs * fs);
-        m.wstride = fs;
+        const unsigned blk = (unsigned)(a.rank_y[y] * a.n_rank_x + a.rank_x[x]);
+        if (a.weights_p) {
+            m.w = a.weights_p + blk * (unsigned)(fs * fsp);
+            m.wstride = fsp;
+        } else {
+            m.w = a.weights + blk * (unsigned)(fs * fs);
+            m.wstride = fs;
+        }
     } else if (a.border_block) {
-        const int fsp = (fs + 3) & ~3;
-        m.w = a.border_wb + (size_t)a.border_block[jinc_border_slot(a.bg, x, y)] * (unsigned)(fs * fsp);
+        m.w = a.border_wb + (unsigned)a.border_block[border_slot32(a.bg, x, y)] * (unsigned)(fs * fsp);
         m.wstride = fsp;
     } else {
         m.w = nullptr;
@@ -432,7 +452,7 @@ __device__ __forceinline__ void strip_sample_staged(const StripArgs& a, const Fr
     const int fs = FSC > 0 ? FSC : a.fs;
     const float* __restrict__ s = tile + (m.sy - sy_lo) * fw + (m.sx - sx_lo);
     float acc = 0.f;
-    if (m.wstride == fs) {
+    if ((m.wstride & 3) != 0) { // unpadded rows (the general path's phase blocks)
         const float* __restrict__ w = m.w;
         for (int ly = 0; ly < fs; ++ly) {
 #pragma unroll
@@ -468,8 +488,8 @@ __device__ __forceinline__ void strip_sample_staged(const StripArgs& a, const Fr
 // thread's samples lie in the same border row or column, a multiple of the phase period apart): the weights are loaded
 // once and feed SPT independent accumulators.
 template <typename T, int FSC, int SPT>
-__device__ __forceinline__ void strip_samples_fused(const StripArgs& a, const FrameSet& fsx, const StripMeta (&m)[SPT], int plane,
-                                                    const float* __restrict__ tile, int fw, int sx_lo, int sy_lo)
+__device__ __forceinline__ void strip_samples_fused(const StripArgs& a, const FrameSet& fsx, const StripMeta (&m)[SPT], unsigned live,
+                                                    int plane, const float* __restrict__ tile, int fw, int sx_lo, int sy_lo)
 {
     const int fs = FSC > 0 ? FSC : a.fs;
     const float* __restrict__ s[SPT];
@@ -507,16 +527,21 @@ __device__ __forceinline__ void strip_samples_fused(const StripArgs& a, const Fr
     const long long dp = pp.dst_pitch[plane];
 #pragma unroll
     for (int k = 0; k < SPT; ++k)
-        dst[(long long)m[k].y * dp + m[k].x] = finish<T>(acc[k], fsx.peak);
+        if (live & (1u << k))
+            dst[(long long)m[k].y * dp + m[k].x] = finish<T>(acc[k], fsx.peak);
 }
 
 // Strip block `sb` of the grid (planes are the slow dimension): one patch of PW x PH outputs, SPT per thread.  The
 // source rectangle the patch reads (window origins are monotonic along both axes) is staged into shared memory as
 // floats when it fits, so the global loads are coalesced, converted once and every window row is read from shared
-// memory; otherwise every sample reads global memory directly.
+// memory; otherwise every sample reads global memory directly.  A thread's SPT samples lie in one output row (wide
+// strips) or one output column (narrow strips), a multiple of the phase period apart, so they normally share one weight
+// block and run fused.
 template <typename T, int FSC, int THREADS = STRIP_THREADS, int SPT = 1>
 __device__ __forceinline__ void strip_block(const StripArgs& a, const FrameSet& fsx, unsigned sb, float* __restrict__ tile)
 {
+    static_assert((SPT & (SPT - 1)) == 0 && (THREADS & (THREADS - 1)) == 0, "powers of two");
+    constexpr int SPT_L2 = SPT == 1 ? 0 : SPT == 2 ? 1 : SPT == 4 ? 2 : 3;
     const int fs = FSC > 0 ? FSC : a.fs;
     const unsigned plane = sb / a.blocks_per_plane;
     const unsigned pid = sb - plane * a.blocks_per_plane;
@@ -531,15 +556,20 @@ __device__ __forceinline__ void strip_block(const StripArgs& a, const FrameSet& 
     const int sx_lo = a.start_x[ox0], sy_lo = a.start_y[oy0];
     const int fw = a.start_x[ox0 + nx - 1] + fs - sx_lo, fh = a.start_y[oy0 + ny - 1] + fs - sy_lo;
     StripMeta meta[SPT];
+    unsigned live = 0;
+    {
+        // sample k of thread t: row mode (x, y) = (tx + k * PW/SPT, ty), column mode (tx, ty + k * PH/SPT)
+        const bool rows = a.row_mode[r] != 0;
+        const int txl = rows ? pwl - SPT_L2 : pwl; // log2 of the threads per patch row
+        const int tx = (int)threadIdx.x & ((1 << txl) - 1), ty = (int)threadIdx.x >> txl;
+        const int dx = rows ? 1 << txl : 0, dy = rows ? 0 : THREADS >> pwl;
 #pragma unroll
-    for (int k = 0; k < SPT; ++k) {
-        const int o = (int)threadIdx.x + k * THREADS;
-        const int lx = o & ((1 << pwl) - 1), ly = o >> pwl;
-        if (lx < nx && ly < ny) {
-            meta[k] = strip_meta<FSC>(a, ox0 + lx, oy0 + ly);
-        } else {
-            meta[k].x = -1;
-            meta[k].wstride = 0;
+        for (int k = 0; k < SPT; ++k) {
+            const int lx = tx + k * dx, ly = ty + k * dy;
+            if (lx < nx && ly < ny) {
+                meta[k] = strip_meta<FSC>(a, ox0 + lx, oy0 + ly);
+                live |= 1u << k;
+            }
         }
     }
     const unsigned n = (unsigned)(fw * fh);
@@ -548,16 +578,14 @@ __device__ __forceinline__ void strip_block(const StripArgs& a, const FrameSet& 
         const PlanePtrs& pp = frame_ptrs(fsx);
         const int pitch = (int)pp.src_pitch[plane];
         const T* __restrict__ src = static_cast<const T*>(pp.src[plane]) + (long long)sy_lo * pitch + sx_lo;
-        const float inv_fw = 1.f / (float)fw;
+        const unsigned magic = 0xFFFFFFFFu / (unsigned)fw + 1u; // floor(e / fw) = umulhi(e, magic) while e * fw < 2^32
         for (unsigned e0 = threadIdx.x; e0 < n; e0 += 4 * THREADS) {
             T v[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) { // all four loads are issued before the first conversion
                 const unsigned e = min(e0 + u * THREADS, n - 1);
-                unsigned row = (unsigned)__float2int_rd(((float)e + 0.5f) * inv_fw);
-                row -= (row * (unsigned)fw > e);
-                row += ((row + 1) * (unsigned)fw <= e);
-                v[u] = __ldg(src + (long long)row * pitch + (e - row * (unsigned)fw));
+                const unsigned row = __umulhi(e, magic);
+                v[u] = __ldg(src + (int)(row * (unsigned)pitch + (e - row * (unsigned)fw)));
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u)
@@ -566,20 +594,26 @@ __device__ __forceinline__ void strip_block(const StripArgs& a, const FrameSet& 
         }
         __syncthreads();
     }
+    if (live == 0)
+        return;
     if (SPT > 1 && staged) {
-        bool same = true;
-        const int fsp = (fs + 3) & ~3;
+        // samples outside the rectangle repeat sample 0 (computed, not stored), so a partly live thread stays fused
+        const int k0 = __ffs(live) - 1;
+        bool same = (meta[k0].wstride & 3) == 0 && meta[k0].wstride != 0;
 #pragma unroll
-        for (int k = 0; k < SPT; ++k)
-            same = same && meta[k].x >= 0 && meta[k].w == meta[0].w && meta[k].wstride == fsp;
+        for (int k = 0; k < SPT; ++k) {
+            if (!(live & (1u << k)))
+                meta[k] = meta[k0];
+            same = same && meta[k].w == meta[k0].w;
+        }
         if (same) {
-            strip_samples_fused<T, FSC, SPT>(a, fsx, meta, (int)plane, tile, fw, sx_lo, sy_lo);
+            strip_samples_fused<T, FSC, SPT>(a, fsx, meta, live, (int)plane, tile, fw, sx_lo, sy_lo);
             return;
         }
     }
 #pragma unroll
     for (int k = 0; k < SPT; ++k) {
-        if (meta[k].x < 0)
+        if (!(live & (1u << k)))
             continue;
         if (staged && meta[k].wstride)
             strip_sample_staged<T, FSC>(a, fsx, meta[k], (int)plane, tile, fw, sx_lo, sy_lo);
@@ -629,6 +663,7 @@ inline long long set_strip_rects(StripArgs& a, const Rect* rects, int n_rects, i
             ++pwl;
         const long long pw = 1ll << pwl, ph = outputs / pw;
         a.rect[k] = rects[r];
+        a.row_mode[k] = w >= h ? 1 : 0; // top/bottom strips are wide, left/right strips are tall
         a.pw_log2[k] = pwl;
         a.patches_x[k] = (unsigned)((w + pw - 1) / pw);
         a.patch_begin[k] = total;
@@ -637,6 +672,7 @@ inline long long set_strip_rects(StripArgs& a, const Rect* rects, int n_rects, i
     }
     for (int j = k; j < 4; ++j) {
         a.rect[j] = Rect{0, 0, 1, 1};
+        a.row_mode[j] = 1;
         a.pw_log2[j] = 3;
         a.patches_x[j] = 1;
         a.patch_begin[j] = total;
@@ -722,7 +758,7 @@ constexpr int DN_TW = 64;  // output columns per tile
 constexpr int DN_TH = 32;  // output rows per tile (integer formats; float tiles are half as tall)
 
 constexpr int DN_STRIP_SPT = 2;    // strip role: outputs per thread, patches at most 64 wide (the windows are wide)
-constexpr int DN_STRIP_MAX_PW = 256;
+constexpr int DN_STRIP_MAX_PW = 64;
 
 enum { DN_CVT_I2F = 0, DN_CVT_PRMT = 1, DN_CVT_FLOAT = 2 };
 

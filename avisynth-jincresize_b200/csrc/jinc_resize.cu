@@ -83,6 +83,7 @@ void fill_strip_args(const jinc_table* t, StripArgs& a)
     a.pos_x = t->ax[0].pos;
     a.pos_y = t->ax[1].pos;
     a.weights = t->d_weights;
+    a.weights_p = t->d_weights_p;
     a.lut = t->d_lut;
     a.border_sum = t->d_border_sum;
     a.border_w = t->d_border_w;

@@ -560,6 +560,19 @@ int jinc_table_build_device(jinc_table* t, const double* lut)
                                   cudaMemcpyDeviceToHost, st));
     }
     JINC_CUDA(cudaStreamSynchronize(st));
+    if (!t->h_weights.empty()) {
+        // the strip role reads weight rows as 16-byte vectors: a second copy with padded rows
+        const int fsp = (s.fs + 3) & ~3;
+        std::vector<float> padded(n_blocks * s.fs * fsp, 0.f);
+        for (size_t b = 0; b < n_blocks; ++b)
+            for (int ly = 0; ly < s.fs; ++ly)
+                memcpy(&padded[(b * s.fs + ly) * fsp], &t->h_weights[b * taps + (size_t)ly * s.fs], s.fs * sizeof(float));
+        if (int rc = dev_alloc(&t->d_weights_p, padded.size()))
+            return rc;
+        JINC_CUDA(cudaMemcpy(t->d_weights_p, padded.data(), padded.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    if (t->bgeom.total >= (1ll << 31))
+        return jinc_fail(JINC_E_UNSUPPORTED, "jinc_table: %lld border pixels exceed the 32-bit slot index", t->bgeom.total);
     return JINC_OK;
 }
 
@@ -617,6 +630,7 @@ extern "C" void jinc_table_destroy(jinc_table* t)
     }
     cudaFree(t->d_lut);
     cudaFree(t->d_weights);
+    cudaFree(t->d_weights_p);
     cudaFree(t->d_border_sum);
     cudaFree(t->d_border_w);
     cudaFree(t->d_border_block);
