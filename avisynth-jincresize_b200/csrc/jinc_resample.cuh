@@ -558,17 +558,55 @@ __device__ __forceinline__ void strip_block(const StripArgs& a, const FrameSet& 
     StripMeta meta[SPT];
     unsigned live = 0;
     {
-        // sample k of thread t: row mode (x, y) = (tx + k * PW/SPT, ty), column mode (tx, ty + k * PH/SPT)
+        // sample k of thread t: row mode (x, y) = (tx + k * PW/SPT, ty), column mode (tx, ty + k * PH/SPT).  The live
+        // samples of a thread are a prefix (coordinates grow with k).  The axis tables are read once per distinct
+        // coordinate: SPT + 1 positions instead of 2 SPT.
         const bool rows = a.row_mode[r] != 0;
         const int txl = rows ? pwl - SPT_L2 : pwl; // log2 of the threads per patch row
         const int tx = (int)threadIdx.x & ((1 << txl) - 1), ty = (int)threadIdx.x >> txl;
         const int dx = rows ? 1 << txl : 0, dy = rows ? 0 : THREADS >> pwl;
+        const int fsp = (fs + 3) & ~3;
+        int sxv[SPT], rxv[SPT], syv[SPT], ryv[SPT];
 #pragma unroll
         for (int k = 0; k < SPT; ++k) {
             const int lx = tx + k * dx, ly = ty + k * dy;
             if (lx < nx && ly < ny) {
-                meta[k] = strip_meta<FSC>(a, ox0 + lx, oy0 + ly);
                 live |= 1u << k;
+                if (k == 0 || rows) {
+                    sxv[k] = a.start_x[ox0 + lx];
+                    rxv[k] = a.rank_x[ox0 + lx];
+                } else {
+                    sxv[k] = sxv[0];
+                    rxv[k] = rxv[0];
+                }
+                if (k == 0 || !rows) {
+                    syv[k] = a.start_y[oy0 + ly];
+                    ryv[k] = a.rank_y[oy0 + ly];
+                } else {
+                    syv[k] = syv[0];
+                    ryv[k] = ryv[0];
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < SPT; ++k) {
+            if (!(live & (1u << k)))
+                continue;
+            StripMeta& m = meta[k];
+            m.x = ox0 + tx + k * dx;
+            m.y = oy0 + ty + k * dy;
+            m.sx = sxv[k];
+            m.sy = syv[k];
+            if (rxv[k] >= 0 && ryv[k] >= 0) { // rank is -1 exactly on border coordinates
+                const unsigned blk = (unsigned)(ryv[k] * a.n_rank_x + rxv[k]);
+                m.w = a.weights_p ? a.weights_p + blk * (unsigned)(fs * fsp) : a.weights + blk * (unsigned)(fs * fs);
+                m.wstride = a.weights_p ? fsp : fs;
+            } else if (a.border_block) {
+                m.w = a.border_wb + (unsigned)a.border_block[border_slot32(a.bg, m.x, m.y)] * (unsigned)(fs * fsp);
+                m.wstride = fsp;
+            } else {
+                m.w = nullptr;
+                m.wstride = 0;
             }
         }
     }
@@ -594,17 +632,16 @@ __device__ __forceinline__ void strip_block(const StripArgs& a, const FrameSet& 
         }
         __syncthreads();
     }
-    if (live == 0)
-        return;
+    if (!(live & 1u))
+        return; // live samples are a prefix
     if (SPT > 1 && staged) {
         // samples outside the rectangle repeat sample 0 (computed, not stored), so a partly live thread stays fused
-        const int k0 = __ffs(live) - 1;
-        bool same = (meta[k0].wstride & 3) == 0 && meta[k0].wstride != 0;
+        bool same = (meta[0].wstride & 3) == 0 && meta[0].wstride != 0;
 #pragma unroll
-        for (int k = 0; k < SPT; ++k) {
+        for (int k = 1; k < SPT; ++k) {
             if (!(live & (1u << k)))
-                meta[k] = meta[k0];
-            same = same && meta[k].w == meta[k0].w;
+                meta[k] = meta[0];
+            same = same && meta[k].w == meta[0].w;
         }
         if (same) {
             strip_samples_fused<T, FSC, SPT>(a, fsx, meta, live, (int)plane, tile, fw, sx_lo, sy_lo);
