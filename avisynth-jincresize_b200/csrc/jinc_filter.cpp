@@ -108,6 +108,16 @@ struct DeviceState {
     int batch_next = 0;
 };
 
+// rows of one plane between host and device: ONE linear transfer when both sides are tightly packed (the DMA engine
+// then moves a single extent instead of a descriptor per row), else a 2-D copy
+cudaError_t copy_plane_async(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t row_bytes, int rows,
+                             cudaMemcpyKind kind, cudaStream_t st)
+{
+    if (dst_pitch == row_bytes && src_pitch == row_bytes)
+        return cudaMemcpyAsync(dst, src, row_bytes * static_cast<size_t>(rows), kind, st);
+    return cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, row_bytes, static_cast<size_t>(rows), kind, st);
+}
+
 bool is_pinned_host(const void* p)
 {
     cudaPointerAttributes at;
@@ -284,8 +294,8 @@ int enqueue_frame(jinc_filter* f, Slot* s, const jinc_frame* frame, int y0_luma,
                 hsrc = stage;
                 hpitch = pl.src_pitch;
             }
-            JINC_CUDA(cudaMemcpy2DAsync(s->d_src + pl.src_off + static_cast<size_t>(sy0[i]) * pl.src_pitch, pl.src_pitch, hsrc,
-                                        hpitch, static_cast<size_t>(pl.src_w) * sb, rows, cudaMemcpyHostToDevice, s->stream));
+            JINC_CUDA(copy_plane_async(s->d_src + pl.src_off + static_cast<size_t>(sy0[i]) * pl.src_pitch, pl.src_pitch, hsrc, hpitch,
+                                       static_cast<size_t>(pl.src_w) * sb, rows, cudaMemcpyHostToDevice, s->stream));
         }
     }
 
@@ -338,8 +348,8 @@ int enqueue_frame(jinc_filter* f, Slot* s, const jinc_frame* frame, int y0_luma,
                 hdst = s->h_dst + pl.dst_off + static_cast<size_t>(oy0[i]) * pl.dst_pitch;
                 hpitch = pl.dst_pitch;
             }
-            JINC_CUDA(cudaMemcpy2DAsync(hdst, hpitch, s->d_dst + pl.dst_off + static_cast<size_t>(oy0[i]) * pl.dst_pitch,
-                                        pl.dst_pitch, static_cast<size_t>(pl.dst_w) * sb, rows, cudaMemcpyDeviceToHost, s->stream));
+            JINC_CUDA(copy_plane_async(hdst, hpitch, s->d_dst + pl.dst_off + static_cast<size_t>(oy0[i]) * pl.dst_pitch, pl.dst_pitch,
+                                       static_cast<size_t>(pl.dst_w) * sb, rows, cudaMemcpyDeviceToHost, s->stream));
         }
     }
     JINC_CUDA(cudaEventRecord(s->done, s->stream));

@@ -262,7 +262,7 @@ def run_b200(args, cfg):
     flt = capi.Filter(src_w=w, src_h=h, target_w=tw, target_h=th, n_planes=len(fmt.planes), sample_bytes=sb, bits=fmt.bits,
                       sub_w=sw, sub_h=sh, src_left=kw.get("src_left", 0.0), src_top=kw.get("src_top", 0.0),
                       quant_x=kw.get("quant_x", 256), quant_y=kw.get("quant_y", 256), tap=cfg["tap"],
-                      blur=kw.get("blur", 0.0), cplace=kw.get("cplace", "mpeg2"), devices=[local_rank], slots_per_device=3)
+                      blur=kw.get("blur", 0.0), cplace=kw.get("cplace", "mpeg2"), devices=[local_rank], slots_per_device=args.inflight)
     infos = [flt.table(k).info for k in range(flt.num_tables)]
     fs_l = infos[0].filter_size
     fs_c = infos[-1].filter_size
@@ -349,7 +349,7 @@ def run_b200(args, cfg):
     def e2e_step():
         tickets = []
         for f in range(F):
-            if len(tickets) >= 3:
+            if len(tickets) >= args.inflight:
                 flt.wait(tickets.pop(0))
             tickets.append(flt.submit_raw(raw[f]))
         for t in tickets:
@@ -405,7 +405,7 @@ def run_b200(args, cfg):
                        "l2": "inputs larger than L2: every step walks %d distinct frames (%.0f MB of planes)" % (F, F * byts / 1e6),
                        "partition": "frame-parallel, one process per GPU, no collective"},
             "e2e": {"value": e2e_value, "unit": "Mpixel/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "jinc_filter_submit/jinc_filter_wait (C ABI host-frame call, 3 frames in flight per GPU), pinned host planes",
+                    "api": "jinc_filter_submit/jinc_filter_wait (C ABI host-frame call, %d frames in flight per GPU), pinned host planes" % args.inflight,
                     "ms_per_step": e2e_s / args.steps * 1e3,
                     "pcie_gbs": (h2d + d2h) * args.steps / e2e_s / 1e9},
             "gpu_launches": gpu_launches,
@@ -435,6 +435,7 @@ def main():
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--inflight", type=int, default=3, help="frames in flight per GPU in the end-to-end leg (= pipeline slots)")
     ap.add_argument("--parts", type=int, default=3, choices=[1, 2, 3],
                     help="diagnosis only: 1 = interior tiles, 2 = border strips, 3 = both (the only valid bench setting)")
     args = ap.parse_args()
