@@ -89,7 +89,7 @@ struct jinc_table {
     float* d_lut = nullptr;      // JINC_LUT_SAMPLES floats (Lut::GetFactor values)
     float* d_weights = nullptr;  // [n_rank_y][n_rank_x][fs*fs] normalised phase blocks
     std::vector<float> h_weights; // host copy (kernel parameters for the fast paths)
-    float* d_weights_p = nullptr; // few-phase tables: the blocks again as [block][fs][fsp], fsp = fs rounded up to 4 (strip role)
+    float* d_weights_p = nullptr; // the blocks again as [block][fs][fsp], fsp = fs rounded up to 4 (null: fs % 4 == 0 or over budget)
     BorderGeom bgeom{};          // strips of border pixels
     float* d_border_sum = nullptr; // [bgeom.total] per-border-pixel normaliser
     float* d_border_w = nullptr;   // [bgeom.total/32][fs*fs][32] resident per-pixel border weights (null: rebuilt on the fly)

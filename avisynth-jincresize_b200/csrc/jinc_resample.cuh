@@ -484,40 +484,51 @@ __device__ __forceinline__ void strip_sample_staged(const StripArgs& a, const Fr
     static_cast<T*>(pp.dst[plane])[(long long)m.y * pp.dst_pitch[plane] + m.x] = finish<T>(acc, fsx.peak);
 }
 
-// SPT samples of one thread that share ONE class block (the usual case in the strips of the periodic geometries: a
-// thread's samples lie in the same border row or column, a multiple of the phase period apart): the weights are loaded
-// once and feed SPT independent accumulators.
-template <typename T, int FSC, int SPT>
+// The SPT samples of one thread, interleaved (SPT independent accumulator chains).  SHARED: they share ONE weight block
+// (the usual case in the strips of the periodic geometries: a thread's samples lie in the same border row or column, a
+// multiple of the phase period apart), so every weight vector is loaded once; otherwise each sample reads its own
+// block (general ratios).  All blocks have rows padded to 16 bytes and the same row stride.
+template <typename T, int FSC, int SPT, bool SHARED>
 __device__ __forceinline__ void strip_samples_fused(const StripArgs& a, const FrameSet& fsx, const StripMeta (&m)[SPT], unsigned live,
                                                     int plane, const float* __restrict__ tile, int fw, int sx_lo, int sy_lo)
 {
     const int fs = FSC > 0 ? FSC : a.fs;
+    constexpr int NW = SHARED ? 1 : SPT;
     const float* __restrict__ s[SPT];
+    const float4* __restrict__ w4[NW];
     float acc[SPT];
 #pragma unroll
     for (int k = 0; k < SPT; ++k) {
         s[k] = tile + (m[k].sy - sy_lo) * fw + (m[k].sx - sx_lo);
         acc[k] = 0.f;
     }
-    const float4* __restrict__ w4 = reinterpret_cast<const float4*>(m[0].w); // rows padded to 16 bytes
+#pragma unroll
+    for (int k = 0; k < NW; ++k)
+        w4[k] = reinterpret_cast<const float4*>(m[k].w); // rows padded to 16 bytes
     const int wq = m[0].wstride / 4;
     for (int ly = 0; ly < fs; ++ly) {
 #pragma unroll
         for (int q = 0; q < (FSC > 0 ? (FSC + 3) / 4 : wq); ++q) {
-            const float4 t = __ldg(w4 + q);
+            float4 t[NW];
+#pragma unroll
+            for (int k = 0; k < NW; ++k)
+                t[k] = __ldg(w4[k] + q);
             const int lx = 4 * q;
 #pragma unroll
             for (int k = 0; k < SPT; ++k) {
-                acc[k] = fmaf(s[k][lx], t.x, acc[k]);
+                const float4& tk = t[SHARED ? 0 : k];
+                acc[k] = fmaf(s[k][lx], tk.x, acc[k]);
                 if (lx + 1 < fs)
-                    acc[k] = fmaf(s[k][lx + 1], t.y, acc[k]);
+                    acc[k] = fmaf(s[k][lx + 1], tk.y, acc[k]);
                 if (lx + 2 < fs)
-                    acc[k] = fmaf(s[k][lx + 2], t.z, acc[k]);
+                    acc[k] = fmaf(s[k][lx + 2], tk.z, acc[k]);
                 if (lx + 3 < fs)
-                    acc[k] = fmaf(s[k][lx + 3], t.w, acc[k]);
+                    acc[k] = fmaf(s[k][lx + 3], tk.w, acc[k]);
             }
         }
-        w4 += wq;
+#pragma unroll
+        for (int k = 0; k < NW; ++k)
+            w4[k] += wq;
 #pragma unroll
         for (int k = 0; k < SPT; ++k)
             s[k] += fw;
@@ -636,15 +647,19 @@ __device__ __forceinline__ void strip_block(const StripArgs& a, const FrameSet& 
         return; // live samples are a prefix
     if (SPT > 1 && staged) {
         // samples outside the rectangle repeat sample 0 (computed, not stored), so a partly live thread stays fused
-        bool same = (meta[0].wstride & 3) == 0 && meta[0].wstride != 0;
+        bool same = true, vec = true;
 #pragma unroll
-        for (int k = 1; k < SPT; ++k) {
+        for (int k = 0; k < SPT; ++k) {
             if (!(live & (1u << k)))
                 meta[k] = meta[0];
             same = same && meta[k].w == meta[0].w;
+            vec = vec && meta[k].wstride != 0 && (meta[k].wstride & 3) == 0 && meta[k].wstride == meta[0].wstride;
         }
-        if (same) {
-            strip_samples_fused<T, FSC, SPT>(a, fsx, meta, live, (int)plane, tile, fw, sx_lo, sy_lo);
+        if (vec) {
+            if (same)
+                strip_samples_fused<T, FSC, SPT, true>(a, fsx, meta, live, (int)plane, tile, fw, sx_lo, sy_lo);
+            else
+                strip_samples_fused<T, FSC, SPT, false>(a, fsx, meta, live, (int)plane, tile, fw, sx_lo, sy_lo);
             return;
         }
     }

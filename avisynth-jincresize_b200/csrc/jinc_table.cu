@@ -26,6 +26,7 @@ namespace {
 
 constexpr int kAxisThreads = 1024;
 constexpr size_t kBorderWeightBudget = (size_t)8 << 30; // resident per-pixel border weights per table
+constexpr size_t kPaddedWeightBudget = (size_t)1 << 30; // second copy of the phase blocks with 16-byte rows
 
 struct AxisKernelArgs {
     float* pos;
@@ -124,6 +125,17 @@ __global__ void __launch_bounds__(kAxisThreads) axis_kernel(AxisKernelArgs ax0, 
         const int begin = __float2int_rz(__fadd_rn(qpos, a.support)) - a.fs + 1;
         a.rep_d2[r * a.fs + l] = jinc_tap_dist2(qpos, a.src_n, begin + l, a.filt_step);
     }
+}
+
+// weight rows padded to 16 bytes (pad = 0)
+__global__ void __launch_bounds__(256) pad_rows_kernel(float* __restrict__ out, const float* __restrict__ in, size_t rows, int fs, int fsp)
+{
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= rows * fsp)
+        return;
+    const size_t r = i / fsp;
+    const int c = (int)(i - r * fsp);
+    out[i] = c < fs ? in[r * fs + c] : 0.f;
 }
 
 // K3: one block per used phase pair (ry, rx).
@@ -560,16 +572,21 @@ int jinc_table_build_device(jinc_table* t, const double* lut)
                                   cudaMemcpyDeviceToHost, st));
     }
     JINC_CUDA(cudaStreamSynchronize(st));
-    if (!t->h_weights.empty()) {
-        // the strip role reads weight rows as 16-byte vectors: a second copy with padded rows
+    if (n_blocks > 0 && (s.fs & 3) != 0) {
+        // the strip role and the general kernel read weight rows as 16-byte vectors: a second copy with padded rows,
+        // [block][fs][fsp], while it fits the budget (many-phase tables reach 65536 blocks)
         const int fsp = (s.fs + 3) & ~3;
-        std::vector<float> padded(n_blocks * s.fs * fsp, 0.f);
-        for (size_t b = 0; b < n_blocks; ++b)
-            for (int ly = 0; ly < s.fs; ++ly)
-                memcpy(&padded[(b * s.fs + ly) * fsp], &t->h_weights[b * taps + (size_t)ly * s.fs], s.fs * sizeof(float));
-        if (int rc = dev_alloc(&t->d_weights_p, padded.size()))
-            return rc;
-        JINC_CUDA(cudaMemcpy(t->d_weights_p, padded.data(), padded.size() * sizeof(float), cudaMemcpyHostToDevice));
+        const size_t padded_floats = n_blocks * s.fs * fsp;
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        if (padded_floats * sizeof(float) <= kPaddedWeightBudget && padded_floats * sizeof(float) < free_b / 4) {
+            if (int rc = dev_alloc(&t->d_weights_p, padded_floats))
+                return rc;
+            const size_t rows = n_blocks * s.fs;
+            pad_rows_kernel<<<(unsigned)((rows * fsp + 255) / 256), 256, 0, st>>>(t->d_weights_p, t->d_weights, rows, s.fs, fsp);
+            JINC_CUDA(cudaGetLastError());
+            JINC_CUDA(cudaStreamSynchronize(st));
+        }
     }
     if (t->bgeom.total >= (1ll << 31))
         return jinc_fail(JINC_E_UNSUPPORTED, "jinc_table: %lld border pixels exceed the 32-bit slot index", t->bgeom.total);

@@ -117,7 +117,7 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -159,6 +159,18 @@ def measured_peaks():
         d = json.load(open(p))
         return d.get("hbm_gbs"), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(config_id: int, frames: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel's launch, from the committed `ncu --set full`
+    capture of the same bench command (profiles/ncu_traffic.json); None when no capture exists for this workload."""
+    try:
+        rec = json.load(open(os.path.join(REPO, "profiles", "ncu_traffic.json"))).get(str(config_id))
+        if rec and rec.get("frames_per_launch") == frames:
+            return float(rec["dram_bytes_per_launch"])
+    except Exception:
+        pass
+    return None
 
 
 def fma_peak_tflops():
@@ -412,7 +424,7 @@ def run_b200(args, cfg):
             "clocks": clocks,
             "roofline": {"bound": "fp32_fma", "kernel": {1: "resample_up2x", 2: "resample_down"}.get(i0.fast_path, "resample_strips") + " (luma-table planes of all %d frames: interior tiles + border strips)" % F,
                          "achieved": achieved_tf, "peak": fma_peak, "unit": "TFLOP/s", "frac": achieved_tf / fma_peak,
-                         "peak_source": fma_how, "traffic": None, "launch_ms": dom_avg_ms,
+                         "peak_source": fma_how, "traffic": ncu_traffic(args.config, F), "launch_ms": dom_avg_ms,
                          "algorithmic_flop_per_launch": dom_flop, "share_of_step": sum(dom_ms) / ms_total},
             "roofline_hbm": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                              "frac": achieved_gbs / hbm_peak, "peak_source": hbm_how,
@@ -430,8 +442,8 @@ def run_b200(args, cfg):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

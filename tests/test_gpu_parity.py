@@ -169,3 +169,41 @@ def test_full_size_properties(capi):
                 assert_plane_close(got[pi][y0:y1], ref[y0:y1], False, f"full/{pi}/{y0}")
         t.close()
     flt.close()
+
+
+@pytest.mark.parametrize("dtype,bits,tap", [(np.uint8, 8, 3), (np.uint16, 16, 4), (np.float32, 32, 3)])
+def test_device_plane_call_with_unaligned_source(capi, dtype, bits, tap):
+    """jinc_resize_plane_device on planes the caller owns: a source whose base and pitch are NOT multiples of four
+    samples must take the scalar tile-staging path of the exact-2x kernel and still match the oracle (the frame
+    pipeline's own buffers are always vector-aligned, so only this entry point reaches it)."""
+    import torch
+
+    from oracle import cpu as oc
+
+    w, h, tw, th = 322, 181, 644, 362
+    sb = np.dtype(dtype).itemsize
+    fmt_peak = float((1 << bits) - 1) if bits < 32 else 0.0
+    rng = np.random.default_rng(7)
+    if bits == 32:
+        plane = rng.random((h, w), dtype=np.float32)
+    else:
+        plane = rng.integers(0, (1 << bits), (h, w)).astype(dtype)
+    pp = oc.plane_params(w, h, tw, th, tap=tap, sub_w=0, sub_h=0)
+    ot = oc.Table(pp[0], oc.make_lut(tap, 0.0))
+    ref = ot.resize(plane, fmt_peak)
+
+    ctx = capi.Context(0)
+    tab = capi.Table(ctx, src_w=w, src_h=h, dst_w=tw, dst_h=th, radius=oc.radius_for_tap(tap))
+    assert tab.info.fast_path == 1
+    tdt = {1: torch.uint8, 2: torch.uint16, 4: torch.float32}[sb]
+    for offset, pitch_elems in ((0, 336), (1, 325), (3, 323)):  # aligned, then two unaligned layouts
+        buf = torch.zeros(offset + pitch_elems * h + 8, dtype=tdt, device="cuda")
+        view = buf[offset:offset + pitch_elems * h].view(h, pitch_elems)
+        view[:, :w].copy_(torch.from_numpy(plane))
+        dpitch = (tw * sb + 63) // 64 * 64
+        dst = torch.zeros((th, dpitch // sb), dtype=tdt, device="cuda")
+        tab.resize_device(sb, fmt_peak, buf.data_ptr() + offset * sb, pitch_elems * sb, dst.data_ptr(), dpitch)
+        torch.cuda.synchronize()
+        got = dst[:, :tw].cpu().numpy()
+        assert_plane_close(got, ref, bits == 32, f"device plane offset={offset} pitch={pitch_elems}")
+    tab.close()
