@@ -809,7 +809,7 @@ inline size_t up2x_smem_bytes(int fs)
 constexpr int DN_TW = 64;  // output columns per tile
 constexpr int DN_TH = 32;  // output rows per tile (integer formats; float tiles are half as tall)
 
-constexpr int DN_STRIP_SPT = 2;    // strip role: outputs per thread, patches at most 64 wide (the windows are wide)
+constexpr int DN_STRIP_SPT = 4;    // strip role: outputs per thread (four independent accumulator chains), patches at most 64 wide (the windows are wide)
 constexpr int DN_STRIP_MAX_PW = 64;
 
 enum { DN_CVT_I2F = 0, DN_CVT_PRMT = 1, DN_CVT_FLOAT = 2 };
