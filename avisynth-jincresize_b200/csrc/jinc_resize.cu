@@ -36,11 +36,145 @@ constexpr int GEN_SPT = 4;                  // outputs per thread of the general
 constexpr int GEN_MAX_PW = 64;              // its patches are 64 x 16 outputs
 constexpr size_t GEN_SMEM = (size_t)96 << 10; // staging space (two blocks per SM)
 
-template <typename T>
-__global__ void __launch_bounds__(STRIP_THREADS) resample_strips(const __grid_constant__ GeneralArgs a)
+// General kernel: one block = one patch of 64 x 16 outputs of ALL NP planes that share the table.  Every output has its
+// own phase block (that is what "general ratio" means), so the weight stream from L1/L2 is the bottleneck: a thread
+// owns 4 outputs of one row and applies each float4 of weights to the same output of all NP planes (and the 4 outputs
+// run interleaved), which divides the weight traffic per sample by NP.  Falls back to the per-plane strip role when
+// the NP source footprints do not fit in shared memory or a sample has no vector-readable block.
+template <typename T, int NP>
+__global__ void __launch_bounds__(STRIP_THREADS) resample_strips(const __grid_constant__ GeneralArgs ga)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    strip_block<T, 0, STRIP_THREADS, GEN_SPT>(a.st, a.fr, blockIdx.x, reinterpret_cast<float*>(smem_raw));
+    float* __restrict__ tile = reinterpret_cast<float*>(smem_raw);
+    const StripArgs& a = ga.st;
+    constexpr int SPT = GEN_SPT, THREADS = STRIP_THREADS;
+    const int fs = a.fs;
+    const unsigned pid = blockIdx.x;
+    const unsigned pyi = pid / a.patches_x[0], pxi = pid - pyi * a.patches_x[0];
+    const int pwl = a.pw_log2[0];
+    const int ox0 = a.rect[0].x0 + (int)(pxi << pwl), oy0 = a.rect[0].y0 + (int)pyi * ((THREADS * SPT) >> pwl);
+    const int nx = min(1 << pwl, a.rect[0].x1 - ox0), ny = min((THREADS * SPT) >> pwl, a.rect[0].y1 - oy0);
+    const int sx_lo = a.start_x[ox0], sy_lo = a.start_y[oy0];
+    const int fw = a.start_x[ox0 + nx - 1] + fs - sx_lo, fh = a.start_y[oy0 + ny - 1] + fs - sy_lo;
+    const unsigned n = (unsigned)(fw * fh);
+
+    // this thread's outputs: (tx + k * PW/SPT, ty); live ones are a prefix
+    const int txl = pwl - 2;
+    const int tx = (int)threadIdx.x & ((1 << txl) - 1), ty = (int)threadIdx.x >> txl;
+    StripMeta meta[SPT];
+    unsigned live = 0;
+    bool vec = true;
+#pragma unroll
+    for (int k = 0; k < SPT; ++k) {
+        const int lx = tx + (k << txl);
+        if (lx < nx && ty < ny) {
+            meta[k] = strip_meta<0>(a, ox0 + lx, oy0 + ty);
+            live |= 1u << k;
+            vec = vec && meta[k].wstride != 0 && (meta[k].wstride & 3) == 0;
+        }
+    }
+    // the whole block takes one path: block-wide vote (every thread reaches it)
+    const bool fast = NP * n <= a.smem_floats && __syncthreads_and(vec ? 1 : 0) != 0;
+    if (!fast) {
+        for (int pl = 0; pl < NP; ++pl) {
+            __syncthreads(); // the previous plane's staged footprint is no longer read
+            strip_block<T, 0, THREADS, SPT>(a, ga.fr, (unsigned)pl * a.blocks_per_plane + pid, tile);
+        }
+        return;
+    }
+
+    const PlanePtrs& pp = frame_ptrs(ga.fr);
+    {
+        const unsigned magic = 0xFFFFFFFFu / (unsigned)fw + 1u; // floor(e / fw) = umulhi(e, magic) while e * fw < 2^32
+#pragma unroll
+        for (int pl = 0; pl < NP; ++pl) {
+            const int pitch = (int)pp.src_pitch[pl];
+            const T* __restrict__ src = static_cast<const T*>(pp.src[pl]) + (long long)sy_lo * pitch + sx_lo;
+            float* __restrict__ tp = tile + pl * n;
+            for (unsigned e0 = threadIdx.x; e0 < n; e0 += 4 * THREADS) {
+                T v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { // all four loads are issued before the first conversion
+                    const unsigned e = min(e0 + u * THREADS, n - 1);
+                    const unsigned row = __umulhi(e, magic);
+                    v[u] = __ldg(src + (int)(row * (unsigned)pitch + (e - row * (unsigned)fw)));
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (e0 + u * THREADS < n)
+                        tp[e0 + u * THREADS] = sample_to_float(v[u]);
+            }
+        }
+    }
+    __syncthreads();
+    if (!(live & 1u))
+        return;
+#pragma unroll
+    for (int k = 1; k < SPT; ++k)
+        if (!(live & (1u << k)))
+            meta[k] = meta[0]; // computed, not stored
+
+    const float* __restrict__ sp[SPT];
+    const float4* __restrict__ w4[SPT];
+    float acc[SPT][NP];
+#pragma unroll
+    for (int k = 0; k < SPT; ++k) {
+        sp[k] = tile + (meta[k].sy - sy_lo) * fw + (meta[k].sx - sx_lo);
+        w4[k] = reinterpret_cast<const float4*>(meta[k].w);
+#pragma unroll
+        for (int pl = 0; pl < NP; ++pl)
+            acc[k][pl] = 0.f;
+    }
+    const int wq = meta[0].wstride / 4; // the same for every block of the table
+    for (int ly = 0; ly < fs; ++ly) {
+        for (int q = 0; q < wq; ++q) {
+            float4 t[SPT];
+#pragma unroll
+            for (int k = 0; k < SPT; ++k)
+                t[k] = __ldg(w4[k] + q);
+            const int lx = 4 * q;
+#pragma unroll
+            for (int k = 0; k < SPT; ++k) {
+#pragma unroll
+                for (int pl = 0; pl < NP; ++pl) {
+                    const float* __restrict__ s = sp[k] + pl * n + lx;
+                    float v = acc[k][pl];
+                    v = fmaf(s[0], t[k].x, v);
+                    if (lx + 1 < fs)
+                        v = fmaf(s[1], t[k].y, v);
+                    if (lx + 2 < fs)
+                        v = fmaf(s[2], t[k].z, v);
+                    if (lx + 3 < fs)
+                        v = fmaf(s[3], t[k].w, v);
+                    acc[k][pl] = v;
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < SPT; ++k) {
+            w4[k] += wq;
+            sp[k] += fw;
+        }
+    }
+#pragma unroll
+    for (int pl = 0; pl < NP; ++pl) {
+        T* __restrict__ dst = static_cast<T*>(pp.dst[pl]);
+        const long long dp = pp.dst_pitch[pl];
+#pragma unroll
+        for (int k = 0; k < SPT; ++k)
+            if (live & (1u << k))
+                dst[(long long)meta[k].y * dp + meta[k].x] = finish<T>(acc[k][pl], ga.fr.peak);
+    }
+}
+
+template <typename T, int NP>
+cudaError_t launch_general_np(const GeneralArgs& ga, unsigned blocks, int n_frames, cudaStream_t st)
+{
+    cudaError_t e = cudaFuncSetAttribute(resample_strips<T, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEN_SMEM);
+    if (e != cudaSuccess)
+        return e;
+    resample_strips<T, NP><<<dim3(blocks, n_frames), STRIP_THREADS, GEN_SMEM, st>>>(ga);
+    return cudaGetLastError();
 }
 
 // weights of one output pixel exactly as the reference defines them (introspection for parity tests)
@@ -192,14 +326,16 @@ int launch_typed(const jinc_table* t, const FrameSet& fr, int n_frames, int y_be
     ga.fr = fr;
     ga.st = sa;
     rects[0] = Rect{0, y_begin, W, y_end};
-    const long long blocks = set_strip_rects(ga.st, rects, 1, STRIP_THREADS * GEN_SPT, GEN_MAX_PW, GEN_SMEM) * fr.n_planes;
+    const long long blocks = set_strip_rects(ga.st, rects, 1, STRIP_THREADS * GEN_SPT, GEN_MAX_PW, GEN_SMEM);
     if (blocks == 0)
         return JINC_OK;
-    cudaError_t e = cudaFuncSetAttribute(resample_strips<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEN_SMEM);
-    if (e != cudaSuccess)
-        return jinc_fail(JINC_E_CUDA, "cudaFuncSetAttribute(strips smem): %s", cudaGetErrorString(e));
-    resample_strips<T><<<dim3((unsigned)blocks, n_frames), STRIP_THREADS, GEN_SMEM, st>>>(ga);
-    e = cudaGetLastError();
+    cudaError_t e = cudaSuccess;
+    switch (fr.n_planes) { // one block covers the patch in every plane of the table
+    case 1: e = launch_general_np<T, 1>(ga, (unsigned)blocks, n_frames, st); break;
+    case 2: e = launch_general_np<T, 2>(ga, (unsigned)blocks, n_frames, st); break;
+    case 3: e = launch_general_np<T, 3>(ga, (unsigned)blocks, n_frames, st); break;
+    default: e = launch_general_np<T, 4>(ga, (unsigned)blocks, n_frames, st); break;
+    }
     if (e != cudaSuccess)
         return jinc_fail(JINC_E_CUDA, "resample_strips launch failed: %s", cudaGetErrorString(e));
     ++*launches;
