@@ -476,7 +476,13 @@ extern "C" int jinc_filter_create(const jinc_filter_params* p, jinc_filter** out
     f->src_bytes = so;
     f->dst_bytes = dof;
 
-    const int spd = p->slots_per_device > 0 ? p->slots_per_device : 3;
+    // frames in flight per GPU: a slot is held from the staging copy of the source until the output has been copied out,
+    // mostly host memcpy time for pageable callers, so small frames get more slots (3..8, about 512 MB per GPU)
+    int spd = p->slots_per_device;
+    if (spd <= 0) {
+        const size_t per_slot = std::max<size_t>(so + dof, 1);
+        spd = static_cast<int>(std::min<size_t>(8, std::max<size_t>(3, (static_cast<size_t>(512) << 20) / per_slot)));
+    }
     for (size_t di = 0; di < dev_ids.size(); ++di) {
         DeviceState d;
         int rc = jinc_ctx_create(dev_ids[di], &d.ctx);

@@ -249,6 +249,30 @@ def run_reference(cfg, steps: int, warmup: int, budget_s: float):
                 ms_per_step=dt * 1e3, steps=1, warmup=0, frames_per_step=rows / th)
 
 
+def run_plugin_e2e(cfg, threads: int, frames: int, steps: int, device: int):
+    """The drop-in path itself: the AviSynth+ C plugin (libjincresize_b200.so) under the mini-host, PAGEABLE host frames
+    in and out through get_frame, `threads` concurrent get_frame callers (what Prefetch(threads) does).  Includes the
+    plugin's staging copies into its pinned slots, H2D, kernels, D2H and the copy into the host's frame."""
+    fmt, w, h, tw, th = cfg["fmt"], cfg["w"], cfg["h"], cfg["tw"], cfg["th"]
+    os.environ["JINCRESIZE_B200_DEVICES"] = str(device)
+    env = ah.Env()
+    env.load_plugin(paths.b200_plugin())
+    src = env.source(fmt, w, h, [synth_frame(fmt, w, h, s) for s in range(min(frames, 4))], num_frames=1 << 20)
+    clip = env.invoke(cfg["fn"], src, tw, th, **cfg["kw"])
+    clip.pull(0, frames, threads)  # warm-up: table build, slot allocation, first-touch of the frame pool
+    f0 = frames
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        clip.pull(f0, frames, threads)
+        f0 += frames
+    dt = time.perf_counter() - t0
+    clip.release()
+    src.release()
+    return {"value": steps * frames * (tw * th / 1e6) / dt, "unit": "Mpixel/s", "threads": threads,
+            "api": "avisynth_c_plugin_init / get_frame under the mini-host, pageable frames, %d concurrent callers" % threads,
+            "ms_per_step": dt / steps * 1e3}
+
+
 # ------------------------------------------------------------------------------------------ GPU arm
 
 def run_b200(args, cfg):
@@ -404,6 +428,12 @@ def run_b200(args, cfg):
         achieved_gbs = dom_bytes / (dom_avg_ms * 1e-3) / 1e9
         h2d = sum(int(np.prod(s)) for s, _ in shapes) * sb * F
         d2h = sum(int(np.prod(d)) for _, d in shapes) * sb * F
+        plugin = None
+        if world == 1 and args.plugin_threads > 0:
+            try:
+                plugin = run_plugin_e2e(cfg, args.plugin_threads, F, max(1, min(args.steps, 5)), local_rank)
+            except Exception as ex:  # the C-ABI figures above stand on their own
+                plugin = {"error": str(ex)[:200]}
         cpu = None
         if world == 1 and not args.no_cpu:
             cpu = run_reference(cfg, steps=3, warmup=1, budget_s=25.0)
@@ -420,6 +450,7 @@ def run_b200(args, cfg):
                     "api": "jinc_filter_submit/jinc_filter_wait (C ABI host-frame call, %d frames in flight per GPU), pinned host planes" % args.inflight,
                     "ms_per_step": e2e_s / args.steps * 1e3,
                     "pcie_gbs": (h2d + d2h) * args.steps / e2e_s / 1e9},
+            "e2e_plugin": plugin,
             "gpu_launches": gpu_launches,
             "clocks": clocks,
             "roofline": {"bound": "fp32_fma", "kernel": {1: "resample_up2x", 2: "resample_down"}.get(i0.fast_path, "resample_strips") + " (luma-table planes of all %d frames: interior tiles + border strips)" % F,
@@ -447,6 +478,8 @@ def main():
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--plugin-threads", type=int, default=8,
+                    help="concurrent get_frame callers of the plugin end-to-end leg (N=1 only; 0 skips it)")
     ap.add_argument("--inflight", type=int, default=3, help="frames in flight per GPU in the end-to-end leg (= pipeline slots)")
     ap.add_argument("--parts", type=int, default=3, choices=[1, 2, 3],
                     help="diagnosis only: 1 = interior tiles, 2 = border strips, 3 = both (the only valid bench setting)")

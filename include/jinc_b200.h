@@ -144,7 +144,7 @@ typedef struct jinc_filter_params {
     int32_t bits;               /* bits per component (8..16, 32) -> peak (:793) */
     int32_t n_devices;          /* 0 => all visible devices */
     int32_t devices[JINC_MAX_DEVICES];
-    int32_t slots_per_device;   /* frames in flight per GPU (0 => 3) */
+    int32_t slots_per_device;   /* frames in flight per GPU (0 => 3..8, by frame size) */
 } jinc_filter_params;
 
 typedef struct jinc_frame {

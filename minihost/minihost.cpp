@@ -22,6 +22,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <variant>
 #include <vector>
 
@@ -231,6 +232,43 @@ AVSC_API(int, avs_get_plane_height_subsampling)(const AVS_VideoInfo* p, int plan
 
 /* ---------------------------------------------------------------- frames */
 
+/* Frame buffers are recycled through a small pool keyed by size, as AviSynth+'s frame cache does: a filter's output
+   frame normally reuses memory that is already mapped (fresh pages are zeroed once, when first allocated). */
+static std::mutex g_pool_mutex;
+static std::unordered_map<size_t, std::vector<void*>> g_pool;
+static const size_t kPoolPerSize = 64;
+
+static void* pool_get(size_t total)
+{
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mutex);
+        auto it = g_pool.find(total);
+        if (it != g_pool.end() && !it->second.empty()) {
+            void* p = it->second.back();
+            it->second.pop_back();
+            return p;
+        }
+    }
+    void* mem = nullptr;
+    if (posix_memalign(&mem, 64, total) != 0)
+        return nullptr;
+    memset(mem, 0, total);
+    return mem;
+}
+
+static void pool_put(void* p, size_t total)
+{
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mutex);
+        auto& v = g_pool[total];
+        if (v.size() < kPoolPerSize) {
+            v.push_back(p);
+            return;
+        }
+    }
+    free(p);
+}
+
 static AVS_VideoFrame* alloc_frame(const AVS_VideoInfo* vi, const AVS_VideoFrame* prop_src)
 {
     const int cs = avs_component_size(vi);
@@ -260,14 +298,11 @@ static AVS_VideoFrame* alloc_frame(const AVS_VideoInfo* vi, const AVS_VideoFrame
     total += 256; /* tail slack: SIMD readers may run past the last row */
 
     auto* vfb = new AVS_VideoFrameBuffer();
-    void* mem = nullptr;
-    if (posix_memalign(&mem, 64, total) != 0)
-        mem = nullptr;
+    void* mem = pool_get(total);
     if (!mem) {
         delete vfb;
         return nullptr;
     }
-    memset(mem, 0, total);
     vfb->data = static_cast<BYTE*>(mem);
     vfb->data_size = (int)total;
     vfb->sequence_number = 0;
@@ -304,7 +339,7 @@ AVSC_API(void, avs_release_video_frame)(AVS_VideoFrame* f)
     if (!f)
         return;
     if (__atomic_sub_fetch(&f->refcount, 1, __ATOMIC_SEQ_CST) == 0) {
-        free(f->vfb->data);
+        pool_put(f->vfb->data, (size_t)f->vfb->data_size);
         delete f->vfb;
         delete static_cast<PropMap*>(f->properties);
         delete f;

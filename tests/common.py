@@ -81,6 +81,10 @@ SMALL_CASES = [
     # exact 2x with the remaining alias taps and a third-size / 3x ratio (general kernel)
     ("up2x_tap6_420p8", ah.YUV420P8, 200, 120, 400, 240, dict(tap=6, cplace="mpeg1")),
     ("third_tap3_y8", ah.Format("y", 8), 600, 360, 200, 120, dict(tap=3)),
+    # general kernel with four planes on one table, and a steep irregular downscale whose source footprints do not fit
+    # in shared memory (per-plane fallback of the general kernel)
+    ("rgbap10_irregular_up", ah.Format("rgbap", 10), 200, 120, 290, 170, dict(tap=4)),
+    ("steep_down_444p16_tap5", ah.Format("444", 16), 900, 540, 200, 124, dict(tap=5)),
 ]
 
 
