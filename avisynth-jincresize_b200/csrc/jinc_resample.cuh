@@ -744,7 +744,7 @@ constexpr int UP_CW = 32 * UP_TX;            // cells per tile row (128 -> 256 o
 constexpr int UP_RPW = 2;                    // cell-row pairs per warp
 constexpr int UP_CH = 2 * UP_WARPS * UP_RPW; // cell rows per tile (32 -> 64 output rows)
 constexpr int UP_STRIP_SPT = 4;              // strip role: outputs per thread (patches of 1024 outputs, up to 256 wide)
-constexpr int UP_STRIP_MAX_PW = 1024;            // a thread's four samples share a border row: x, x + 256, ...
+constexpr int UP_STRIP_MAX_PW = 64;   // wide strips are cut into 64 x 8 patches: the rows of a strip share most of their source rows
 
 template <int FS>
 struct UpGeom {
