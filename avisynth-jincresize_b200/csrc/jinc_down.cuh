@@ -93,9 +93,9 @@ __global__ void __launch_bounds__((DownGeom<T, FS, Q, NX, NY>::THREADS), 2)
         return;
     }
     Word* tile = reinterpret_cast<Word*>(smem_raw); // [NROWP][D][SUB] (+pad): word (k, c) at k*RS + (c%D)*SUB + c/D
-    const int plane = role_id / a.tiles_per_plane;
+    const int plane = (int)div_by(role_id, a.tiles_per_plane_magic);
     const int tidx = role_id - plane * a.tiles_per_plane;
-    const int tile_y = tidx / a.tiles_x, tile_x = tidx - tile_y * a.tiles_x;
+    const int tile_y = (int)div_by((unsigned)tidx, a.tiles_x_magic), tile_x = tidx - tile_y * a.tiles_x;
     const PlanePtrs& pp = frame_ptrs(a.fr);
     const T* __restrict__ src = static_cast<const T*>(pp.src[plane]);
     T* __restrict__ dst = static_cast<T*>(pp.dst[plane]);
@@ -206,6 +206,8 @@ int launch_down_cfg(DownArgs& a, const DownWeights<FS, Q>& w, long long strip_bl
         strip_blocks_of ? set_strip_rects(a.st, rects, n_rects, G::THREADS * DN_STRIP_SPT, DN_STRIP_MAX_PW, G::SMEM) * a.fr.n_planes : 0;
     a.tiles_x = (a.x1 - a.x0 + DN_TW - 1) / DN_TW;
     a.tiles_per_plane = a.tiles_x * ((a.y1 - a.y0 + G::TH - 1) / G::TH);
+    a.tiles_x_magic = div_magic((unsigned)a.tiles_x);
+    a.tiles_per_plane_magic = div_magic((unsigned)a.tiles_per_plane);
     if (a.interior_blocks)
         a.interior_blocks = a.tiles_per_plane * a.fr.n_planes;
     auto kern = resample_down<T, FS, Q, NX, NY, CVT>;

@@ -167,6 +167,11 @@ __device__ __forceinline__ void store8<uint8_t>(uint8_t* p, const float (&v)[8],
     *reinterpret_cast<uint2*>(p) = make_uint2(q[0], q[1]);
 }
 
+// Division of a small block index by a launch constant without the ~20-instruction integer-division sequence:
+// floor(n / d) = umulhi(n, ceil(2^32 / d)) as long as n * d < 2^32 (grids here stay far below that).
+inline unsigned div_magic(unsigned d) { return d <= 1 ? 0u : (unsigned)((0x100000000ull + d - 1) / d); }
+__device__ __forceinline__ unsigned div_by(unsigned n, unsigned magic) { return magic ? __umulhi(n, magic) : n; }
+
 // ------------------------------------------------------------------------------------------ shared argument blocks
 
 struct Rect {
@@ -214,6 +219,7 @@ struct StripArgs {
     int pw_log2[4];            // log2 of the patch width (patch height = outputs per block / width)
     int row_mode[4];           // 1: a thread's samples lie in one output row (top/bottom strips), 0: in one column
     unsigned blocks_per_plane; // = patch_begin[4]; the grid holds this many strip blocks per plane
+    unsigned blocks_per_plane_magic, patches_x_magic[4]; // div_magic of the two divisors above
     unsigned smem_floats;      // shared memory a strip block may use to stage its source footprint (0: none)
 };
 
@@ -554,11 +560,11 @@ __device__ __forceinline__ void strip_block(const StripArgs& a, const FrameSet& 
     static_assert((SPT & (SPT - 1)) == 0 && (THREADS & (THREADS - 1)) == 0, "powers of two");
     constexpr int SPT_L2 = SPT == 1 ? 0 : SPT == 2 ? 1 : SPT == 4 ? 2 : 3;
     const int fs = FSC > 0 ? FSC : a.fs;
-    const unsigned plane = sb / a.blocks_per_plane;
+    const unsigned plane = div_by(sb, a.blocks_per_plane_magic);
     const unsigned pid = sb - plane * a.blocks_per_plane;
     const int r = (int)(pid >= a.patch_begin[1]) + (int)(pid >= a.patch_begin[2]) + (int)(pid >= a.patch_begin[3]);
     const unsigned lp = pid - a.patch_begin[r];
-    const unsigned pyi = lp / a.patches_x[r], pxi = lp - pyi * a.patches_x[r];
+    const unsigned pyi = div_by(lp, a.patches_x_magic[r]), pxi = lp - pyi * a.patches_x[r];
     const int pwl = a.pw_log2[r];
     const int ox0 = a.rect[r].x0 + (int)(pxi << pwl), oy0 = a.rect[r].y0 + (int)pyi * ((THREADS * SPT) >> pwl);
     const int nx = min(1 << pwl, a.rect[r].x1 - ox0), ny = min((THREADS * SPT) >> pwl, a.rect[r].y1 - oy0);
@@ -718,6 +724,7 @@ inline long long set_strip_rects(StripArgs& a, const Rect* rects, int n_rects, i
         a.row_mode[k] = w >= h ? 1 : 0; // top/bottom strips are wide, left/right strips are tall
         a.pw_log2[k] = pwl;
         a.patches_x[k] = (unsigned)((w + pw - 1) / pw);
+        a.patches_x_magic[k] = div_magic(a.patches_x[k]);
         a.patch_begin[k] = total;
         total += a.patches_x[k] * (unsigned)((h + ph - 1) / ph);
         ++k;
@@ -727,10 +734,12 @@ inline long long set_strip_rects(StripArgs& a, const Rect* rects, int n_rects, i
         a.row_mode[j] = 1;
         a.pw_log2[j] = 3;
         a.patches_x[j] = 1;
+        a.patches_x_magic[j] = div_magic(1);
         a.patch_begin[j] = total;
     }
     a.patch_begin[4] = total;
     a.blocks_per_plane = total;
+    a.blocks_per_plane_magic = div_magic(total);
     a.smem_floats = (unsigned)(smem_bytes / sizeof(float));
     return total;
 }
@@ -770,6 +779,7 @@ struct UpArgs {
     int sx0, sy0;         // window origin of cell (0,0), phase (0,0)
     int cy_begin, cy_end; // cell rows to produce (row-band split)
     int tiles_x, tiles_per_plane, interior_blocks; // interior_blocks = tiles_per_plane * n_planes
+    unsigned tiles_x_magic, tiles_per_plane_magic; // div_magic of the two tile divisors
     int strip_blocks, strip_shift;
 };
 
@@ -862,6 +872,7 @@ struct DownArgs {
     int x0, y0, x1, y1;  // output rectangle produced by the tiles (y0..y1 already cut to the row band)
     int tsx0, tsy0;      // window origin of output (x0, y0)
     int tiles_x, tiles_per_plane, interior_blocks, strip_blocks, strip_shift;
+    unsigned tiles_x_magic, tiles_per_plane_magic; // div_magic of the two tile divisors
     int pre_shift;       // PRMT conversion: samples are staged as x << pre_shift
     float bias_even, bias_odd, out_scale; // PRMT conversion: out = ((acc.x - bias_even) + (acc.y - bias_odd)) * out_scale
 };

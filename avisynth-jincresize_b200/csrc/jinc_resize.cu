@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(STRIP_THREADS) resample_strips(const __grid_co
     constexpr int SPT = GEN_SPT, THREADS = STRIP_THREADS;
     const int fs = a.fs;
     const unsigned pid = blockIdx.x;
-    const unsigned pyi = pid / a.patches_x[0], pxi = pid - pyi * a.patches_x[0];
+    const unsigned pyi = div_by(pid, a.patches_x_magic[0]), pxi = pid - pyi * a.patches_x[0];
     const int pwl = a.pw_log2[0];
     const int ox0 = a.rect[0].x0 + (int)(pxi << pwl), oy0 = a.rect[0].y0 + (int)pyi * ((THREADS * SPT) >> pwl);
     const int nx = min(1 << pwl, a.rect[0].x1 - ox0), ny = min((THREADS * SPT) >> pwl, a.rect[0].y1 - oy0);
@@ -276,6 +276,8 @@ int launch_typed(const jinc_table* t, const FrameSet& fr, int n_frames, int y_be
             a.cy_end = ce;
             a.tiles_x = (u.ncx + UP_CW - 1) / UP_CW;
             a.tiles_per_plane = a.tiles_x * ((ce - cb + UP_CH - 1) / UP_CH);
+            a.tiles_x_magic = div_magic((unsigned)a.tiles_x);
+            a.tiles_per_plane_magic = div_magic((unsigned)a.tiles_per_plane);
             a.interior_blocks = (parts & JINC_PART_INTERIOR) ? a.tiles_per_plane * fr.n_planes : 0;
             if (a.interior_blocks + strip_blocks == 0)
                 return JINC_OK;

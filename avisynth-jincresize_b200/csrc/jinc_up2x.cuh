@@ -61,9 +61,9 @@ __global__ void __launch_bounds__(UP_THREADS, (FS >= 13 ? 4 : 6))
 
     // -------------------- interior tile role
     float2* tile = reinterpret_cast<float2*>(smem_raw); // [NR][4][SUB] pairs {S[r][c], S[r+1][c]}
-    const int plane = role_id / a.tiles_per_plane;
+    const int plane = (int)div_by(role_id, a.tiles_per_plane_magic);
     const int tidx = role_id - plane * a.tiles_per_plane;
-    const int tile_y = tidx / a.tiles_x, tile_x = tidx - tile_y * a.tiles_x;
+    const int tile_y = (int)div_by((unsigned)tidx, a.tiles_x_magic), tile_x = tidx - tile_y * a.tiles_x;
     const PlanePtrs& pp = frame_ptrs(a.fr);
     const T* __restrict__ src = static_cast<const T*>(pp.src[plane]);
     T* __restrict__ dst = static_cast<T*>(pp.dst[plane]);
