@@ -81,6 +81,10 @@ SMALL_CASES = [
     # exact 2x with the remaining alias taps and a third-size / 3x ratio (general kernel)
     ("up2x_tap6_420p8", ah.YUV420P8, 200, 120, 400, 240, dict(tap=6, cplace="mpeg1")),
     ("third_tap3_y8", ah.Format("y", 8), 600, 360, 200, 120, dict(tap=3)),
+    # 3:2 upscale (720p -> 1080p class): NOT periodic under the reference's float-accumulated positions (4+ phases per axis)
+    ("up1p5_tap3_420p8", ah.YUV420P8, 320, 180, 480, 270, dict(tap=3)),
+    ("up1p5_tap4_444p16_crop", ah.YUV444P16, 240, 136, 360, 204, dict(tap=4, src_left=1.25, src_top=0.75)),
+    ("up1p5_tap3_f32_y", ah.Format("y", 32), 200, 120, 300, 180, dict(tap=3)),
     # general kernel with four planes on one table, and a steep irregular downscale whose source footprints do not fit
     # in shared memory (per-plane fallback of the general kernel)
     ("rgbap10_irregular_up", ah.Format("rgbap", 10), 200, 120, 290, 170, dict(tap=4)),
