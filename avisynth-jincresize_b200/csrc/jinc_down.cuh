@@ -63,12 +63,12 @@ __device__ __forceinline__ void down_row_pair(const typename G::Word* __restrict
         }
 #pragma unroll
         for (int j = 0; j < NY; ++j) {
-            const int kk = k - j * G::JSTEP; // weight row pair of output row j
-            if (ALL || (kk >= 0 && kk < G::NKW)) {
+            const int kk = k - j * G::OFF1; // weight row pair of output row j
+            if (ALL || (kk >= 0 && kk < (j == 0 ? G::NKW : G::NKW1))) {
 #pragma unroll
                 for (int m = 0; m < G::MT; ++m) {
                     if (Q * m + p < FS) {
-                        const float2 w = W.w[kk][p][m];
+                        const float2 w = W.w[G::ODD ? j : 0][kk][p][m];
 #pragma unroll
                         for (int i = 0; i < NX; ++i)
                             acc[j][i] = __ffma2_rn(s[i + m], w, acc[j][i]);
@@ -147,7 +147,7 @@ __global__ void __launch_bounds__((DownGeom<T, FS, Q, NX, NY>::THREADS), 2)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int lx_ = lane % G::LX, ly_ = lane / G::LX;
     const int row0 = (warp * G::LY + ly_) * NY; // first output row of this thread inside the tile
-    const Word* __restrict__ trow = tile + (size_t)(row0 * G::JSTEP) * G::RS + lx_;
+    const Word* __restrict__ trow = tile + (size_t)((warp * G::LY + ly_) * G::HALF) * G::RS + lx_;
 
     float2 acc[NY][NX];
 #pragma unroll
@@ -156,7 +156,7 @@ __global__ void __launch_bounds__((DownGeom<T, FS, Q, NX, NY>::THREADS), 2)
         for (int i = 0; i < NX; ++i)
             acc[j][i] = make_float2(0.f, 0.f);
 
-    constexpr int K_ALL0 = G::JSTEP * (NY - 1); // first row pair at which every output row is inside its window
+    constexpr int K_ALL0 = G::OFF1 * (NY - 1); // first row pair at which every output row is inside its window
     int k = 0;
 #pragma unroll 1
     for (; k < K_ALL0; ++k, trow += G::RS)
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__((DownGeom<T, FS, Q, NX, NY>::THREADS), 2)
 #pragma unroll
         for (int i = 0; i < NX; ++i) {
             if (CVT == DN_CVT_PRMT)
-                v[i] = ((acc[j][i].x - a.bias_even) + (acc[j][i].y - a.bias_odd)) * a.out_scale;
+                v[i] = ((acc[j][i].x - a.bias_x[j]) + (acc[j][i].y - a.bias_y[j])) * a.out_scale;
             else
                 v[i] = acc[j][i].x + acc[j][i].y;
         }
@@ -236,19 +236,26 @@ int launch_down_fs(const jinc_table* t, DownArgs& a, bool want_strips, int n_fra
     DownWeights<FS, Q> w;
     memset(&w, 0, sizeof(w));
     const float* blk = t->h_weights.data() + (size_t)d.wblock * FS * FS;
-    double sum_even = 0.0, sum_odd = 0.0;
-    for (int ly = 0; ly < FS; ++ly)
-        for (int lx = 0; lx < FS; ++lx) {
-            const float v = blk[ly * FS + lx];
-            float2& e = w.w[ly >> 1][lx % Q][lx / Q];
-            if (ly & 1) {
-                e.y = v;
-                sum_odd += v;
-            } else {
-                e.x = v;
-                sum_even += v;
+    // set 0 pairs rows (2k, 2k+1); set 1 (odd ratios) pairs rows (2k-1, 2k); sums per half for the PRMT bias
+    double sum_x[2] = {0.0, 0.0}, sum_y[2] = {0.0, 0.0};
+    for (int set = 0; set < DownWeights<FS, Q>::NSET; ++set)
+        for (int ly = 0; ly < FS; ++ly)
+            for (int lx = 0; lx < FS; ++lx) {
+                const float v = blk[ly * FS + lx];
+                const int r = ly + set; // row index inside the (shifted) pair grid
+                float2& e = w.w[set][r >> 1][lx % Q][lx / Q];
+                if (r & 1) {
+                    e.y = v;
+                    sum_y[set] += v;
+                } else {
+                    e.x = v;
+                    sum_x[set] += v;
+                }
             }
-        }
+    if (DownWeights<FS, Q>::NSET == 1) {
+        sum_x[1] = sum_x[0];
+        sum_y[1] = sum_y[0];
+    }
     if constexpr (sizeof(T) == 4) {
         return launch_down_cfg<T, FS, Q, DN_NX, DN_NY, DN_CVT_FLOAT>(a, w, want_strips, n_frames, st, rects, n_rects);
     } else {
@@ -256,8 +263,10 @@ int launch_down_fs(const jinc_table* t, DownArgs& a, bool want_strips, int n_fra
         if (bits <= 15) {
             // f = 0.5 + (x << pre_shift) / 65536  =>  sum(w f) = 0.5 sum(w) + sum(w x) * 2^(pre_shift - 16)
             a.pre_shift = 15 - bits;
-            a.bias_even = (float)(0.5 * sum_even);
-            a.bias_odd = (float)(0.5 * sum_odd);
+            for (int j = 0; j < 2; ++j) {
+                a.bias_x[j] = (float)(0.5 * sum_x[j]);
+                a.bias_y[j] = (float)(0.5 * sum_y[j]);
+            }
             a.out_scale = (float)(1 << (16 - a.pre_shift));
             return launch_down_cfg<T, FS, Q, DN_NX, DN_NY, DN_CVT_PRMT>(a, w, want_strips, n_frames, st, rects, n_rects);
         }
@@ -279,6 +288,7 @@ int launch_down(const jinc_table* t, DownArgs& a, bool want_strips, int n_frames
         JINC_DOWN_CASE(2, 17) // tap 4, 1/2
         JINC_DOWN_CASE(2, 25) // tap 6, 1/2
         JINC_DOWN_CASE(2, 33) // tap 8, 1/2
+        JINC_DOWN_CASE(3, 20) // tap 3, 1/3
         JINC_DOWN_CASE(4, 26) // tap 3, 1/4
         JINC_DOWN_CASE(4, 34) // tap 4, 1/4
         JINC_DOWN_CASE(4, 50) // tap 6, 1/4

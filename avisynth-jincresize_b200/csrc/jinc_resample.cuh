@@ -834,17 +834,22 @@ struct DownGeom {
     static constexpr int WARPS = TH / (LY * NY);
     static constexpr int THREADS = 32 * WARPS;
     static constexpr int FSE = (FS + 1) & ~1;           // window rows rounded up to whole pairs
-    static constexpr int NKW = FSE / 2;                 // weight row pairs
+    static constexpr bool ODD = (Q & 1) != 0;
+    // Row pairs are formed from the tile origin.  With an odd ratio the second output row of a thread starts on an odd
+    // source row: its window is taken one row early with a leading zero weight (weight set 1: {w[2k-1], w[2k]}), so it
+    // still reads whole pairs, OFF1 pairs below the first row.
+    static constexpr int NKW = FSE / 2;                 // weight row pairs of output row 0 (set 0: {w[2k], w[2k+1]})
+    static constexpr int NKW1 = ODD ? (FS + 2) / 2 : NKW; // weight row pairs of output row 1
+    static constexpr int OFF1 = ODD ? (Q - 1) / 2 : Q / 2; // row pairs between output rows 0 and 1 of a thread
     static constexpr int MT = (FS + Q - 1) / Q;         // taps per polyphase component
     static constexpr int SPAN = NX + MT - 1;            // values a thread reads per (row pair, p)
     static constexpr int D = Q * NX;                    // column de-interleave modulus
     static constexpr int NCOL = Q * (DN_TW - 1) + Q * (MT - 1) + Q; // columns a tile row can be asked for
     static constexpr int SUB = (NCOL + D - 1) / D;
-    static constexpr int NROWS = Q * (TH - 1) + FSE;
+    static constexpr int NROWS = Q * (TH - 1) + 2 * NKW1;
     static constexpr int NROWP = (NROWS + 1) / 2;       // row pairs per tile
-    static constexpr int JSTEP = Q / 2;                 // row pairs between consecutive output rows
-    static constexpr int NK = NKW + JSTEP * (NY - 1);   // row pairs a thread walks
-    static constexpr int HALF = NY * JSTEP;             // row pairs between lane groups that differ in y
+    static constexpr int NK = OFF1 * (NY - 1) + NKW1;   // row pairs a thread walks
+    static constexpr int HALF = NY * Q / 2;             // row pairs between lane groups that differ in y
     static constexpr int rs_pad()
     {
         for (int pad = 0; pad < 32; ++pad) // lane group g lands on banks [g*LX, g*LX + LX)
@@ -854,7 +859,7 @@ struct DownGeom {
     }
     static constexpr int RS = D * SUB + rs_pad();       // row-pair stride in words
     static constexpr size_t SMEM = (size_t)NROWP * RS * sizeof(Word);
-    static_assert(Q % 2 == 0, "tap pairing needs an even ratio");
+    static_assert(NY == 2, "the thread's two output rows carry the pairing parity");
     static_assert(TH % (LY * NY) == 0 && WARPS >= 1, "tile rows must split evenly over the warps");
     static_assert(LX - 1 + (Q * (SPAN - 1) + Q - 1) / D < SUB, "span reaches past the tile row");
 };
@@ -862,7 +867,9 @@ struct DownGeom {
 template <int FS, int Q>
 struct alignas(16) DownWeights {
     static constexpr int MT = (FS + Q - 1) / Q;
-    float2 w[((FS + 1) & ~1) / 2][Q][MT]; // [ly/2][p][m] = {w[ly][Q*m+p], w[ly+1][Q*m+p]}; entries outside the window are 0
+    static constexpr int NSET = (Q & 1) ? 2 : 1;                        // odd ratios: a second set shifted by one row
+    static constexpr int NKWMAX = (Q & 1) ? (FS + 2) / 2 : ((FS + 1) & ~1) / 2;
+    float2 w[NSET][NKWMAX][Q][MT]; // set 0: [k][p][m] = {w[2k][Q*m+p], w[2k+1][Q*m+p]}; set 1: {w[2k-1][..], w[2k][..]}; outside the window 0
 };
 
 struct DownArgs {
@@ -874,7 +881,7 @@ struct DownArgs {
     int tiles_x, tiles_per_plane, interior_blocks, strip_blocks, strip_shift;
     unsigned tiles_x_magic, tiles_per_plane_magic; // div_magic of the two tile divisors
     int pre_shift;       // PRMT conversion: samples are staged as x << pre_shift
-    float bias_even, bias_odd, out_scale; // PRMT conversion: out = ((acc.x - bias_even) + (acc.y - bias_odd)) * out_scale
+    float bias_x[2], bias_y[2], out_scale; // PRMT conversion, output row j of a thread: out = ((acc.x - bias_x[j]) + (acc.y - bias_y[j])) * out_scale
 };
 
 // ---- launch entry points, one explicit instantiation per sample type (jinc_up2x_*.cu, jinc_down_*.cu)
@@ -890,7 +897,7 @@ inline bool down_supported(const jinc_table* t)
     if (!t->down.ok || t->down.qx != t->down.qy)
         return false;
     switch (t->down.qx * 1000 + t->sc.fs) {
-    case 2013: case 2017: case 2025: case 2033: case 4026: case 4034: case 4050: return true;
+    case 2013: case 2017: case 2025: case 2033: case 3020: case 4026: case 4034: case 4050: return true;
     default: return false;
     }
 }
