@@ -185,14 +185,23 @@ __global__ void __launch_bounds__((DownGeom<T, FS, Q, NX, NY>::THREADS), 2)
             else
                 v[i] = acc[j][i].x + acc[j][i].y;
         }
-        T* o = dst + (long long)oy * dp + ox;
-        if (ox + NX <= a.x1) {
-            store_run<T, NX>(o, v, a.fr.peak);
+        if (a.out_stride == 1) {
+            T* o = dst + (long long)oy * dp + ox;
+            if (ox + NX <= a.x1) {
+                store_run<T, NX>(o, v, a.fr.peak);
+            } else {
+#pragma unroll
+                for (int i = 0; i < NX; ++i)
+                    if (ox + i < a.x1)
+                        o[i] = finish<T>(v[i], a.fr.peak);
+            }
         } else {
+            // periodic pass: this sub-lattice owns every out_stride-th sample of every out_stride-th row
+            T* o = dst + (long long)(a.out_y0 + a.out_stride * (oy - a.y0)) * dp + (a.out_x0 + a.out_stride * (ox - a.x0));
 #pragma unroll
             for (int i = 0; i < NX; ++i)
                 if (ox + i < a.x1)
-                    o[i] = finish<T>(v[i], a.fr.peak);
+                    o[i * a.out_stride] = finish<T>(v[i], a.fr.peak);
         }
     }
 }
@@ -229,13 +238,12 @@ int launch_down_cfg(DownArgs& a, const DownWeights<FS, Q>& w, long long strip_bl
 constexpr int DN_NX = 8, DN_NY = 2; // outputs per thread
 
 template <typename T, int FS, int Q>
-int launch_down_fs(const jinc_table* t, DownArgs& a, bool want_strips, int n_frames, cudaStream_t st, const Rect* rects, int n_rects)
+int launch_down_fs(const jinc_table* t, DownArgs& a, int wblock, bool want_strips, int n_frames, cudaStream_t st, const Rect* rects, int n_rects)
 {
     static_assert(sizeof(DownWeights<FS, Q>) + sizeof(DownArgs) < 32000, "kernel parameters exceed the 32 KB limit");
-    const DownPlan& d = t->down;
     DownWeights<FS, Q> w;
     memset(&w, 0, sizeof(w));
-    const float* blk = t->h_weights.data() + (size_t)d.wblock * FS * FS;
+    const float* blk = t->h_weights.data() + (size_t)wblock * FS * FS;
     // set 0 pairs rows (2k, 2k+1); set 1 (odd ratios) pairs rows (2k-1, 2k); sums per half for the PRMT bias
     double sum_x[2] = {0.0, 0.0}, sum_y[2] = {0.0, 0.0};
     for (int set = 0; set < DownWeights<FS, Q>::NSET; ++set)
@@ -278,16 +286,24 @@ int launch_down_fs(const jinc_table* t, DownArgs& a, bool want_strips, int n_fra
 
 // 0 launched, 2 nothing to do, 1 unsupported geometry, <0 error
 template <typename T>
-int launch_down(const jinc_table* t, DownArgs& a, bool want_strips, int n_frames, cudaStream_t st, const Rect* rects, int n_rects)
+int launch_down(const jinc_table* t, DownArgs& a, int q, int wblock, bool want_strips, int n_frames, cudaStream_t st, const Rect* rects,
+                int n_rects)
 {
-    const int key = t->down.qx * 1000 + t->sc.fs;
+    if (a.out_stride < 1) {
+        a.out_stride = 1;
+        a.out_x0 = a.x0;
+        a.out_y0 = a.y0;
+    }
+    const int key = q * 1000 + t->sc.fs;
     switch (key) {
 #define JINC_DOWN_CASE(Q_, FS_) \
-    case Q_ * 1000 + FS_: return launch_down_fs<T, FS_, Q_>(t, a, want_strips, n_frames, st, rects, n_rects);
+    case Q_ * 1000 + FS_: return launch_down_fs<T, FS_, Q_>(t, a, wblock, want_strips, n_frames, st, rects, n_rects);
         JINC_DOWN_CASE(2, 13) // tap 3, 1/2
         JINC_DOWN_CASE(2, 17) // tap 4, 1/2
         JINC_DOWN_CASE(2, 25) // tap 6, 1/2
         JINC_DOWN_CASE(2, 33) // tap 8, 1/2
+        JINC_DOWN_CASE(3, 10) // tap 3, 2:3 periodic passes
+        JINC_DOWN_CASE(3, 13) // tap 4, 2:3 periodic passes
         JINC_DOWN_CASE(3, 20) // tap 3, 1/3
         JINC_DOWN_CASE(4, 26) // tap 3, 1/4
         JINC_DOWN_CASE(4, 34) // tap 4, 1/4

@@ -81,6 +81,18 @@ struct DownPlan {
     int wblock = 0;
 };
 
+// Exactly periodic rational ratio: output P*c + p reads the window at Q*c + off[p] with phase block p, on both axes
+// (the reference accumulates positions in float, so this needs crop/dst = m/2^k: 2:3 and 3:4 ratios).  Every (py, px)
+// sub-lattice is an integer-ratio-Q problem of its own, run as one pass of the polyphase kernel with output stride P.
+struct PeriodicPlan {
+    bool ok = false;
+    int P = 0, Q = 0;
+    int x0 = 0, y0 = 0, ncx = 0, ncy = 0; // first output of the periodic interior, cells per axis
+    int sx0 = 0, sy0 = 0;                 // window origin of cell (0,0), phase (0,0)
+    int ox[4] = {0, 0, 0, 0}, oy[4] = {0, 0, 0, 0}; // origin offset of phase p
+    int wblock[4][4] = {};                // [py][px] -> phase-block index
+};
+
 struct jinc_table {
     jinc_ctx* ctx = nullptr;
     jinc_table_params params{};
@@ -104,6 +116,7 @@ struct jinc_table {
     std::vector<float> h_pos[2];
     Up2xPlan up2x;
     DownPlan down;
+    PeriodicPlan periodic;
     int fast_path = JINC_PATH_GENERAL;
     int ix0 = 0, ix1 = 0, iy0 = 0, iy1 = 0; // interior rectangle run by the fast path (empty if none)
 };

@@ -876,7 +876,9 @@ struct DownArgs {
     FrameSet fr;
     StripArgs st;
     int src_w, src_h;
-    int x0, y0, x1, y1;  // output rectangle produced by the tiles (y0..y1 already cut to the row band)
+    int x0, y0, x1, y1;  // output rectangle produced by the tiles (y0..y1 already cut to the row band); for a periodic pass
+                         // these count CELLS of the pass's sub-lattice
+    int out_x0, out_y0, out_stride; // plane coordinates of (x0, y0) and the distance between neighbouring outputs (1, or P)
     int tsx0, tsy0;      // window origin of output (x0, y0)
     int tiles_x, tiles_per_plane, interior_blocks, strip_blocks, strip_shift;
     unsigned tiles_x_magic, tiles_per_plane_magic; // div_magic of the two tile divisors
@@ -890,7 +892,19 @@ template <typename T>
 int launch_up2x(const jinc_table* t, UpArgs& a, long long strip_blocks, int n_frames, cudaStream_t st);
 // 0 launched, 2 nothing to do, 1 unsupported geometry, <0 error
 template <typename T>
-int launch_down(const jinc_table* t, DownArgs& a, bool want_strips, int n_frames, cudaStream_t st, const Rect* rects, int n_rects);
+int launch_down(const jinc_table* t, DownArgs& a, int q, int wblock, bool want_strips, int n_frames, cudaStream_t st, const Rect* rects,
+                int n_rects);
+
+inline bool periodic_supported(const jinc_table* t)
+{
+    const PeriodicPlan& u = t->periodic;
+    if (!u.ok || u.P != 2 || u.Q != 3)
+        return false;
+    switch (t->sc.fs) {
+    case 10: case 13: return true; // taps 3 and 4 at 2:3
+    default: return false;
+    }
+}
 
 inline bool down_supported(const jinc_table* t)
 {

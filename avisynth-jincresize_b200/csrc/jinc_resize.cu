@@ -289,6 +289,50 @@ int launch_typed(const jinc_table* t, const FrameSet& fr, int n_frames, int y_be
             }
         }
     }
+    if (t->fast_path == JINC_PATH_PERIODIC && periodic_supported(t)) {
+        const PeriodicPlan& u = t->periodic;
+        // cells whose P output rows lie inside [y_begin, y_end)
+        const int cb = (std::max(y_begin, u.y0) - u.y0 + u.P - 1) / u.P;
+        const int ce = (std::min(y_end, u.y0 + u.P * u.ncy) - u.y0) / u.P;
+        if (ce > cb) {
+            const int fy0 = u.y0 + u.P * cb, fy1 = u.y0 + u.P * ce;
+            if (parts & JINC_PART_BORDER) {
+                rects[n_rects++] = Rect{0, y_begin, W, fy0};
+                rects[n_rects++] = Rect{0, fy1, W, y_end};
+                rects[n_rects++] = Rect{0, fy0, t->ix0, fy1};
+                rects[n_rects++] = Rect{t->ix1, fy0, W, fy1};
+            }
+            bool first = true;
+            for (int py = 0; py < u.P; ++py)
+                for (int px = 0; px < u.P; ++px) {
+                    // one pass per phase pair: an integer-ratio-Q problem over the cells, written with stride P
+                    DownArgs a;
+                    memset(&a, 0, sizeof(a));
+                    a.fr = fr;
+                    a.st = sa;
+                    a.src_w = t->sc.src_w;
+                    a.src_h = t->sc.src_h;
+                    a.x0 = 0;
+                    a.x1 = u.ncx;
+                    a.y0 = cb;
+                    a.y1 = ce;
+                    a.tsx0 = u.sx0 + u.ox[px];
+                    a.tsy0 = u.sy0 + u.oy[py] + u.Q * cb;
+                    a.out_x0 = u.x0 + px;
+                    a.out_y0 = u.y0 + u.P * cb + py;
+                    a.out_stride = u.P;
+                    a.interior_blocks = (parts & JINC_PART_INTERIOR) ? 1 : 0;
+                    const bool strips_now = first && n_rects > 0; // the border strips ride on the first pass
+                    const int rc = launch_down<T>(t, a, u.Q, u.wblock[py][px], strips_now, n_frames, st, rects, strips_now ? n_rects : 0);
+                    if (rc < 0 || rc == 1)
+                        return rc < 0 ? rc : jinc_fail(JINC_E_UNSUPPORTED, "resize: periodic pass not instantiated (fs %d)", t->sc.fs);
+                    if (rc == 0)
+                        ++*launches;
+                    first = false;
+                }
+            return JINC_OK;
+        }
+    }
     if (t->fast_path == JINC_PATH_DOWN_INT && down_supported(t)) {
         const DownPlan& d = t->down;
         const int fy0 = std::max(y_begin, d.y0), fy1 = std::min(y_end, d.y0 + d.ny);
@@ -312,7 +356,7 @@ int launch_typed(const jinc_table* t, const FrameSet& fr, int n_frames, int y_be
             a.tsx0 = d.sx0;
             a.tsy0 = d.sy0 + d.qy * (fy0 - d.y0);
             a.interior_blocks = (parts & JINC_PART_INTERIOR) ? 1 : 0; // resolved to the tile count by the launcher
-            const int rc = launch_down<T>(t, a, n_rects > 0, n_frames, st, rects, n_rects);
+            const int rc = launch_down<T>(t, a, d.qx, d.wblock, n_rects > 0, n_frames, st, rects, n_rects);
             if (rc != 1) {
                 if (rc == 0)
                     ++*launches;

@@ -324,6 +324,24 @@ int axis_down_ratio(const std::vector<int32_t>& start, const std::vector<int32_t
     return q;
 }
 
+// Periodic axis: start[i+P] == start[i] + Q and rank[i+P] == rank[i] over the interior run; smallest P in 2..4.
+bool axis_periodic(const std::vector<int32_t>& start, const std::vector<int32_t>& rank, int a, int b, int& P, int& Q)
+{
+    for (P = 2; P <= 4; ++P) {
+        if (b - a < 4 * P)
+            continue;
+        Q = start[a + P] - start[a];
+        if (Q < 1)
+            continue;
+        bool ok = true;
+        for (int i = a; ok && i + P < b; ++i)
+            ok = start[i + P] == start[i] + Q && rank[i + P] == rank[i];
+        if (ok)
+            return true;
+    }
+    return false;
+}
+
 void plan_fast_paths(jinc_table* t)
 {
     int ax_a[2], ax_b[2];
@@ -380,6 +398,36 @@ void plan_fast_paths(jinc_table* t)
             t->ix1 = d.x0 + d.nx;
             t->iy0 = d.y0;
             t->iy1 = d.y0 + d.ny;
+        }
+        return; // an integer ratio also looks periodic (P = 2, Q = 2q): it is the polyphase kernel's own case
+    }
+    int Px = 0, Qx = 0, Py = 0, Qy = 0;
+    if (axis_periodic(t->h_start[0], t->h_rank[0], ax_a[0], ax_b[0], Px, Qx) &&
+        axis_periodic(t->h_start[1], t->h_rank[1], ax_a[1], ax_b[1], Py, Qy) && Px == Py && Qx == Qy && !(Px == 2 && Qx == 1)) {
+        PeriodicPlan& u = t->periodic;
+        u.P = Px;
+        u.Q = Qx;
+        u.x0 = ax_a[0];
+        u.y0 = ax_a[1];
+        u.ncx = (ax_b[0] - u.x0) / u.P;
+        u.ncy = (ax_b[1] - u.y0) / u.P;
+        if (u.ncx >= 8 && u.ncy >= 2) {
+            u.sx0 = t->h_start[0][u.x0];
+            u.sy0 = t->h_start[1][u.y0];
+            for (int p = 0; p < u.P; ++p) {
+                u.ox[p] = t->h_start[0][u.x0 + p] - u.sx0;
+                u.oy[p] = t->h_start[1][u.y0 + p] - u.sy0;
+            }
+            for (int py = 0; py < u.P; ++py)
+                for (int px = 0; px < u.P; ++px)
+                    u.wblock[py][px] = t->h_rank[1][u.y0 + py] * nrx + t->h_rank[0][u.x0 + px];
+            u.ok = true;
+            // the polyphase kernel is selected in jinc_resize.cu when it supports this (fs, P, Q)
+            t->fast_path = JINC_PATH_PERIODIC;
+            t->ix0 = u.x0;
+            t->ix1 = u.x0 + u.P * u.ncx;
+            t->iy0 = u.y0;
+            t->iy1 = u.y0 + u.P * u.ncy;
         }
     }
 }

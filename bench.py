@@ -57,7 +57,7 @@ CONFIGS = {
     # not BASELINE configs: the "next" row of SURVEY.md 8(f), ratios that are not exact 2x / 1/n (general kernel)
     6: dict(name="1280x720 YUV420P8 -> 1920x1080 Jinc36Resize (1.5x, general path)", fmt=ah.YUV420P8, w=1280, h=720, tw=1920,
             th=1080, fn="Jinc36Resize", kw=dict(), tap=3, frames=48),
-    7: dict(name="1920x1080 YUV420P8 -> 1280x720 Jinc36Resize (2/3 downscale, general path)", fmt=ah.YUV420P8, w=1920, h=1080,
+    7: dict(name="1920x1080 YUV420P8 -> 1280x720 Jinc36Resize (2:3 downscale, periodic path)", fmt=ah.YUV420P8, w=1920, h=1080,
             tw=1280, th=720, fn="Jinc36Resize", kw=dict(), tap=3, frames=48),
     8: dict(name="1920x1080 YUV444P16 -> 2500x1400 Jinc64Resize (irregular ratio, many phases)", fmt=ah.YUV444P16, w=1920, h=1080,
             tw=2500, th=1400, fn="Jinc64Resize", kw=dict(), tap=4, frames=12),
@@ -453,7 +453,7 @@ def run_b200(args, cfg):
             "e2e_plugin": plugin,
             "gpu_launches": gpu_launches,
             "clocks": clocks,
-            "roofline": {"bound": "fp32_fma", "kernel": {1: "resample_up2x", 2: "resample_down"}.get(i0.fast_path, "resample_strips") + " (luma-table planes of all %d frames: interior tiles + border strips)" % F,
+            "roofline": {"bound": "fp32_fma", "kernel": {1: "resample_up2x", 2: "resample_down", 3: "resample_down (2:3 periodic, first of 4 passes)"}.get(i0.fast_path, "resample_strips") + " (luma-table planes of all %d frames: interior tiles + border strips)" % F,
                          "achieved": achieved_tf, "peak": fma_peak, "unit": "TFLOP/s", "frac": achieved_tf / fma_peak,
                          "peak_source": fma_how, "traffic": ncu_traffic(args.config, F), "launch_ms": dom_avg_ms,
                          "algorithmic_flop_per_launch": dom_flop, "share_of_step": sum(dom_ms) / ms_total},

@@ -78,7 +78,8 @@ typedef struct jinc_table_params {
 enum {
     JINC_PATH_GENERAL = 0,   /* one thread per output sample, weights gathered per sample */
     JINC_PATH_UP2X = 1,      /* exact 2x upscale: 2x2 phase classes, register-tiled FFMA2 kernel */
-    JINC_PATH_DOWN_INT = 2   /* integer-ratio downscale: one phase, polyphase register-tiled kernel */
+    JINC_PATH_DOWN_INT = 2,  /* integer-ratio downscale: one phase, polyphase register-tiled kernel */
+    JINC_PATH_PERIODIC = 3   /* exactly periodic rational ratio (2:3, e.g. 1080p -> 720p): P x P passes of the polyphase kernel */
 };
 
 typedef struct jinc_table_info {
