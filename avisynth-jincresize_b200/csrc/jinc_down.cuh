@@ -302,6 +302,8 @@ int launch_down(const jinc_table* t, DownArgs& a, int q, int wblock, bool want_s
         JINC_DOWN_CASE(2, 17) // tap 4, 1/2
         JINC_DOWN_CASE(2, 25) // tap 6, 1/2
         JINC_DOWN_CASE(2, 33) // tap 8, 1/2
+        JINC_DOWN_CASE(3, 7)  // tap 3, 4:3 periodic passes
+        JINC_DOWN_CASE(3, 9)  // tap 4, 4:3 periodic passes
         JINC_DOWN_CASE(3, 10) // tap 3, 2:3 periodic passes
         JINC_DOWN_CASE(3, 13) // tap 4, 2:3 periodic passes
         JINC_DOWN_CASE(3, 20) // tap 3, 1/3

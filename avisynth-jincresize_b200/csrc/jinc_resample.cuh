@@ -898,12 +898,13 @@ int launch_down(const jinc_table* t, DownArgs& a, int q, int wblock, bool want_s
 inline bool periodic_supported(const jinc_table* t)
 {
     const PeriodicPlan& u = t->periodic;
-    if (!u.ok || u.P != 2 || u.Q != 3)
+    if (!u.ok || u.Q != 3)
         return false;
-    switch (t->sc.fs) {
-    case 10: case 13: return true; // taps 3 and 4 at 2:3
-    default: return false;
-    }
+    if (u.P == 2)
+        return t->sc.fs == 10 || t->sc.fs == 13; // taps 3 and 4 at 2:3 (1080p -> 720p)
+    if (u.P == 4)
+        return t->sc.fs == 7 || t->sc.fs == 9;   // taps 3 and 4 at 4:3 (1080p -> 1440p)
+    return false;
 }
 
 inline bool down_supported(const jinc_table* t)

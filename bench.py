@@ -59,6 +59,8 @@ CONFIGS = {
             th=1080, fn="Jinc36Resize", kw=dict(), tap=3, frames=48),
     7: dict(name="1920x1080 YUV420P8 -> 1280x720 Jinc36Resize (2:3 downscale, periodic path)", fmt=ah.YUV420P8, w=1920, h=1080,
             tw=1280, th=720, fn="Jinc36Resize", kw=dict(), tap=3, frames=48),
+    9: dict(name="1920x1080 YUV420P8 -> 2560x1440 Jinc36Resize (4:3 upscale, periodic path)", fmt=ah.YUV420P8, w=1920, h=1080,
+            tw=2560, th=1440, fn="Jinc36Resize", kw=dict(), tap=3, frames=32),
     8: dict(name="1920x1080 YUV444P16 -> 2500x1400 Jinc64Resize (irregular ratio, many phases)", fmt=ah.YUV444P16, w=1920, h=1080,
             tw=2500, th=1400, fn="Jinc64Resize", kw=dict(), tap=4, frames=12),
 }

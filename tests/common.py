@@ -90,6 +90,9 @@ SMALL_CASES = [
     ("down2to3_tap4_444p16_crop", ah.YUV444P16, 360, 204, 240, 136, dict(tap=4, src_left=1.5, src_top=0.75, src_width=357.0, src_height=202.5)),
     ("down2to3_tap3_f32_y", ah.Format("y", 32), 300, 180, 200, 120, dict(tap=3)),
     ("down2to3_tap3_422p10_mpeg1", ah.Format("422", 10), 384, 216, 256, 144, dict(tap=3, cplace="mpeg1")),
+    # 4:3 upscale (1080p -> 1440p class): exactly periodic (source step 0.75), sixteen passes
+    ("up4to3_tap3_420p8", ah.YUV420P8, 360, 204, 480, 272, dict(tap=3)),
+    ("up4to3_tap4_y16", ah.Format("y", 16), 270, 150, 360, 200, dict(tap=4)),
     # general kernel with four planes on one table, and a steep irregular downscale whose source footprints do not fit
     # in shared memory (per-plane fallback of the general kernel)
     ("rgbap10_irregular_up", ah.Format("rgbap", 10), 200, 120, 290, 170, dict(tap=4)),
