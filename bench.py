@@ -275,6 +275,30 @@ def run_plugin_e2e(cfg, threads: int, frames: int, steps: int, device: int):
             "ms_per_step": dt / steps * 1e3}
 
 
+def bind_to_gpu_numa(device_index: int):
+    """One process per GPU: pin this process to the CPUs NVML reports as local to its GPU BEFORE any pinned host buffer is
+    allocated, so the frames it DMAs live on the GPU's own NUMA node (with 4+ GPUs on a two-socket box, remote buffers
+    cut the end-to-end rate).  Returns the number of CPUs bound to, or None when NVML gives no answer."""
+    try:
+        import pynvml
+        import torch
+
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(device_index)
+        bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * i + b for i, wd in enumerate(mask) for b in range(64) if (wd >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 # ------------------------------------------------------------------------------------------ GPU arm
 
 def run_b200(args, cfg):
@@ -289,6 +313,7 @@ def run_b200(args, cfg):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa_cpus = bind_to_gpu_numa(local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -447,7 +472,8 @@ def run_b200(args, cfg):
             "config": {"workload": cfg["name"], "config_id": args.config, "frames_per_step": F,
                        "sample_type": f"{fmt.family}{fmt.bits}", "filter_size": fs_l, **({"parts": args.parts, "INVALID": "diagnostic run, part of the frame skipped"} if args.parts != 3 else {}),
                        "l2": "inputs larger than L2: every step walks %d distinct frames (%.0f MB of planes)" % (F, F * byts / 1e6),
-                       "partition": "frame-parallel, one process per GPU, no collective"},
+                       "partition": "frame-parallel, one process per GPU, no collective",
+                       "host_affinity": ("each rank bound to the %d CPUs local to its GPU" % numa_cpus) if numa_cpus else "unbound"},
             "e2e": {"value": e2e_value, "unit": "Mpixel/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "jinc_filter_submit/jinc_filter_wait (C ABI host-frame call, %d frames in flight per GPU), pinned host planes" % args.inflight,
                     "ms_per_step": e2e_s / args.steps * 1e3,
