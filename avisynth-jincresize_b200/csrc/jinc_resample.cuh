@@ -7,17 +7,25 @@
 // One launch covers ALL planes that share a coefficient table, for a whole BATCH of frames, interior and border
 // together; blocks take one of two roles:
 //
-//   interior tile (exact 2x upscale, every "JincNNResize(2w,2h)" use)
-//       The table has 2x2 phase classes.  A thread owns TX=4 source-aligned cells x 2 cell rows = 8x4 output samples in
-//       16 float2 accumulators.  The source tile lives in shared memory as VERTICAL PAIRS {S[r][c], S[r+1][c]} so one
-//       packed FFMA2 (fma.rn.f32x2, new on sm_100) updates the same phase of two cell rows with a single scalar
-//       weight.  Weights arrive as kernel parameters (constant bank) and reach the FMA pipe through uniform registers
-//       (LDCU -> FFMA2 R, R, UR, R): weights cost no shared-memory or register-file bandwidth.  Pair columns are
-//       de-interleaved by (c & 3) so a warp's LDS.64 is bank-conflict free.
-//   strip chunk (256 output samples of the border strips, or of the whole plane when the table has no fast path)
-//       One thread per output sample, all planes of the table in one pass.  Samples whose window was clamped get the
-//       reference's per-pixel weights on the fly: exact LUT index per tap, divided by the per-pixel normaliser that
-//       the table build stored (:443-514); other samples gather their shared phase block from the L2-resident table.
+//   interior tile
+//       exact 2x upscale (jinc_up2x.cuh, every "JincNNResize(2w,2h)" use): the table has 2x2 phase classes.  A thread
+//       owns TX=4 source-aligned cells x 2 cell rows = 8x4 output samples in 16 float2 accumulators.  The source tile
+//       lives in shared memory as VERTICAL PAIRS {S[r][c], S[r+1][c]} so one packed FFMA2 (fma.rn.f32x2, new on sm_100)
+//       updates the same phase of two cell rows with a single scalar weight.  Weights arrive as kernel parameters
+//       (constant bank) and reach the FMA pipe through uniform registers (LDCU -> FFMA2 R, R, UR, R): they cost no
+//       shared-memory or register-file bandwidth.  Pair columns are de-interleaved by (c & 3) so a warp's LDS.64 is
+//       bank-conflict free.
+//       integer-ratio downscale and the passes of the periodic 2:3 / 4:3 paths (jinc_down.cuh): polyphase columns,
+//       vertical tap pairing, raw sample pairs in shared memory.
+//   strip patch (512 output samples of the border strips; strip_block below)
+//       One thread = 4 output samples that share a border row or column (hence, normally, one weight block): the
+//       patch's source footprint is staged in shared memory as floats, weights are read as float4 rows from the
+//       per-class border blocks or the padded phase blocks.  Border pixels that fold into no class fall back to
+//       resident per-pixel weights or to the reference's formula evaluated per tap (exact LUT index, divided by the
+//       stored per-pixel normaliser, :443-514).
+//
+// General ratios (no fast path) run resample_strips in jinc_resize.cu: the same patch scheme over the whole plane, one
+// block covering the patch in every plane of the table.
 //
 // The kernels are split over several translation units (one per sample type and kernel family) so that the build
 // runs in parallel; everything here is a template, inline, or a plain struct.
@@ -806,8 +814,11 @@ inline size_t up2x_smem_bytes(int fs)
 //     uses each for up to NX outputs, and one weight fetch feeds NX FFMA2s;
 //   * tap pairing: one packed FFMA2 multiplies the vertical sample pair {S[r][c], S[r+1][c]} with the weight pair
 //     {w[ly][lx], w[ly+1][lx]} into the two halves of ONE output's accumulator (even-row and odd-row partial sums,
-//     added in the epilogue).  Q is even, so every output row of the thread sees the same pairing and a staged pair
-//     is reused for all NY output rows of the thread;
+//     added in the epilogue).  With an even Q every output row of the thread sees the same pairing and a staged pair
+//     is reused for both output rows of the thread; with an odd Q (1/3, and the passes of the periodic 2:3 / 4:3
+//     paths, where each phase pair's sub-lattice is a ratio-3 problem written with an output stride) the second row
+//     starts on an odd source row, so its window is taken one row early with a leading zero weight -- a second weight
+//     set {w[2k-1], w[2k]}, still warp-uniform;
 //   * raw sample pairs in shared memory for integer formats (two 16-bit samples per 32-bit word; u8 is widened while
 //     staging), so a 64x32-output tile with its 302x174-sample footprint fits twice per SM.  The float value is made
 //     after the shared-memory load.  For depths up to 15 bits that costs ONE byte permute per sample: staging stores

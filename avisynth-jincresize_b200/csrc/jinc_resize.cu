@@ -7,17 +7,25 @@
 // One launch covers ALL planes that share a coefficient table, for a whole BATCH of frames, interior and border
 // together; blocks take one of two roles:
 //
-//   interior tile (exact 2x upscale, every "JincNNResize(2w,2h)" use)
-//       The table has 2x2 phase classes.  A thread owns TX=4 source-aligned cells x 2 cell rows = 8x4 output samples in
-//       16 float2 accumulators.  The source tile lives in shared memory as VERTICAL PAIRS {S[r][c], S[r+1][c]} so one
-//       packed FFMA2 (fma.rn.f32x2, new on sm_100) updates the same phase of two cell rows with a single scalar
-//       weight.  Weights arrive as kernel parameters (constant bank) and reach the FMA pipe through uniform registers
-//       (LDCU -> FFMA2 R, R, UR, R): weights cost no shared-memory or register-file bandwidth.  Pair columns are
-//       de-interleaved by (c & 3) so a warp's LDS.64 is bank-conflict free.
-//   strip chunk (256 output samples of the border strips, or of the whole plane when the table has no fast path)
-//       One thread per output sample, all planes of the table in one pass.  Samples whose window was clamped get the
-//       reference's per-pixel weights on the fly: exact LUT index per tap, divided by the per-pixel normaliser that
-//       the table build stored (:443-514); other samples gather their shared phase block from the L2-resident table.
+//   interior tile
+//       exact 2x upscale (jinc_up2x.cuh, every "JincNNResize(2w,2h)" use): the table has 2x2 phase classes.  A thread
+//       owns TX=4 source-aligned cells x 2 cell rows = 8x4 output samples in 16 float2 accumulators.  The source tile
+//       lives in shared memory as VERTICAL PAIRS {S[r][c], S[r+1][c]} so one packed FFMA2 (fma.rn.f32x2, new on sm_100)
+//       updates the same phase of two cell rows with a single scalar weight.  Weights arrive as kernel parameters
+//       (constant bank) and reach the FMA pipe through uniform registers (LDCU -> FFMA2 R, R, UR, R): they cost no
+//       shared-memory or register-file bandwidth.  Pair columns are de-interleaved by (c & 3) so a warp's LDS.64 is
+//       bank-conflict free.
+//       integer-ratio downscale and the passes of the periodic 2:3 / 4:3 paths (jinc_down.cuh): polyphase columns,
+//       vertical tap pairing, raw sample pairs in shared memory.
+//   strip patch (512 output samples of the border strips; strip_block below)
+//       One thread = 4 output samples that share a border row or column (hence, normally, one weight block): the
+//       patch's source footprint is staged in shared memory as floats, weights are read as float4 rows from the
+//       per-class border blocks or the padded phase blocks.  Border pixels that fold into no class fall back to
+//       resident per-pixel weights or to the reference's formula evaluated per tap (exact LUT index, divided by the
+//       stored per-pixel normaliser, :443-514).
+//
+// General ratios (no fast path) run resample_strips in jinc_resize.cu: the same patch scheme over the whole plane, one
+// block covering the patch in every plane of the table.
 //
 // This translation unit holds the general (any ratio) kernel and the launcher; the exact-2x and integer-ratio
 // downscale kernels live in jinc_up2x_*.cu / jinc_down_*.cu (one per sample type, so the build runs in parallel).
