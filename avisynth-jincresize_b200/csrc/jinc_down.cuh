@@ -79,19 +79,25 @@ __device__ __forceinline__ void down_row_pair(const typename G::Word* __restrict
     }
 }
 
-template <typename T, int FS, int Q, int NX, int NY, int CVT>
+template <typename T, int FS, int Q, int NX, int NY, int CVT, int NPASS>
 __global__ void __launch_bounds__((DownGeom<T, FS, Q, NX, NY>::THREADS), 2)
-    resample_down(const __grid_constant__ DownArgs a, const __grid_constant__ DownWeights<FS, Q> W)
+    resample_down(const __grid_constant__ DownArgs a, const __grid_constant__ DownWeightsN<FS, Q, NPASS> WN)
 {
     using G = DownGeom<T, FS, Q, NX, NY>;
     using Word = typename G::Word;
     extern __shared__ __align__(16) unsigned char smem_raw[];
 
+    // blockIdx.z = pass (periodic paths); the border strips ride on pass 0
+    const int pz = NPASS > 1 ? (int)blockIdx.z : 0;
+    const DownPass& ps = a.pass[pz];
+    const DownWeights<FS, Q>& W = WN.pass[pz];
     unsigned role_id;
-    if (block_role(blockIdx.x, (unsigned)a.strip_blocks, a.strip_shift, role_id)) {
+    if (block_role(blockIdx.x, pz == 0 ? (unsigned)a.strip_blocks : 0u, a.strip_shift, role_id)) {
         strip_block<T, FS, G::THREADS, DN_STRIP_SPT>(a.st, a.fr, role_id, reinterpret_cast<float*>(smem_raw));
         return;
     }
+    if (role_id >= (unsigned)a.interior_blocks)
+        return; // grid positions of pass 0's strip blocks in the other passes
     Word* tile = reinterpret_cast<Word*>(smem_raw); // [NROWP][D][SUB] (+pad): word (k, c) at k*RS + (c%D)*SUB + c/D
     const int plane = (int)div_by(role_id, a.tiles_per_plane_magic);
     const int tidx = role_id - plane * a.tiles_per_plane;
@@ -103,7 +109,7 @@ __global__ void __launch_bounds__((DownGeom<T, FS, Q, NX, NY>::THREADS), 2)
     const long long dp = pp.dst_pitch[plane];
 
     const int ox0 = a.x0 + tile_x * DN_TW, oy0 = a.y0 + tile_y * G::TH; // first output of the tile
-    const int tsx = a.tsx0 + Q * (tile_x * DN_TW), tsy = a.tsy0 + Q * (tile_y * G::TH);
+    const int tsx = ps.tsx0 + Q * (tile_x * DN_TW), tsy = ps.tsy0 + Q * (tile_y * G::TH);
 
     // ---- stage the tile: a warp takes whole row pairs, a lane the columns lane + 32 q.  All loads of KU row pairs are
     //      issued before the first store so ~40 global loads per thread are in flight.
@@ -181,7 +187,7 @@ __global__ void __launch_bounds__((DownGeom<T, FS, Q, NX, NY>::THREADS), 2)
 #pragma unroll
         for (int i = 0; i < NX; ++i) {
             if (CVT == DN_CVT_PRMT)
-                v[i] = ((acc[j][i].x - a.bias_x[j]) + (acc[j][i].y - a.bias_y[j])) * a.out_scale;
+                v[i] = ((acc[j][i].x - ps.bias_x[j]) + (acc[j][i].y - ps.bias_y[j])) * a.out_scale;
             else
                 v[i] = acc[j][i].x + acc[j][i].y;
         }
@@ -197,7 +203,7 @@ __global__ void __launch_bounds__((DownGeom<T, FS, Q, NX, NY>::THREADS), 2)
             }
         } else {
             // periodic pass: this sub-lattice owns every out_stride-th sample of every out_stride-th row
-            T* o = dst + (long long)(a.out_y0 + a.out_stride * (oy - a.y0)) * dp + (a.out_x0 + a.out_stride * (ox - a.x0));
+            T* o = dst + (long long)(ps.out_y0 + a.out_stride * (oy - a.y0)) * dp + (ps.out_x0 + a.out_stride * (ox - a.x0));
 #pragma unroll
             for (int i = 0; i < NX; ++i)
                 if (ox + i < a.x1)
@@ -206,8 +212,8 @@ __global__ void __launch_bounds__((DownGeom<T, FS, Q, NX, NY>::THREADS), 2)
     }
 }
 
-template <typename T, int FS, int Q, int NX, int NY, int CVT>
-int launch_down_cfg(DownArgs& a, const DownWeights<FS, Q>& w, long long strip_blocks_of, int n_frames, cudaStream_t st,
+template <typename T, int FS, int Q, int NX, int NY, int CVT, int NPASS>
+int launch_down_cfg(DownArgs& a, const DownWeightsN<FS, Q, NPASS>& w, long long strip_blocks_of, int n_frames, cudaStream_t st,
                     const Rect* rects, int n_rects)
 {
     using G = DownGeom<T, FS, Q, NX, NY>;
@@ -219,7 +225,7 @@ int launch_down_cfg(DownArgs& a, const DownWeights<FS, Q>& w, long long strip_bl
     a.tiles_per_plane_magic = div_magic((unsigned)a.tiles_per_plane);
     if (a.interior_blocks)
         a.interior_blocks = a.tiles_per_plane * a.fr.n_planes;
-    auto kern = resample_down<T, FS, Q, NX, NY, CVT>;
+    auto kern = resample_down<T, FS, Q, NX, NY, CVT, NPASS>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
     if (e != cudaSuccess)
         return jinc_fail(JINC_E_CUDA, "cudaFuncSetAttribute(down smem %zu): %s", G::SMEM, cudaGetErrorString(e));
@@ -227,7 +233,8 @@ int launch_down_cfg(DownArgs& a, const DownWeights<FS, Q>& w, long long strip_bl
         return 2;
     a.strip_blocks = (int)strip_blocks;
     a.strip_shift = strip_role_shift(a.interior_blocks, strip_blocks);
-    dim3 grid((unsigned)(a.interior_blocks + strip_blocks), n_frames, 1);
+    a.n_passes = NPASS;
+    dim3 grid((unsigned)(a.interior_blocks + strip_blocks), n_frames, NPASS);
     kern<<<grid, G::THREADS, G::SMEM, st>>>(a, w);
     e = cudaGetLastError();
     if (e != cudaSuccess)
@@ -237,79 +244,81 @@ int launch_down_cfg(DownArgs& a, const DownWeights<FS, Q>& w, long long strip_bl
 
 constexpr int DN_NX = 8, DN_NY = 2; // outputs per thread
 
-template <typename T, int FS, int Q>
-int launch_down_fs(const jinc_table* t, DownArgs& a, int wblock, bool want_strips, int n_frames, cudaStream_t st, const Rect* rects, int n_rects)
+template <typename T, int FS, int Q, int NPASS>
+int launch_down_fs(const jinc_table* t, DownArgs& a, const int* wblocks, bool want_strips, int n_frames, cudaStream_t st, const Rect* rects,
+                   int n_rects)
 {
-    static_assert(sizeof(DownWeights<FS, Q>) + sizeof(DownArgs) < 32000, "kernel parameters exceed the 32 KB limit");
-    DownWeights<FS, Q> w;
+    static_assert(sizeof(DownWeightsN<FS, Q, NPASS>) + sizeof(DownArgs) < 32000, "kernel parameters exceed the 32 KB limit");
+    static_assert(NPASS <= DN_MAX_PASSES, "too many passes");
+    DownWeightsN<FS, Q, NPASS> w;
     memset(&w, 0, sizeof(w));
-    const float* blk = t->h_weights.data() + (size_t)wblock * FS * FS;
-    // set 0 pairs rows (2k, 2k+1); set 1 (odd ratios) pairs rows (2k-1, 2k); sums per half for the PRMT bias
-    double sum_x[2] = {0.0, 0.0}, sum_y[2] = {0.0, 0.0};
-    for (int set = 0; set < DownWeights<FS, Q>::NSET; ++set)
-        for (int ly = 0; ly < FS; ++ly)
-            for (int lx = 0; lx < FS; ++lx) {
-                const float v = blk[ly * FS + lx];
-                const int r = ly + set; // row index inside the (shifted) pair grid
-                float2& e = w.w[set][r >> 1][lx % Q][lx / Q];
-                if (r & 1) {
-                    e.y = v;
-                    sum_y[set] += v;
-                } else {
-                    e.x = v;
-                    sum_x[set] += v;
+    const int bits = sizeof(T) == 4 ? 32 : t_bits_from_peak(a.fr.peak);
+    for (int ps = 0; ps < NPASS; ++ps) {
+        const float* blk = t->h_weights.data() + (size_t)wblocks[ps] * FS * FS;
+        // set 0 pairs rows (2k, 2k+1); set 1 (odd ratios) pairs rows (2k-1, 2k); sums per half for the PRMT bias
+        double sum_x[2] = {0.0, 0.0}, sum_y[2] = {0.0, 0.0};
+        for (int set = 0; set < DownWeights<FS, Q>::NSET; ++set)
+            for (int ly = 0; ly < FS; ++ly)
+                for (int lx = 0; lx < FS; ++lx) {
+                    const float v = blk[ly * FS + lx];
+                    const int r = ly + set; // row index inside the (shifted) pair grid
+                    float2& e = w.pass[ps].w[set][r >> 1][lx % Q][lx / Q];
+                    if (r & 1) {
+                        e.y = v;
+                        sum_y[set] += v;
+                    } else {
+                        e.x = v;
+                        sum_x[set] += v;
+                    }
                 }
-            }
-    if (DownWeights<FS, Q>::NSET == 1) {
-        sum_x[1] = sum_x[0];
-        sum_y[1] = sum_y[0];
+        if (DownWeights<FS, Q>::NSET == 1) {
+            sum_x[1] = sum_x[0];
+            sum_y[1] = sum_y[0];
+        }
+        for (int j = 0; j < 2; ++j) {
+            a.pass[ps].bias_x[j] = (float)(0.5 * sum_x[j]);
+            a.pass[ps].bias_y[j] = (float)(0.5 * sum_y[j]);
+        }
     }
     if constexpr (sizeof(T) == 4) {
-        return launch_down_cfg<T, FS, Q, DN_NX, DN_NY, DN_CVT_FLOAT>(a, w, want_strips, n_frames, st, rects, n_rects);
+        return launch_down_cfg<T, FS, Q, DN_NX, DN_NY, DN_CVT_FLOAT, NPASS>(a, w, want_strips, n_frames, st, rects, n_rects);
     } else {
-        const int bits = t_bits_from_peak(a.fr.peak);
         if (bits <= 15) {
             // f = 0.5 + (x << pre_shift) / 65536  =>  sum(w f) = 0.5 sum(w) + sum(w x) * 2^(pre_shift - 16)
             a.pre_shift = 15 - bits;
-            for (int j = 0; j < 2; ++j) {
-                a.bias_x[j] = (float)(0.5 * sum_x[j]);
-                a.bias_y[j] = (float)(0.5 * sum_y[j]);
-            }
             a.out_scale = (float)(1 << (16 - a.pre_shift));
-            return launch_down_cfg<T, FS, Q, DN_NX, DN_NY, DN_CVT_PRMT>(a, w, want_strips, n_frames, st, rects, n_rects);
+            return launch_down_cfg<T, FS, Q, DN_NX, DN_NY, DN_CVT_PRMT, NPASS>(a, w, want_strips, n_frames, st, rects, n_rects);
         }
         if constexpr (sizeof(T) == 2)
-            return launch_down_cfg<T, FS, Q, DN_NX, DN_NY, DN_CVT_I2F>(a, w, want_strips, n_frames, st, rects, n_rects);
+            return launch_down_cfg<T, FS, Q, DN_NX, DN_NY, DN_CVT_I2F, NPASS>(a, w, want_strips, n_frames, st, rects, n_rects);
         return 1;
     }
 }
 
 // 0 launched, 2 nothing to do, 1 unsupported geometry, <0 error
 template <typename T>
-int launch_down(const jinc_table* t, DownArgs& a, int q, int wblock, bool want_strips, int n_frames, cudaStream_t st, const Rect* rects,
-                int n_rects)
+int launch_down(const jinc_table* t, DownArgs& a, int q, const int* wblocks, bool want_strips, int n_frames, cudaStream_t st,
+                const Rect* rects, int n_rects)
 {
-    if (a.out_stride < 1) {
+    if (a.out_stride < 1)
         a.out_stride = 1;
-        a.out_x0 = a.x0;
-        a.out_y0 = a.y0;
-    }
-    const int key = q * 1000 + t->sc.fs;
+    const int np = a.n_passes < 1 ? 1 : a.n_passes;
+    const int key = np * 100000 + q * 1000 + t->sc.fs;
     switch (key) {
-#define JINC_DOWN_CASE(Q_, FS_) \
-    case Q_ * 1000 + FS_: return launch_down_fs<T, FS_, Q_>(t, a, wblock, want_strips, n_frames, st, rects, n_rects);
-        JINC_DOWN_CASE(2, 13) // tap 3, 1/2
-        JINC_DOWN_CASE(2, 17) // tap 4, 1/2
-        JINC_DOWN_CASE(2, 25) // tap 6, 1/2
-        JINC_DOWN_CASE(2, 33) // tap 8, 1/2
-        JINC_DOWN_CASE(3, 7)  // tap 3, 4:3 periodic passes
-        JINC_DOWN_CASE(3, 9)  // tap 4, 4:3 periodic passes
-        JINC_DOWN_CASE(3, 10) // tap 3, 2:3 periodic passes
-        JINC_DOWN_CASE(3, 13) // tap 4, 2:3 periodic passes
-        JINC_DOWN_CASE(3, 20) // tap 3, 1/3
-        JINC_DOWN_CASE(4, 26) // tap 3, 1/4
-        JINC_DOWN_CASE(4, 34) // tap 4, 1/4
-        JINC_DOWN_CASE(4, 50) // tap 6, 1/4
+#define JINC_DOWN_CASE(NP_, Q_, FS_) \
+    case NP_ * 100000 + Q_ * 1000 + FS_: return launch_down_fs<T, FS_, Q_, NP_>(t, a, wblocks, want_strips, n_frames, st, rects, n_rects);
+        JINC_DOWN_CASE(1, 2, 13)  // tap 3, 1/2
+        JINC_DOWN_CASE(1, 2, 17)  // tap 4, 1/2
+        JINC_DOWN_CASE(1, 2, 25)  // tap 6, 1/2
+        JINC_DOWN_CASE(1, 2, 33)  // tap 8, 1/2
+        JINC_DOWN_CASE(16, 3, 7)  // tap 3, 4:3 periodic: sixteen passes in one launch
+        JINC_DOWN_CASE(16, 3, 9)  // tap 4, 4:3 periodic
+        JINC_DOWN_CASE(4, 3, 10)  // tap 3, 2:3 periodic: four passes in one launch
+        JINC_DOWN_CASE(4, 3, 13)  // tap 4, 2:3 periodic
+        JINC_DOWN_CASE(1, 3, 20)  // tap 3, 1/3
+        JINC_DOWN_CASE(1, 4, 26)  // tap 3, 1/4
+        JINC_DOWN_CASE(1, 4, 34)  // tap 4, 1/4
+        JINC_DOWN_CASE(1, 4, 50)  // tap 6, 1/4
 #undef JINC_DOWN_CASE
     default: return 1;
     }

@@ -2,5 +2,5 @@
 #include "jinc_down.cuh"
 
 namespace jinc_rs {
-template int launch_down<float>(const jinc_table*, DownArgs&, int, int, bool, int, cudaStream_t, const Rect*, int);
+template int launch_down<float>(const jinc_table*, DownArgs&, int, const int*, bool, int, cudaStream_t, const Rect*, int);
 }

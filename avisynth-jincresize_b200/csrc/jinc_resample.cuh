@@ -883,18 +883,34 @@ struct alignas(16) DownWeights {
     float2 w[NSET][NKWMAX][Q][MT]; // set 0: [k][p][m] = {w[2k][Q*m+p], w[2k+1][Q*m+p]}; set 1: {w[2k-1][..], w[2k][..]}; outside the window 0
 };
 
+// the weight blocks of all passes of one launch (1 for an integer ratio; P*P for the periodic paths: blockIdx.z = pass)
+template <int FS, int Q, int NPASS>
+struct alignas(16) DownWeightsN {
+    DownWeights<FS, Q> pass[NPASS];
+};
+
+constexpr int DN_MAX_PASSES = 16;
+
+// what differs between the passes of a launch
+struct DownPass {
+    int tsx0, tsy0;       // window origin of output (x0, y0)
+    int out_x0, out_y0;   // plane coordinates of (x0, y0)
+    float bias_x[2], bias_y[2]; // PRMT conversion, output row j of a thread: out = ((acc.x - bias_x[j]) + (acc.y - bias_y[j])) * out_scale
+};
+
 struct DownArgs {
     FrameSet fr;
     StripArgs st;
     int src_w, src_h;
-    int x0, y0, x1, y1;  // output rectangle produced by the tiles (y0..y1 already cut to the row band); for a periodic pass
-                         // these count CELLS of the pass's sub-lattice
-    int out_x0, out_y0, out_stride; // plane coordinates of (x0, y0) and the distance between neighbouring outputs (1, or P)
-    int tsx0, tsy0;      // window origin of output (x0, y0)
+    int x0, y0, x1, y1;  // output rectangle produced by the tiles (y0..y1 already cut to the row band); for the periodic
+                         // paths these count CELLS of a pass's sub-lattice
+    int out_stride;      // distance between neighbouring outputs in the plane (1, or P for a periodic pass)
+    int n_passes;
+    DownPass pass[DN_MAX_PASSES];
     int tiles_x, tiles_per_plane, interior_blocks, strip_blocks, strip_shift;
     unsigned tiles_x_magic, tiles_per_plane_magic; // div_magic of the two tile divisors
     int pre_shift;       // PRMT conversion: samples are staged as x << pre_shift
-    float bias_x[2], bias_y[2], out_scale; // PRMT conversion, output row j of a thread: out = ((acc.x - bias_x[j]) + (acc.y - bias_y[j])) * out_scale
+    float out_scale;     // PRMT conversion: power-of-two rescale of the de-biased sum
 };
 
 // ---- launch entry points, one explicit instantiation per sample type (jinc_up2x_*.cu, jinc_down_*.cu)
@@ -903,8 +919,8 @@ template <typename T>
 int launch_up2x(const jinc_table* t, UpArgs& a, long long strip_blocks, int n_frames, cudaStream_t st);
 // 0 launched, 2 nothing to do, 1 unsupported geometry, <0 error
 template <typename T>
-int launch_down(const jinc_table* t, DownArgs& a, int q, int wblock, bool want_strips, int n_frames, cudaStream_t st, const Rect* rects,
-                int n_rects);
+int launch_down(const jinc_table* t, DownArgs& a, int q, const int* wblocks, bool want_strips, int n_frames, cudaStream_t st,
+                const Rect* rects, int n_rects);
 
 inline bool periodic_supported(const jinc_table* t)
 {

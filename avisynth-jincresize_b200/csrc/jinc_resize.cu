@@ -310,34 +310,36 @@ int launch_typed(const jinc_table* t, const FrameSet& fr, int n_frames, int y_be
                 rects[n_rects++] = Rect{0, fy0, t->ix0, fy1};
                 rects[n_rects++] = Rect{t->ix1, fy0, W, fy1};
             }
-            bool first = true;
+            // one launch, one pass (blockIdx.z) per phase pair: an integer-ratio-Q problem over the cells, written with
+            // stride P; the border strips ride on pass 0
+            DownArgs a;
+            memset(&a, 0, sizeof(a));
+            a.fr = fr;
+            a.st = sa;
+            a.src_w = t->sc.src_w;
+            a.src_h = t->sc.src_h;
+            a.x0 = 0;
+            a.x1 = u.ncx;
+            a.y0 = cb;
+            a.y1 = ce;
+            a.out_stride = u.P;
+            a.n_passes = u.P * u.P;
+            int wblocks[DN_MAX_PASSES];
             for (int py = 0; py < u.P; ++py)
                 for (int px = 0; px < u.P; ++px) {
-                    // one pass per phase pair: an integer-ratio-Q problem over the cells, written with stride P
-                    DownArgs a;
-                    memset(&a, 0, sizeof(a));
-                    a.fr = fr;
-                    a.st = sa;
-                    a.src_w = t->sc.src_w;
-                    a.src_h = t->sc.src_h;
-                    a.x0 = 0;
-                    a.x1 = u.ncx;
-                    a.y0 = cb;
-                    a.y1 = ce;
-                    a.tsx0 = u.sx0 + u.ox[px];
-                    a.tsy0 = u.sy0 + u.oy[py] + u.Q * cb;
-                    a.out_x0 = u.x0 + px;
-                    a.out_y0 = u.y0 + u.P * cb + py;
-                    a.out_stride = u.P;
-                    a.interior_blocks = (parts & JINC_PART_INTERIOR) ? 1 : 0;
-                    const bool strips_now = first && n_rects > 0; // the border strips ride on the first pass
-                    const int rc = launch_down<T>(t, a, u.Q, u.wblock[py][px], strips_now, n_frames, st, rects, strips_now ? n_rects : 0);
-                    if (rc < 0 || rc == 1)
-                        return rc < 0 ? rc : jinc_fail(JINC_E_UNSUPPORTED, "resize: periodic pass not instantiated (fs %d)", t->sc.fs);
-                    if (rc == 0)
-                        ++*launches;
-                    first = false;
+                    DownPass& ps = a.pass[py * u.P + px];
+                    ps.tsx0 = u.sx0 + u.ox[px];
+                    ps.tsy0 = u.sy0 + u.oy[py] + u.Q * cb;
+                    ps.out_x0 = u.x0 + px;
+                    ps.out_y0 = u.y0 + u.P * cb + py;
+                    wblocks[py * u.P + px] = u.wblock[py][px];
                 }
+            a.interior_blocks = (parts & JINC_PART_INTERIOR) ? 1 : 0;
+            const int rc = launch_down<T>(t, a, u.Q, wblocks, n_rects > 0, n_frames, st, rects, n_rects);
+            if (rc < 0 || rc == 1)
+                return rc < 0 ? rc : jinc_fail(JINC_E_UNSUPPORTED, "resize: periodic passes not instantiated (fs %d)", t->sc.fs);
+            if (rc == 0)
+                ++*launches;
             return JINC_OK;
         }
     }
@@ -361,10 +363,14 @@ int launch_typed(const jinc_table* t, const FrameSet& fr, int n_frames, int y_be
             a.x1 = d.x0 + d.nx;
             a.y0 = fy0;
             a.y1 = fy1;
-            a.tsx0 = d.sx0;
-            a.tsy0 = d.sy0 + d.qy * (fy0 - d.y0);
+            a.n_passes = 1;
+            a.out_stride = 1;
+            a.pass[0].tsx0 = d.sx0;
+            a.pass[0].tsy0 = d.sy0 + d.qy * (fy0 - d.y0);
+            a.pass[0].out_x0 = a.x0;
+            a.pass[0].out_y0 = a.y0;
             a.interior_blocks = (parts & JINC_PART_INTERIOR) ? 1 : 0; // resolved to the tile count by the launcher
-            const int rc = launch_down<T>(t, a, d.qx, d.wblock, n_rects > 0, n_frames, st, rects, n_rects);
+            const int rc = launch_down<T>(t, a, d.qx, &d.wblock, n_rects > 0, n_frames, st, rects, n_rects);
             if (rc != 1) {
                 if (rc == 0)
                     ++*launches;

@@ -481,7 +481,7 @@ def run_b200(args, cfg):
             "e2e_plugin": plugin,
             "gpu_launches": gpu_launches,
             "clocks": clocks,
-            "roofline": {"bound": "fp32_fma", "kernel": {1: "resample_up2x", 2: "resample_down", 3: "resample_down (2:3 periodic, first of 4 passes)"}.get(i0.fast_path, "resample_strips") + " (luma-table planes of all %d frames: interior tiles + border strips)" % F,
+            "roofline": {"bound": "fp32_fma", "kernel": {1: "resample_up2x", 2: "resample_down", 3: "resample_down (periodic passes in one launch)"}.get(i0.fast_path, "resample_strips") + " (luma-table planes of all %d frames: interior tiles + border strips)" % F,
                          "achieved": achieved_tf, "peak": fma_peak, "unit": "TFLOP/s", "frac": achieved_tf / fma_peak,
                          "peak_source": fma_how, "traffic": ncu_traffic(args.config, F), "launch_ms": dom_avg_ms,
                          "algorithmic_flop_per_launch": dom_flop, "share_of_step": sum(dom_ms) / ms_total},
