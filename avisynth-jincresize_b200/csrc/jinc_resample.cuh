@@ -791,14 +791,16 @@ struct UpArgs {
     int strip_blocks, strip_shift;
 };
 
-inline bool up2x_supported(int fs) { return fs == 7 || fs == 9 || fs == 13 || fs == 17; }
+inline bool up2x_supported(int fs) { return fs == 7 || fs == 9 || fs == 11 || fs == 13 || fs == 15 || fs == 17; } // taps 3..8
 
 inline size_t up2x_smem_bytes(int fs)
 {
     switch (fs) {
     case 7: return UpGeom<7>::SMEM;
     case 9: return UpGeom<9>::SMEM;
+    case 11: return UpGeom<11>::SMEM;
     case 13: return UpGeom<13>::SMEM;
+    case 15: return UpGeom<15>::SMEM;
     case 17: return UpGeom<17>::SMEM;
     default: return 0;
     }

@@ -237,7 +237,9 @@ int launch_up2x(const jinc_table* t, UpArgs& a, long long strip_blocks, int n_fr
     switch (t->sc.fs) {
     case 7: return launch_up2x_fs<T, 7>(t, a, strip_blocks, n_frames, st);   // tap 3  (Jinc36Resize)
     case 9: return launch_up2x_fs<T, 9>(t, a, strip_blocks, n_frames, st);   // tap 4  (Jinc64Resize)
+    case 11: return launch_up2x_fs<T, 11>(t, a, strip_blocks, n_frames, st); // tap 5
     case 13: return launch_up2x_fs<T, 13>(t, a, strip_blocks, n_frames, st); // tap 6  (Jinc144Resize)
+    case 15: return launch_up2x_fs<T, 15>(t, a, strip_blocks, n_frames, st); // tap 7
     case 17: return launch_up2x_fs<T, 17>(t, a, strip_blocks, n_frames, st); // tap 8  (Jinc256Resize)
     default: return 1;
     }

@@ -80,6 +80,8 @@ SMALL_CASES = [
     ("quarter_tap6_f32_y", ah.Format("y", 32), 640, 400, 160, 100, dict(tap=6)),
     # exact 2x with the remaining alias taps and a third-size / 3x ratio (general kernel)
     ("up2x_tap6_420p8", ah.YUV420P8, 200, 120, 400, 240, dict(tap=6, cplace="mpeg1")),
+    ("up2x_tap5_444p10", ah.Format("444", 10), 160, 96, 320, 192, dict(tap=5)),
+    ("up2x_tap7_f32_y", ah.Format("y", 32), 160, 96, 320, 192, dict(tap=7, src_left=0.5)),
     ("third_tap3_y8", ah.Format("y", 8), 600, 360, 200, 120, dict(tap=3)),
     # 3:2 upscale (720p -> 1080p class): NOT periodic under the reference's float-accumulated positions (4+ phases per axis)
     ("up1p5_tap3_420p8", ah.YUV420P8, 320, 180, 480, 270, dict(tap=3)),
