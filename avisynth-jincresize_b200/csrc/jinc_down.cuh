@@ -307,6 +307,8 @@ int launch_down(const jinc_table* t, DownArgs& a, int q, const int* wblocks, boo
     switch (key) {
 #define JINC_DOWN_CASE(NP_, Q_, FS_) \
     case NP_ * 100000 + Q_ * 1000 + FS_: return launch_down_fs<T, FS_, Q_, NP_>(t, a, wblocks, want_strips, n_frames, st, rects, n_rects);
+        JINC_DOWN_CASE(16, 1, 7)  // tap 3, 4x upscale: sixteen unit-step passes in one launch
+        JINC_DOWN_CASE(16, 1, 9)  // tap 4, 4x upscale
         JINC_DOWN_CASE(1, 2, 13)  // tap 3, 1/2
         JINC_DOWN_CASE(1, 2, 17)  // tap 4, 1/2
         JINC_DOWN_CASE(1, 2, 25)  // tap 6, 1/2

@@ -927,12 +927,12 @@ int launch_down(const jinc_table* t, DownArgs& a, int q, const int* wblocks, boo
 inline bool periodic_supported(const jinc_table* t)
 {
     const PeriodicPlan& u = t->periodic;
-    if (!u.ok || u.Q != 3)
+    if (!u.ok)
         return false;
-    if (u.P == 2)
+    if (u.P == 2 && u.Q == 3)
         return t->sc.fs == 10 || t->sc.fs == 13; // taps 3 and 4 at 2:3 (1080p -> 720p)
-    if (u.P == 4)
-        return t->sc.fs == 7 || t->sc.fs == 9;   // taps 3 and 4 at 4:3 (1080p -> 1440p)
+    if (u.P == 4 && (u.Q == 3 || u.Q == 1))
+        return t->sc.fs == 7 || t->sc.fs == 9;   // taps 3 and 4 at 4:3 (1080p -> 1440p) and at 4x (540p -> 2160p)
     return false;
 }
 

@@ -95,6 +95,9 @@ SMALL_CASES = [
     # 4:3 upscale (1080p -> 1440p class): exactly periodic (source step 0.75), sixteen passes
     ("up4to3_tap3_420p8", ah.YUV420P8, 360, 204, 480, 272, dict(tap=3)),
     ("up4to3_tap4_y16", ah.Format("y", 16), 270, 150, 360, 200, dict(tap=4)),
+    # 4x upscale: exactly periodic (source step 0.25), sixteen unit-step passes
+    ("up4x_tap3_420p8", ah.YUV420P8, 160, 90, 640, 360, dict(tap=3)),
+    ("up4x_tap4_rgbp16", ah.Format("rgbp", 16), 120, 68, 480, 272, dict(tap=4)),
     # general kernel with four planes on one table, and a steep irregular downscale whose source footprints do not fit
     # in shared memory (per-plane fallback of the general kernel)
     ("rgbap10_irregular_up", ah.Format("rgbap", 10), 200, 120, 290, 170, dict(tap=4)),
