@@ -5,10 +5,13 @@
 //
 // Frame pipeline: every GPU of the filter owns `slots_per_device` in-flight slots, each with its own CUDA
 // stream, device source/destination buffers and pinned staging buffers laid out identically to the device
-// buffers (so one cudaMemcpyAsync moves all planes).  A frame takes a slot (GPUs round-robin), is staged,
-// copied H2D, resampled and copied D2H on that slot's stream; concurrent callers (AviSynth Prefetch threads,
-// or jinc_filter_submit) therefore overlap staging, PCIe transfers in both directions and kernels across
-// slots and GPUs.  Frames are independent, so there is no inter-GPU traffic and no collective.
+// buffers (so one cudaMemcpyAsync moves all planes).  A frame takes a slot (GPUs round-robin), is copied H2D,
+// resampled and copied D2H on that slot's stream; concurrent callers (AviSynth Prefetch threads, or
+// jinc_filter_submit) therefore overlap PCIe transfers in both directions and kernels across slots and GPUs.
+// Caller memory that is page-locked (by the caller, or registered here once a pageable frame buffer comes back:
+// jinc_hostmem.h) is moved by DMA directly; only first-seen pageable buffers are staged through the slot's pinned
+// mirror, with the copy split over helper threads.  Frames are independent, and so are row bands of one frame
+// (jinc_filter_process_bands): there is no inter-GPU traffic and no collective.
 #include <algorithm>
 #include <atomic>
 #include <condition_variable>
@@ -16,6 +19,9 @@
 #include <memory>
 #include <mutex>
 
+#include <random>
+
+#include "jinc_hostmem.h"
 #include "jinc_internal.h"
 
 // ================================================================ contexts
@@ -84,7 +90,16 @@ struct PlaneLayout {
     size_t src_pitch = 0, dst_pitch = 0;
 };
 
+// bytes written into a directly addressed destination plane before the transfers are enqueued; still there afterwards
+// means the transfer went elsewhere (stale registration of a buffer the host has freed and re-mapped)
+struct Sentinel {
+    unsigned char* at = nullptr;
+    uint64_t value = 0;
+};
+constexpr int kSentinelsPerPlane = 4;
+
 struct Slot {
+    enum State { FREE, BUSY, WAITING };
     int dev_index = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
@@ -92,40 +107,50 @@ struct Slot {
     unsigned char* d_dst = nullptr;
     unsigned char* h_src = nullptr; // pinned
     unsigned char* h_dst = nullptr; // pinned
-    bool busy = false;
+    State state = FREE;
     int64_t ticket = -1;
-    jinc_frame pending{}; // destination of an outstanding submit
+    jinc_frame pending{}; // the frame of an outstanding enqueue
     bool dst_direct = false;
+    jinc_hostmem::Pin src_pin, dst_pin;
+    Sentinel sentinel[JINC_MAX_PLANES * kSentinelsPerPlane];
+    int n_sentinels = 0;
 };
 
 struct DeviceState {
     jinc_ctx* ctx = nullptr;
     jinc_table* tables[2] = {nullptr, nullptr};
-    // ring of small device buffers holding the plane-pointer records of batched launches
+    // ring of small device buffers holding the plane-pointer records of batched launches; an entry is reused only after
+    // the launch that read it has finished (event), whatever streams the calls use
     static constexpr int kRing = 8;
     unsigned char* batch_ptrs[kRing] = {};
     size_t batch_cap[kRing] = {};
+    cudaEvent_t batch_done[kRing] = {};
     int batch_next = 0;
 };
 
-// rows of one plane between host and device: ONE linear transfer when both sides are tightly packed (the DMA engine
-// then moves a single extent instead of a descriptor per row), else a 2-D copy
-cudaError_t copy_plane_async(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t row_bytes, int rows,
+// rows of one plane between host and device.  `linear`: both sides have the same pitch and the bytes between rows may be
+// carried along, so ONE extent moves (the DMA engine takes a single descriptor instead of one per row); else a 2-D copy.
+cudaError_t copy_plane_async(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t row_bytes, int rows, bool linear,
                              cudaMemcpyKind kind, cudaStream_t st)
 {
-    if (dst_pitch == row_bytes && src_pitch == row_bytes)
-        return cudaMemcpyAsync(dst, src, row_bytes * static_cast<size_t>(rows), kind, st);
+    if (linear && dst_pitch == src_pitch)
+        return cudaMemcpyAsync(dst, src, dst_pitch * static_cast<size_t>(rows - 1) + row_bytes, kind, st);
     return cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, row_bytes, static_cast<size_t>(rows), kind, st);
 }
 
-bool is_pinned_host(const void* p)
+std::atomic<int64_t> g_direct_src{0}, g_direct_dst{0}, g_staged{0};
+std::atomic<int> g_live_filters{0};
+
+uint64_t fresh_nonce()
 {
-    cudaPointerAttributes at;
-    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
-        cudaGetLastError();
-        return false;
-    }
-    return at.type == cudaMemoryTypeHost;
+    static std::atomic<uint64_t> ctr{[] {
+        std::random_device rd;
+        return (static_cast<uint64_t>(rd()) << 32) ^ rd();
+    }()};
+    uint64_t z = ctr.fetch_add(0x9E3779B97F4A7C15ull) + 0x9E3779B97F4A7C15ull; // splitmix64
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
 }
 
 } // namespace
@@ -141,7 +166,7 @@ struct jinc_filter {
     std::vector<std::unique_ptr<Slot>> slots;
     std::mutex mu;
     std::condition_variable cv;
-    std::atomic<int64_t> next_ticket{0};
+    int64_t next_ticket = 0; // under mu
     std::atomic<int64_t> rr{0};
     std::atomic<int64_t> launches{0};
 };
@@ -196,48 +221,58 @@ void derive_table_params(const jinc_filter_params& p, jinc_table_params out[2], 
 
 void release_slot(jinc_filter* f, Slot* s)
 {
+    jinc_hostmem::release(&s->src_pin);
+    jinc_hostmem::release(&s->dst_pin);
     {
         std::lock_guard<std::mutex> lk(f->mu);
-        s->busy = false;
+        s->state = Slot::FREE;
         s->ticket = -1;
     }
     f->cv.notify_all();
 }
 
-// Take a free slot, preferring GPU (n mod G) so consecutive frames spread over all GPUs.
-Slot* acquire_slot(jinc_filter* f)
+// f->mu held: a free slot, on GPU `want` if it has one (`only`: on no other GPU)
+Slot* find_free_slot(jinc_filter* f, int want, bool only)
+{
+    Slot* any = nullptr;
+    for (auto& s : f->slots) {
+        if (s->state != Slot::FREE)
+            continue;
+        if (s->dev_index == want)
+            return s.get();
+        if (!any)
+            any = s.get();
+    }
+    return only ? nullptr : any;
+}
+
+// Take a free slot, preferring GPU (n mod G) so consecutive frames spread over all GPUs; the slot's ticket is assigned
+// under the lock.  block = false: nullptr when every slot is taken.
+Slot* acquire_slot(jinc_filter* f, bool block)
 {
     const int nd = static_cast<int>(f->devs.size());
     const int want = static_cast<int>(f->rr.fetch_add(1) % nd);
     std::unique_lock<std::mutex> lk(f->mu);
     for (;;) {
-        Slot* any = nullptr;
-        for (auto& s : f->slots) {
-            if (s->busy)
-                continue;
-            if (s->dev_index == want) {
-                s->busy = true;
-                return s.get();
-            }
-            if (!any)
-                any = s.get();
+        if (Slot* s = find_free_slot(f, want, false)) {
+            s->state = Slot::BUSY;
+            s->ticket = f->next_ticket++;
+            return s;
         }
-        if (any) {
-            any->busy = true;
-            return any;
-        }
+        if (!block)
+            return nullptr;
         f->cv.wait(lk);
     }
 }
 
-void copy_rows(unsigned char* dst, size_t dst_pitch, const unsigned char* src, ptrdiff_t src_pitch, size_t row_bytes, int rows)
+// the whole plane as the caller describes it (registration keys must not depend on the band being processed)
+bool plane_range(const void* base, ptrdiff_t pitch, size_t row_bytes, int rows, jinc_hostmem::Range* r)
 {
-    if (static_cast<ptrdiff_t>(dst_pitch) == src_pitch && dst_pitch == row_bytes) {
-        memcpy(dst, src, row_bytes * rows);
-        return;
-    }
-    for (int y = 0; y < rows; ++y)
-        memcpy(dst + static_cast<size_t>(y) * dst_pitch, src + static_cast<ptrdiff_t>(y) * src_pitch, row_bytes);
+    if (pitch < static_cast<ptrdiff_t>(row_bytes) || rows < 1)
+        return false; // bottom-up or overlapping rows: staged
+    r->lo = static_cast<const unsigned char*>(base);
+    r->hi = r->lo + static_cast<size_t>(pitch) * (rows - 1) + row_bytes;
+    return true;
 }
 
 // Enqueue H2D + kernels + D2H for output rows [y0,y1) (luma rows) of `frame` on slot s.
@@ -246,14 +281,15 @@ int enqueue_frame(jinc_filter* f, Slot* s, const jinc_frame* frame, int y0_luma,
     DeviceState& d = f->devs[s->dev_index];
     JINC_CUDA(cudaSetDevice(d.ctx->device));
     const int sb = f->p.sample_bytes;
+    const int np = f->p.n_planes;
+    const bool may_register = !(f->p.flags & JINC_FILTER_NO_HOST_REGISTER);
+    const bool padding_ok = (f->p.flags & JINC_FILTER_DST_PADDING_WRITABLE) != 0;
+    s->pending = *frame;
+    s->n_sentinels = 0;
 
-    // ---- source planes -> device
-    bool all_pinned = true;
-    for (int i = 0; i < f->p.n_planes; ++i)
-        all_pinned = all_pinned && is_pinned_host(frame->src[i]);
-    // per plane: the source rows this band's windows reach
+    // per plane: the output rows of this band and the source rows its windows reach
     int sy0[JINC_MAX_PLANES], sy1[JINC_MAX_PLANES], oy0[JINC_MAX_PLANES], oy1[JINC_MAX_PLANES];
-    for (int i = 0; i < f->p.n_planes; ++i) {
+    for (int i = 0; i < np; ++i) {
         const PlaneLayout& pl = f->planes[i];
         const jinc_table* t = d.tables[pl.table];
         const int shift = (pl.table == 1) ? f->p.sub_h : 0;
@@ -272,31 +308,55 @@ int enqueue_frame(jinc_filter* f, Slot* s, const jinc_frame* frame, int y0_luma,
             sy1[i] = std::min(hi, pl.src_h);
         }
     }
-    if (whole && !all_pinned) {
-        // pageable caller memory: stage into the slot's pinned mirror, then ONE copy for all planes
-        for (int i = 0; i < f->p.n_planes; ++i) {
-            const PlaneLayout& pl = f->planes[i];
-            copy_rows(s->h_src + pl.src_off, pl.src_pitch, static_cast<const unsigned char*>(frame->src[i]),
-                      frame->src_pitch[i], static_cast<size_t>(pl.src_w) * sb, pl.src_h);
+
+    // ---- source planes -> device
+    jinc_hostmem::Range rs[JINC_MAX_PLANES];
+    bool src_direct = true, src_packed = whole;
+    for (int i = 0; i < np; ++i) {
+        const PlaneLayout& pl = f->planes[i];
+        src_direct = src_direct && plane_range(frame->src[i], frame->src_pitch[i], static_cast<size_t>(pl.src_w) * sb, pl.src_h, &rs[i]);
+        src_packed = src_packed && frame->src_pitch[i] == static_cast<ptrdiff_t>(pl.src_pitch) &&
+                     static_cast<const unsigned char*>(frame->src[i]) - static_cast<const unsigned char*>(frame->src[0]) ==
+                         static_cast<ptrdiff_t>(pl.src_off);
+    }
+    src_direct = src_direct && jinc_hostmem::acquire(rs, np, may_register, &s->src_pin);
+    if (src_direct) {
+        g_direct_src.fetch_add(1, std::memory_order_relaxed);
+        if (src_packed) {
+            // the caller's planes are packed exactly like the slot (AviSynth+ frame buffers are): one transfer per frame
+            const PlaneLayout& last = f->planes[np - 1];
+            const size_t bytes = last.src_off + last.src_pitch * (last.src_h - 1) + static_cast<size_t>(last.src_w) * sb;
+            JINC_CUDA(cudaMemcpyAsync(s->d_src, frame->src[0], bytes, cudaMemcpyHostToDevice, s->stream));
+        } else {
+            for (int i = 0; i < np; ++i) {
+                const PlaneLayout& pl = f->planes[i];
+                const int rows = sy1[i] - sy0[i];
+                if (rows <= 0)
+                    continue;
+                JINC_CUDA(copy_plane_async(s->d_src + pl.src_off + static_cast<size_t>(sy0[i]) * pl.src_pitch, pl.src_pitch,
+                                           static_cast<const unsigned char*>(frame->src[i]) + static_cast<ptrdiff_t>(sy0[i]) * frame->src_pitch[i],
+                                           static_cast<size_t>(frame->src_pitch[i]), static_cast<size_t>(pl.src_w) * sb, rows, true,
+                                           cudaMemcpyHostToDevice, s->stream));
+            }
         }
-        JINC_CUDA(cudaMemcpyAsync(s->d_src, s->h_src, f->src_bytes, cudaMemcpyHostToDevice, s->stream));
     } else {
-        for (int i = 0; i < f->p.n_planes; ++i) {
+        // pageable caller memory seen for the first time (or not registrable): stage into the slot's pinned mirror
+        g_staged.fetch_add(1, std::memory_order_relaxed);
+        for (int i = 0; i < np; ++i) {
             const PlaneLayout& pl = f->planes[i];
             const int rows = sy1[i] - sy0[i];
             if (rows <= 0)
                 continue;
-            const unsigned char* hsrc = static_cast<const unsigned char*>(frame->src[i]) + static_cast<ptrdiff_t>(sy0[i]) * frame->src_pitch[i];
-            size_t hpitch = static_cast<size_t>(frame->src_pitch[i]);
-            if (!all_pinned) {
-                unsigned char* stage = s->h_src + pl.src_off + static_cast<size_t>(sy0[i]) * pl.src_pitch;
-                copy_rows(stage, pl.src_pitch, hsrc, frame->src_pitch[i], static_cast<size_t>(pl.src_w) * sb, rows);
-                hsrc = stage;
-                hpitch = pl.src_pitch;
-            }
-            JINC_CUDA(copy_plane_async(s->d_src + pl.src_off + static_cast<size_t>(sy0[i]) * pl.src_pitch, pl.src_pitch, hsrc, hpitch,
-                                       static_cast<size_t>(pl.src_w) * sb, rows, cudaMemcpyHostToDevice, s->stream));
+            jinc_hostmem::copy_rows(s->h_src + pl.src_off + static_cast<size_t>(sy0[i]) * pl.src_pitch, pl.src_pitch,
+                                    static_cast<const unsigned char*>(frame->src[i]) + static_cast<ptrdiff_t>(sy0[i]) * frame->src_pitch[i],
+                                    frame->src_pitch[i], static_cast<size_t>(pl.src_w) * sb, rows);
+            if (!whole)
+                JINC_CUDA(copy_plane_async(s->d_src + pl.src_off + static_cast<size_t>(sy0[i]) * pl.src_pitch, pl.src_pitch,
+                                           s->h_src + pl.src_off + static_cast<size_t>(sy0[i]) * pl.src_pitch, pl.src_pitch,
+                                           static_cast<size_t>(pl.src_w) * sb, rows, true, cudaMemcpyHostToDevice, s->stream));
         }
+        if (whole)
+            JINC_CUDA(cudaMemcpyAsync(s->d_src, s->h_src, f->src_bytes, cudaMemcpyHostToDevice, s->stream));
     }
 
     // ---- kernels: planes that share a table go out in one launch
@@ -305,7 +365,7 @@ int enqueue_frame(jinc_filter* f, Slot* s, const jinc_frame* frame, int y0_luma,
         void* dst[JINC_MAX_PLANES];
         ptrdiff_t sp[JINC_MAX_PLANES], dp[JINC_MAX_PLANES];
         int n = 0, yb = 0, ye = 0;
-        for (int i = 0; i < f->p.n_planes; ++i) {
+        for (int i = 0; i < np; ++i) {
             const PlaneLayout& pl = f->planes[i];
             if (pl.table != k)
                 continue;
@@ -327,33 +387,69 @@ int enqueue_frame(jinc_filter* f, Slot* s, const jinc_frame* frame, int y0_luma,
     }
 
     // ---- destination planes -> host
-    bool dst_pinned = true;
-    for (int i = 0; i < f->p.n_planes; ++i)
-        dst_pinned = dst_pinned && is_pinned_host(frame->dst[i]);
-    s->dst_direct = dst_pinned;
-    if (whole && !dst_pinned) {
+    jinc_hostmem::Range rd[JINC_MAX_PLANES];
+    bool dst_direct = true, dst_packed = whole, dst_tight = true;
+    for (int i = 0; i < np; ++i) {
+        const PlaneLayout& pl = f->planes[i];
+        const size_t row_bytes = static_cast<size_t>(pl.dst_w) * sb;
+        dst_direct = dst_direct && plane_range(frame->dst[i], frame->dst_pitch[i], row_bytes, pl.dst_h, &rd[i]);
+        dst_tight = dst_tight && frame->dst_pitch[i] == static_cast<ptrdiff_t>(row_bytes);
+        dst_packed = dst_packed && frame->dst_pitch[i] == static_cast<ptrdiff_t>(pl.dst_pitch) &&
+                     static_cast<unsigned char*>(frame->dst[i]) - static_cast<unsigned char*>(frame->dst[0]) == static_cast<ptrdiff_t>(pl.dst_off);
+    }
+    dst_direct = dst_direct && jinc_hostmem::acquire(rd, np, may_register, &s->dst_pin);
+    s->dst_direct = dst_direct;
+    const bool carry_padding = dst_tight || padding_ok; // bytes between rows (and planes) may be written
+    if (dst_direct) {
+        g_direct_dst.fetch_add(1, std::memory_order_relaxed);
+        if (jinc_hostmem::registered_here(&s->dst_pin)) {
+            // arrival check: sentinels at the corners of every plane's band must be overwritten by the transfer
+            for (int i = 0; i < np; ++i) {
+                const PlaneLayout& pl = f->planes[i];
+                const size_t row_bytes = static_cast<size_t>(pl.dst_w) * sb;
+                if (oy1[i] <= oy0[i] || row_bytes < sizeof(uint64_t))
+                    continue;
+                const int rows[2] = {oy0[i], oy1[i] - 1};
+                const size_t cols[2] = {0, row_bytes - sizeof(uint64_t)};
+                for (int a = 0; a < 2; ++a)
+                    for (int b = 0; b < 2; ++b) {
+                        Sentinel& q = s->sentinel[s->n_sentinels++];
+                        q.at = static_cast<unsigned char*>(frame->dst[i]) + static_cast<ptrdiff_t>(rows[a]) * frame->dst_pitch[i] + cols[b];
+                        q.value = fresh_nonce();
+                        memcpy(q.at, &q.value, sizeof(q.value));
+                    }
+            }
+        }
+        if (dst_packed && carry_padding) {
+            const PlaneLayout& last = f->planes[np - 1];
+            const size_t bytes = last.dst_off + last.dst_pitch * (last.dst_h - 1) + static_cast<size_t>(last.dst_w) * sb;
+            JINC_CUDA(cudaMemcpyAsync(frame->dst[0], s->d_dst, bytes, cudaMemcpyDeviceToHost, s->stream));
+        } else {
+            for (int i = 0; i < np; ++i) {
+                const PlaneLayout& pl = f->planes[i];
+                const int rows = oy1[i] - oy0[i];
+                if (rows <= 0)
+                    continue;
+                JINC_CUDA(copy_plane_async(static_cast<unsigned char*>(frame->dst[i]) + static_cast<ptrdiff_t>(oy0[i]) * frame->dst_pitch[i],
+                                           static_cast<size_t>(frame->dst_pitch[i]), s->d_dst + pl.dst_off + static_cast<size_t>(oy0[i]) * pl.dst_pitch,
+                                           pl.dst_pitch, static_cast<size_t>(pl.dst_w) * sb, rows, carry_padding, cudaMemcpyDeviceToHost,
+                                           s->stream));
+            }
+        }
+    } else if (whole) {
         JINC_CUDA(cudaMemcpyAsync(s->h_dst, s->d_dst, f->dst_bytes, cudaMemcpyDeviceToHost, s->stream));
     } else {
-        for (int i = 0; i < f->p.n_planes; ++i) {
+        for (int i = 0; i < np; ++i) {
             const PlaneLayout& pl = f->planes[i];
             const int rows = oy1[i] - oy0[i];
             if (rows <= 0)
                 continue;
-            unsigned char* hdst;
-            size_t hpitch;
-            if (dst_pinned) {
-                hdst = static_cast<unsigned char*>(frame->dst[i]) + static_cast<ptrdiff_t>(oy0[i]) * frame->dst_pitch[i];
-                hpitch = static_cast<size_t>(frame->dst_pitch[i]);
-            } else {
-                hdst = s->h_dst + pl.dst_off + static_cast<size_t>(oy0[i]) * pl.dst_pitch;
-                hpitch = pl.dst_pitch;
-            }
-            JINC_CUDA(copy_plane_async(hdst, hpitch, s->d_dst + pl.dst_off + static_cast<size_t>(oy0[i]) * pl.dst_pitch, pl.dst_pitch,
-                                       static_cast<size_t>(pl.dst_w) * sb, rows, cudaMemcpyDeviceToHost, s->stream));
+            const size_t off = pl.dst_off + static_cast<size_t>(oy0[i]) * pl.dst_pitch;
+            JINC_CUDA(copy_plane_async(s->h_dst + off, pl.dst_pitch, s->d_dst + off, pl.dst_pitch, static_cast<size_t>(pl.dst_w) * sb, rows,
+                                       true, cudaMemcpyDeviceToHost, s->stream));
         }
     }
     JINC_CUDA(cudaEventRecord(s->done, s->stream));
-    s->pending = *frame;
     return JINC_OK;
 }
 
@@ -363,9 +459,25 @@ int finish_frame(jinc_filter* f, Slot* s, int y0_luma, int y1_luma, bool whole)
     DeviceState& d = f->devs[s->dev_index];
     JINC_CUDA(cudaSetDevice(d.ctx->device));
     JINC_CUDA(cudaEventSynchronize(s->done));
-    if (s->dst_direct)
-        return JINC_OK;
     const int sb = f->p.sample_bytes;
+    bool from_mirror = !s->dst_direct;
+    if (s->dst_direct && s->n_sentinels > 0) {
+        bool arrived = true;
+        for (int k = 0; k < s->n_sentinels; ++k) {
+            uint64_t now;
+            memcpy(&now, s->sentinel[k].at, sizeof(now));
+            arrived = arrived && now != s->sentinel[k].value;
+        }
+        if (!arrived) {
+            // the registration behind this buffer is stale: drop it for good and deliver through the pinned mirror
+            jinc_hostmem::distrust(&s->dst_pin);
+            JINC_CUDA(cudaMemcpyAsync(s->h_dst, s->d_dst, f->dst_bytes, cudaMemcpyDeviceToHost, s->stream));
+            JINC_CUDA(cudaStreamSynchronize(s->stream));
+            from_mirror = true;
+        }
+    }
+    if (!from_mirror)
+        return JINC_OK;
     for (int i = 0; i < f->p.n_planes; ++i) {
         const PlaneLayout& pl = f->planes[i];
         const int shift = (pl.table == 1) ? f->p.sub_h : 0;
@@ -373,9 +485,9 @@ int finish_frame(jinc_filter* f, Slot* s, int y0_luma, int y1_luma, bool whole)
         const int b = whole ? pl.dst_h : std::min(pl.dst_h, (y1_luma + (1 << shift) - 1) >> shift);
         if (b <= a)
             continue;
-        copy_rows(static_cast<unsigned char*>(s->pending.dst[i]) + static_cast<ptrdiff_t>(a) * s->pending.dst_pitch[i],
-                  static_cast<size_t>(s->pending.dst_pitch[i]), s->h_dst + pl.dst_off + static_cast<size_t>(a) * pl.dst_pitch,
-                  static_cast<ptrdiff_t>(pl.dst_pitch), static_cast<size_t>(pl.dst_w) * sb, b - a);
+        jinc_hostmem::copy_rows(static_cast<unsigned char*>(s->pending.dst[i]) + static_cast<ptrdiff_t>(a) * s->pending.dst_pitch[i],
+                                static_cast<size_t>(s->pending.dst_pitch[i]), s->h_dst + pl.dst_off + static_cast<size_t>(a) * pl.dst_pitch,
+                                static_cast<ptrdiff_t>(pl.dst_pitch), static_cast<size_t>(pl.dst_w) * sb, b - a);
     }
     return JINC_OK;
 }
@@ -390,6 +502,26 @@ int check_frame(const jinc_filter* f, const jinc_frame* frame)
     return JINC_OK;
 }
 
+int submit_impl(jinc_filter* f, const jinc_frame* frame, int64_t* ticket, bool block)
+{
+    if (int rc = check_frame(f, frame))
+        return rc;
+    if (!ticket)
+        return jinc_fail(JINC_E_INVALID, "jinc_filter_submit: null ticket");
+    Slot* s = acquire_slot(f, block);
+    if (!s)
+        return jinc_fail(JINC_E_BUSY, "jinc_filter_try_submit: all %zu in-flight slots are taken", f->slots.size());
+    const int64_t tk = s->ticket;
+    const int rc = enqueue_frame(f, s, frame, 0, f->p.target_h, true);
+    if (rc != JINC_OK) {
+        cudaStreamSynchronize(s->stream);
+        release_slot(f, s);
+        return rc;
+    }
+    *ticket = tk;
+    return JINC_OK;
+}
+
 } // namespace
 
 extern "C" void jinc_filter_destroy(jinc_filter* f)
@@ -400,6 +532,8 @@ extern "C" void jinc_filter_destroy(jinc_filter* f)
         cudaSetDevice(f->devs[s->dev_index].ctx->device);
         if (s->stream)
             cudaStreamSynchronize(s->stream);
+        jinc_hostmem::release(&s->src_pin);
+        jinc_hostmem::release(&s->dst_pin);
         cudaFree(s->d_src);
         cudaFree(s->d_dst);
         cudaFreeHost(s->h_src);
@@ -412,14 +546,22 @@ extern "C" void jinc_filter_destroy(jinc_filter* f)
     for (DeviceState& d : f->devs) {
         if (d.ctx)
             cudaSetDevice(d.ctx->device);
-        for (unsigned char* b : d.batch_ptrs)
-            cudaFree(b);
+        for (int k = 0; k < DeviceState::kRing; ++k) {
+            if (d.batch_done[k]) {
+                cudaEventSynchronize(d.batch_done[k]);
+                cudaEventDestroy(d.batch_done[k]);
+            }
+            cudaFree(d.batch_ptrs[k]);
+        }
         jinc_table_destroy(d.tables[0]);
         jinc_table_destroy(d.tables[1]);
         jinc_ctx_destroy(d.ctx);
     }
     delete f;
+    g_live_filters.fetch_sub(1);
 }
+
+extern "C" int jinc_filter_live_count(void) { return g_live_filters.load(); }
 
 extern "C" int jinc_filter_create(const jinc_filter_params* p, jinc_filter** out)
 {
@@ -430,12 +572,19 @@ extern "C" int jinc_filter_create(const jinc_filter_params* p, jinc_filter** out
         return jinc_fail(JINC_E_INVALID, "jinc_filter_create: n_planes must be 1..4");
     if (p->sample_bytes != 1 && p->sample_bytes != 2 && p->sample_bytes != 4)
         return jinc_fail(JINC_E_INVALID, "jinc_filter_create: sample_bytes must be 1, 2 or 4");
+    // bits feed peak = (1 << bits) - 1 (:793): 8 for one-byte samples, 10..16 for two-byte samples; float ignores it
+    if ((p->sample_bytes == 1 && p->bits != 8) || (p->sample_bytes == 2 && (p->bits < 9 || p->bits > 16)))
+        return jinc_fail(JINC_E_INVALID, "jinc_filter_create: %d bits per component do not fit %d-byte samples", p->bits, p->sample_bytes);
     if (p->tap < 1 || p->tap > 16)
         return jinc_fail(JINC_E_INVALID, "JincResize: tap must be between 1..16.");
     if (p->src_w < 1 || p->src_h < 1 || p->target_w < 1 || p->target_h < 1)
         return jinc_fail(JINC_E_INVALID, "jinc_filter_create: clip dimensions must be positive");
     if (p->sub_w < 0 || p->sub_w > 2 || p->sub_h < 0 || p->sub_h > 2)
         return jinc_fail(JINC_E_INVALID, "jinc_filter_create: bad chroma subsampling");
+    if (p->n_devices > JINC_MAX_DEVICES)
+        return jinc_fail(JINC_E_INVALID, "jinc_filter_create: at most %d devices", JINC_MAX_DEVICES);
+    if (p->slots_per_device < 0 || p->slots_per_device > 64)
+        return jinc_fail(JINC_E_INVALID, "jinc_filter_create: slots_per_device must be 0..64");
 
     int visible = jinc_device_count();
     if (visible == 0)
@@ -445,16 +594,19 @@ extern "C" int jinc_filter_create(const jinc_filter_params* p, jinc_filter** out
         for (int i = 0; i < visible && i < JINC_MAX_DEVICES; ++i)
             dev_ids.push_back(i);
     } else {
-        for (int i = 0; i < p->n_devices && i < JINC_MAX_DEVICES; ++i)
+        for (int i = 0; i < p->n_devices; ++i)
             dev_ids.push_back(p->devices[i]);
     }
 
     std::unique_ptr<jinc_filter, void (*)(jinc_filter*)> f(new jinc_filter(), jinc_filter_destroy);
+    g_live_filters.fetch_add(1);
     f->p = *p;
     f->peak = (p->sample_bytes == 4) ? 0.f : static_cast<float>((1 << p->bits) - 1); // :793
     derive_table_params(*p, f->tparams, &f->n_tables);
 
-    // plane layout shared by device and pinned buffers
+    // Plane layout shared by device and pinned buffers: 64-byte pitches and 64-byte plane offsets.  Vector loads/stores
+    // stay aligned, a plane whose host rows have the same pitch moves as ONE linear transfer instead of a row-by-row 2-D
+    // copy, and a frame buffer packed by the same rule (AviSynth+ frame buffers are) moves as one transfer per frame.
     size_t so = 0, dof = 0;
     for (int i = 0; i < p->n_planes; ++i) {
         PlaneLayout& pl = f->planes[i];
@@ -464,38 +616,39 @@ extern "C" int jinc_filter_create(const jinc_filter_params* p, jinc_filter** out
         pl.src_h = tp.src_h;
         pl.dst_w = tp.dst_w;
         pl.dst_h = tp.dst_h;
-        // 64-byte pitches: vector loads/stores stay aligned, and for the usual widths the pitch equals the row size, so a
-        // plane whose host rows are tightly packed moves as ONE linear DMA transfer instead of a row-by-row 2-D copy
         pl.src_pitch = align_up(static_cast<size_t>(pl.src_w) * p->sample_bytes, 64);
         pl.dst_pitch = align_up(static_cast<size_t>(pl.dst_w) * p->sample_bytes, 64);
         pl.src_off = so;
         pl.dst_off = dof;
-        so += align_up(pl.src_pitch * pl.src_h, 256);
-        dof += align_up(pl.dst_pitch * pl.dst_h, 256);
+        so += pl.src_pitch * pl.src_h;
+        dof += pl.dst_pitch * pl.dst_h;
     }
+    so = align_up(so, 256);
+    dof = align_up(dof, 256);
     f->src_bytes = so;
     f->dst_bytes = dof;
 
-    // frames in flight per GPU: a slot is held from the staging copy of the source until the output has been copied out,
-    // mostly host memcpy time for pageable callers, so small frames get more slots (3..8, about 512 MB per GPU)
+    // frames in flight per GPU: a slot is held from the first copy of the source until the output has arrived, so small
+    // frames get more slots (3..8, about 512 MB per GPU)
     int spd = p->slots_per_device;
     if (spd <= 0) {
         const size_t per_slot = std::max<size_t>(so + dof, 1);
         spd = static_cast<int>(std::min<size_t>(8, std::max<size_t>(3, (static_cast<size_t>(512) << 20) / per_slot)));
     }
     for (size_t di = 0; di < dev_ids.size(); ++di) {
-        DeviceState d;
+        f->devs.emplace_back(); // owned by the filter from here on: an early return frees whatever has been created
+        DeviceState& d = f->devs.back();
         int rc = jinc_ctx_create(dev_ids[di], &d.ctx);
         if (rc != JINC_OK)
             return rc;
-        f->devs.push_back(d);
         for (int k = 0; k < f->n_tables; ++k) {
-            rc = jinc_table_create(f->devs.back().ctx, &f->tparams[k], &f->devs.back().tables[k]);
+            rc = jinc_table_create(d.ctx, &f->tparams[k], &d.tables[k]);
             if (rc != JINC_OK)
                 return rc;
         }
         for (int sidx = 0; sidx < spd; ++sidx) {
-            auto s = std::make_unique<Slot>();
+            f->slots.push_back(std::make_unique<Slot>());
+            Slot* s = f->slots.back().get();
             s->dev_index = static_cast<int>(di);
             JINC_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
             JINC_CUDA(cudaEventCreateWithFlags(&s->done, cudaEventDisableTiming));
@@ -504,10 +657,8 @@ extern "C" int jinc_filter_create(const jinc_filter_params* p, jinc_filter** out
                 cudaHostAlloc(reinterpret_cast<void**>(&s->h_src), so, cudaHostAllocPortable) != cudaSuccess ||
                 cudaHostAlloc(reinterpret_cast<void**>(&s->h_dst), dof, cudaHostAllocPortable) != cudaSuccess) {
                 const char* msg = cudaGetErrorString(cudaGetLastError());
-                f->slots.push_back(std::move(s));
                 return jinc_fail(JINC_E_NOMEM, "JincResize: failed to allocate frame buffers (%zu + %zu bytes): %s", so, dof, msg);
             }
-            f->slots.push_back(std::move(s));
         }
     }
     *out = f.release();
@@ -523,13 +674,29 @@ extern "C" const jinc_table* jinc_filter_table(const jinc_filter* f, int k)
 
 extern "C" int jinc_filter_num_tables(const jinc_filter* f) { return f ? f->n_tables : 0; }
 extern "C" int jinc_filter_num_devices(const jinc_filter* f) { return f ? static_cast<int>(f->devs.size()) : 0; }
+extern "C" int jinc_filter_num_slots(const jinc_filter* f) { return f ? static_cast<int>(f->slots.size()) : 0; }
 extern "C" int64_t jinc_filter_kernel_launches(const jinc_filter* f) { return f ? f->launches.load() : 0; }
+
+extern "C" void jinc_host_buffer_stats(int64_t* registered_bytes, int64_t* registrations, int64_t* direct_src_frames,
+                                       int64_t* direct_dst_frames, int64_t* staged_frames)
+{
+    if (registered_bytes)
+        *registered_bytes = static_cast<int64_t>(jinc_hostmem::registered_bytes());
+    if (registrations)
+        *registrations = jinc_hostmem::registrations();
+    if (direct_src_frames)
+        *direct_src_frames = g_direct_src.load();
+    if (direct_dst_frames)
+        *direct_dst_frames = g_direct_dst.load();
+    if (staged_frames)
+        *staged_frames = g_staged.load();
+}
 
 extern "C" int jinc_filter_process(jinc_filter* f, const jinc_frame* frame)
 {
     if (int rc = check_frame(f, frame))
         return rc;
-    Slot* s = acquire_slot(f);
+    Slot* s = acquire_slot(f, true);
     int rc = enqueue_frame(f, s, frame, 0, f->p.target_h, true);
     if (rc == JINC_OK)
         rc = finish_frame(f, s, 0, f->p.target_h, true);
@@ -601,6 +768,8 @@ extern "C" int jinc_filter_process_device_batch(jinc_filter* f, int device_index
             for (int i = 0; i < f->p.n_planes; ++i) {
                 if (f->planes[i].table != k)
                     continue;
+                if (!frames[fi].src[i] || !frames[fi].dst[i])
+                    return jinc_fail(JINC_E_INVALID, "jinc_filter_process_device_batch: frame %d plane %d has a null pointer", fi, i);
                 src[n] = frames[fi].src[i];
                 dst[n] = frames[fi].dst[i];
                 sp[n] = frames[fi].src_pitch[i];
@@ -614,26 +783,31 @@ extern "C" int jinc_filter_process_device_batch(jinc_filter* f, int device_index
         }
         if (n == 0)
             continue;
-        unsigned char* dbuf;
-        {
-            std::lock_guard<std::mutex> lk(f->mu);
-            const int slot = d.batch_next;
-            d.batch_next = (d.batch_next + 1) % DeviceState::kRing;
-            if (d.batch_cap[slot] < host.size()) {
-                cudaFree(d.batch_ptrs[slot]);
-                d.batch_ptrs[slot] = nullptr;
-                d.batch_cap[slot] = 0;
-                if (cudaMalloc(reinterpret_cast<void**>(&d.batch_ptrs[slot]), host.size()) != cudaSuccess)
-                    return jinc_fail(JINC_E_NOMEM, "jinc_filter_process_device_batch: cudaMalloc(%zu) failed", host.size());
-                d.batch_cap[slot] = host.size();
-            }
-            dbuf = d.batch_ptrs[slot];
+        // The whole sequence -- take the ring entry, order it after its previous reader, upload, launch, record -- runs
+        // under the lock, so two callers on different streams cannot interleave on one entry.
+        std::lock_guard<std::mutex> lk(f->mu);
+        const int slot = d.batch_next;
+        d.batch_next = (d.batch_next + 1) % DeviceState::kRing;
+        if (!d.batch_done[slot])
+            JINC_CUDA(cudaEventCreateWithFlags(&d.batch_done[slot], cudaEventDisableTiming));
+        else
+            JINC_CUDA(cudaStreamWaitEvent(st, d.batch_done[slot], 0)); // the launch that last read this entry
+        if (d.batch_cap[slot] < host.size()) {
+            JINC_CUDA(cudaEventSynchronize(d.batch_done[slot])); // no-op for a fresh event
+            cudaFree(d.batch_ptrs[slot]);
+            d.batch_ptrs[slot] = nullptr;
+            d.batch_cap[slot] = 0;
+            if (cudaMalloc(reinterpret_cast<void**>(&d.batch_ptrs[slot]), host.size()) != cudaSuccess)
+                return jinc_fail(JINC_E_NOMEM, "jinc_filter_process_device_batch: cudaMalloc(%zu) failed", host.size());
+            d.batch_cap[slot] = host.size();
         }
+        unsigned char* dbuf = d.batch_ptrs[slot];
         // pageable source: staged by the runtime before the call returns, ordered before the kernel on `st`
         JINC_CUDA(cudaMemcpyAsync(dbuf, host.data(), host.size(), cudaMemcpyHostToDevice, st));
         int launched = 0;
         const int rc = jinc_launch_resize_batch(d.ctx, d.tables[k], f->p.sample_bytes, f->peak, n, dbuf, n_frames, st, &launched, parts);
         f->launches.fetch_add(launched);
+        JINC_CUDA(cudaEventRecord(d.batch_done[slot], st));
         if (rc != JINC_OK)
             return rc;
     }
@@ -642,20 +816,12 @@ extern "C" int jinc_filter_process_device_batch(jinc_filter* f, int device_index
 
 extern "C" int jinc_filter_submit(jinc_filter* f, const jinc_frame* frame, int64_t* ticket)
 {
-    if (int rc = check_frame(f, frame))
-        return rc;
-    if (!ticket)
-        return jinc_fail(JINC_E_INVALID, "jinc_filter_submit: null ticket");
-    Slot* s = acquire_slot(f);
-    const int rc = enqueue_frame(f, s, frame, 0, f->p.target_h, true);
-    if (rc != JINC_OK) {
-        cudaStreamSynchronize(s->stream);
-        release_slot(f, s);
-        return rc;
-    }
-    s->ticket = f->next_ticket.fetch_add(1);
-    *ticket = s->ticket;
-    return JINC_OK;
+    return submit_impl(f, frame, ticket, true);
+}
+
+extern "C" int jinc_filter_try_submit(jinc_filter* f, const jinc_frame* frame, int64_t* ticket)
+{
+    return submit_impl(f, frame, ticket, false);
 }
 
 extern "C" int jinc_filter_wait(jinc_filter* f, int64_t ticket)
@@ -666,11 +832,14 @@ extern "C" int jinc_filter_wait(jinc_filter* f, int64_t ticket)
     {
         std::lock_guard<std::mutex> lk(f->mu);
         for (auto& c : f->slots)
-            if (c->busy && c->ticket == ticket)
+            if (c->state == Slot::BUSY && c->ticket == ticket) {
                 s = c.get();
+                s->state = Slot::WAITING; // a second waiter on the same ticket finds nothing
+            }
     }
     if (!s)
-        return jinc_fail(JINC_E_INVALID, "jinc_filter_wait: unknown ticket %lld", static_cast<long long>(ticket));
+        return jinc_fail(JINC_E_INVALID, "jinc_filter_wait: unknown ticket %lld (never issued, or already waited on)",
+                         static_cast<long long>(ticket));
     const int rc = finish_frame(f, s, 0, f->p.target_h, true);
     release_slot(f, s);
     return rc;
@@ -695,6 +864,72 @@ extern "C" int jinc_plan_row_bands(int target_h, int n_parts, int32_t* y_begin, 
     return JINC_OK;
 }
 
+extern "C" int jinc_filter_process_bands(jinc_filter* f, const jinc_frame* frame, int n_bands)
+{
+    if (int rc = check_frame(f, frame))
+        return rc;
+    if (n_bands < 1 || n_bands > 4096)
+        return jinc_fail(JINC_E_INVALID, "jinc_filter_process_bands: n_bands must be 1..4096");
+    const int nd = static_cast<int>(f->devs.size());
+    std::vector<int32_t> yb(n_bands), ye(n_bands);
+    if (int rc = jinc_plan_row_bands(f->p.target_h, n_bands, yb.data(), ye.data()))
+        return rc;
+
+    // Band i runs on GPU i % G through a slot of that GPU.  This caller never blocks on a slot while it holds one: when
+    // its GPU has none free it first completes its own oldest band, so concurrent callers cannot deadlock each other.
+    struct InFlight {
+        Slot* s;
+        int y0, y1;
+    };
+    std::vector<InFlight> fifo;
+    size_t head = 0;
+    int rc = JINC_OK;
+    auto finish_oldest = [&]() {
+        InFlight& b = fifo[head++];
+        if (rc == JINC_OK)
+            rc = finish_frame(f, b.s, b.y0, b.y1, false);
+        else
+            cudaStreamSynchronize(b.s->stream);
+        release_slot(f, b.s);
+    };
+    for (int i = 0; i < n_bands && rc == JINC_OK; ++i) {
+        if (ye[i] <= yb[i])
+            continue;
+        Slot* s = nullptr;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(f->mu);
+                s = find_free_slot(f, i % nd, true);
+                if (!s && head == fifo.size()) {
+                    f->cv.wait(lk); // holding nothing: waiting is safe
+                    continue;
+                }
+                if (s) {
+                    s->state = Slot::BUSY;
+                    s->ticket = f->next_ticket++;
+                }
+            }
+            if (s)
+                break;
+            finish_oldest();
+            if (rc != JINC_OK)
+                break;
+        }
+        if (!s)
+            break;
+        rc = enqueue_frame(f, s, frame, yb[i], ye[i], false);
+        if (rc != JINC_OK) {
+            cudaStreamSynchronize(s->stream);
+            release_slot(f, s);
+            break;
+        }
+        fifo.push_back(InFlight{s, yb[i], ye[i]});
+    }
+    while (head < fifo.size())
+        finish_oldest();
+    return rc;
+}
+
 extern "C" int jinc_filter_process_split(jinc_filter* f, const jinc_frame* frame)
 {
     if (int rc = check_frame(f, frame))
@@ -702,44 +937,5 @@ extern "C" int jinc_filter_process_split(jinc_filter* f, const jinc_frame* frame
     const int nd = static_cast<int>(f->devs.size());
     if (nd == 1)
         return jinc_filter_process(f, frame);
-    // one slot per GPU, bands cut on multiples of 16 luma rows (whole cell pairs for luma and subsampled chroma)
-    std::vector<Slot*> held(nd, nullptr);
-    {
-        std::unique_lock<std::mutex> lk(f->mu);
-        for (;;) {
-            bool ok = true;
-            for (int di = 0; di < nd && ok; ++di) {
-                held[di] = nullptr;
-                for (auto& s : f->slots)
-                    if (!s->busy && s->dev_index == di) {
-                        held[di] = s.get();
-                        break;
-                    }
-                ok = held[di] != nullptr;
-            }
-            if (ok)
-                break;
-            f->cv.wait(lk);
-        }
-        for (Slot* s : held)
-            s->busy = true;
-    }
-    std::vector<int32_t> yb(nd), ye(nd);
-    int rc = jinc_plan_row_bands(f->p.target_h, nd, yb.data(), ye.data());
-    std::vector<std::pair<int, int>> ranges(nd);
-    for (int di = 0; di < nd; ++di) {
-        ranges[di] = {yb[di], ye[di]};
-        if (ye[di] > yb[di] && rc == JINC_OK)
-            rc = enqueue_frame(f, held[di], frame, yb[di], ye[di], false);
-    }
-    for (int di = 0; di < nd; ++di) {
-        if (ranges[di].second > ranges[di].first) {
-            if (rc == JINC_OK)
-                rc = finish_frame(f, held[di], ranges[di].first, ranges[di].second, false);
-            else
-                cudaStreamSynchronize(held[di]->stream);
-        }
-        release_slot(f, held[di]);
-    }
-    return rc;
+    return jinc_filter_process_bands(f, frame, nd);
 }

@@ -1,0 +1,377 @@
+// jinc_hostmem.cpp -- registry of the caller's host frame buffers and the helper threads of the staging copies.
+// See jinc_hostmem.h.  Everything here is host-side bookkeeping around JincResize_GetFrame's frame buffers
+// (src/JincResize.cpp:603-630); no pixel is computed here.
+#include "jinc_hostmem.h"
+
+#include <unistd.h>
+
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <functional>
+#include <map>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+namespace jinc_hostmem {
+
+namespace {
+
+struct Entry {
+    enum State { SEEN, EXTERNAL, REGISTERED, REGISTERING, REFUSED };
+    uintptr_t lo = 0, hi = 0;         // the buffer as the caller describes it
+    uintptr_t reg_lo = 0, reg_hi = 0; // the page-aligned range registered here
+    State state = SEEN;
+    int sightings = 0;
+    int users = 0;
+    bool poisoned = false;
+    uint64_t tick = 0;
+};
+
+std::mutex g_mu;
+std::map<uintptr_t, Entry*> g_entries; // by lo
+size_t g_reg_bytes = 0;
+uint64_t g_tick = 0;
+long g_registrations = 0;
+
+constexpr size_t kMaxEntries = 4096;
+constexpr uintptr_t kGroupGap = 64 << 10; // planes closer than this belong to one allocation
+
+size_t budget_bytes()
+{
+    static const size_t b = [] {
+        const char* s = getenv("JINCRESIZE_B200_HOSTREG_MB");
+        const long mb = s ? atol(s) : 8192;
+        return static_cast<size_t>(mb < 0 ? 0 : mb) << 20;
+    }();
+    return b;
+}
+
+uintptr_t page_size()
+{
+    static const uintptr_t p = [] {
+        const long v = sysconf(_SC_PAGESIZE);
+        return static_cast<uintptr_t>(v > 0 ? v : 4096);
+    }();
+    return p;
+}
+
+bool is_pinned_host(uintptr_t p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, reinterpret_cast<const void*>(p)) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+}
+
+// g_mu held
+void unregister_locked(Entry* e)
+{
+    if (e->state == Entry::REGISTERED) {
+        if (cudaHostUnregister(reinterpret_cast<void*>(e->reg_lo)) != cudaSuccess)
+            cudaGetLastError();
+        g_reg_bytes -= e->reg_hi - e->reg_lo;
+        e->state = Entry::SEEN;
+        e->reg_lo = e->reg_hi = 0;
+    }
+}
+
+// g_mu held: least-recently-used idle registrations go until `need` more bytes fit the budget
+bool make_room_locked(size_t need)
+{
+    if (need > budget_bytes())
+        return false;
+    while (g_reg_bytes + need > budget_bytes()) {
+        Entry* victim = nullptr;
+        for (auto& kv : g_entries) {
+            Entry* e = kv.second;
+            if (e->state == Entry::REGISTERED && e->users == 0 && (!victim || e->tick < victim->tick))
+                victim = e;
+        }
+        if (!victim)
+            return false;
+        unregister_locked(victim);
+        victim->sightings = 0;
+    }
+    return true;
+}
+
+// g_mu held: forget buffers that never came back once the table grows
+void prune_locked()
+{
+    if (g_entries.size() < kMaxEntries)
+        return;
+    std::vector<std::pair<uint64_t, uintptr_t>> idle;
+    for (auto& kv : g_entries)
+        if (kv.second->users == 0 && (kv.second->state == Entry::SEEN || kv.second->state == Entry::REFUSED))
+            idle.emplace_back(kv.second->tick, kv.first);
+    std::sort(idle.begin(), idle.end());
+    for (size_t i = 0; i < idle.size() / 2; ++i) {
+        auto it = g_entries.find(idle[i].second);
+        delete it->second;
+        g_entries.erase(it);
+    }
+}
+
+// registers e's range; called WITHOUT g_mu (page-locking a large frame buffer takes milliseconds), e->state is REGISTERING
+bool do_register(Entry* e)
+{
+    const uintptr_t ps = page_size();
+    const uintptr_t lo = e->lo & ~(ps - 1), hi = (e->hi + ps - 1) & ~(ps - 1);
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (!make_room_locked(hi - lo))
+            return false;
+        g_reg_bytes += hi - lo; // reserved
+    }
+    cudaError_t err = cudaHostRegister(reinterpret_cast<void*>(lo), hi - lo, cudaHostRegisterPortable);
+    if (err == cudaErrorHostMemoryAlreadyRegistered) {
+        // a stale registration of ours overlaps (the host re-cut its memory): drop the idle ones and try once more
+        cudaGetLastError();
+        {
+            std::lock_guard<std::mutex> lk(g_mu);
+            for (auto& kv : g_entries) {
+                Entry* o = kv.second;
+                if (o != e && o->state == Entry::REGISTERED && o->users == 0 && o->reg_lo < hi && lo < o->reg_hi) {
+                    unregister_locked(o);
+                    o->sightings = 0;
+                }
+            }
+        }
+        err = cudaHostRegister(reinterpret_cast<void*>(lo), hi - lo, cudaHostRegisterPortable);
+    }
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (err != cudaSuccess) {
+        cudaGetLastError();
+        g_reg_bytes -= hi - lo;
+        return false;
+    }
+    e->reg_lo = lo;
+    e->reg_hi = hi;
+    ++g_registrations;
+    return true;
+}
+
+} // namespace
+
+bool acquire(const Range* ranges, int n, bool may_register, Pin* pin)
+{
+    pin->n = 0;
+    if (n < 1 || n > JINC_MAX_PLANES)
+        return false;
+    // planes of one frame buffer form one range
+    Range sorted[JINC_MAX_PLANES];
+    for (int i = 0; i < n; ++i) {
+        if (!ranges[i].lo || ranges[i].hi <= ranges[i].lo)
+            return false;
+        sorted[i] = ranges[i];
+    }
+    std::sort(sorted, sorted + n, [](const Range& a, const Range& b) { return a.lo < b.lo; });
+    uintptr_t glo[JINC_MAX_PLANES], ghi[JINC_MAX_PLANES];
+    int ng = 0;
+    for (int i = 0; i < n; ++i) {
+        const uintptr_t lo = reinterpret_cast<uintptr_t>(sorted[i].lo), hi = reinterpret_cast<uintptr_t>(sorted[i].hi);
+        if (ng > 0 && lo <= ghi[ng - 1] + kGroupGap) {
+            ghi[ng - 1] = std::max(ghi[ng - 1], hi);
+        } else {
+            glo[ng] = lo;
+            ghi[ng] = hi;
+            ++ng;
+        }
+    }
+
+    Entry* got[JINC_MAX_PLANES];
+    std::unique_lock<std::mutex> lk(g_mu);
+    for (int g = 0; g < ng; ++g) {
+        Entry* e = nullptr;
+        auto it = g_entries.find(glo[g]);
+        if (it != g_entries.end()) {
+            e = it->second;
+            if (e->hi != ghi[g]) { // another buffer now lives at this address
+                if (e->users > 0 || e->state == Entry::REGISTERING)
+                    return false;
+                unregister_locked(e);
+                delete e;
+                g_entries.erase(it);
+                e = nullptr;
+            }
+        }
+        if (!e) {
+            prune_locked();
+            e = new Entry();
+            e->lo = glo[g];
+            e->hi = ghi[g];
+            e->state = (is_pinned_host(glo[g]) && is_pinned_host(ghi[g] - 1)) ? Entry::EXTERNAL : Entry::SEEN;
+            g_entries.emplace(glo[g], e);
+        }
+        ++e->sightings;
+        e->tick = ++g_tick;
+        if (e->state == Entry::SEEN && may_register && e->sightings >= 2 && !e->poisoned) {
+            e->state = Entry::REGISTERING;
+            lk.unlock();
+            const bool ok = do_register(e);
+            lk.lock();
+            e->state = ok ? Entry::REGISTERED : Entry::REFUSED;
+        }
+        if (e->state != Entry::EXTERNAL && e->state != Entry::REGISTERED)
+            return false;
+        got[g] = e;
+    }
+    for (int g = 0; g < ng; ++g) {
+        ++got[g]->users;
+        pin->entry[g] = got[g];
+    }
+    pin->n = ng;
+    return true;
+}
+
+void release(Pin* pin)
+{
+    if (pin->n == 0)
+        return;
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (int g = 0; g < pin->n; ++g) {
+        Entry* e = static_cast<Entry*>(pin->entry[g]);
+        if (--e->users == 0 && e->poisoned) {
+            unregister_locked(e);
+            e->state = Entry::REFUSED;
+        }
+    }
+    pin->n = 0;
+}
+
+bool registered_here(const Pin* pin)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (int g = 0; g < pin->n; ++g)
+        if (static_cast<const Entry*>(pin->entry[g])->state == Entry::REGISTERED)
+            return true;
+    return false;
+}
+
+void distrust(Pin* pin)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (int g = 0; g < pin->n; ++g) {
+        Entry* e = static_cast<Entry*>(pin->entry[g]);
+        if (e->state == Entry::REGISTERED)
+            e->poisoned = true;
+    }
+}
+
+size_t registered_bytes()
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    return g_reg_bytes;
+}
+
+long registrations()
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    return g_registrations;
+}
+
+// ------------------------------------------------------------------------------------------ staging copies
+
+namespace {
+
+class CopyPool {
+public:
+    static CopyPool& get()
+    {
+        static CopyPool* p = new CopyPool(); // never destroyed: helper threads may outlive static destructors
+        return *p;
+    }
+    int helpers() const { return static_cast<int>(threads_.size()); }
+    void run(std::function<void()> fn)
+    {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            q_.push_back(std::move(fn));
+        }
+        cv_.notify_one();
+    }
+
+private:
+    CopyPool()
+    {
+        const char* s = getenv("JINCRESIZE_B200_COPY_THREADS");
+        const int hw = static_cast<int>(std::thread::hardware_concurrency());
+        int n = s ? atoi(s) : std::min(3, std::max(0, hw / 4 - 1));
+        n = std::max(0, std::min(n, 16));
+        for (int i = 0; i < n; ++i) {
+            threads_.emplace_back([this] {
+                for (;;) {
+                    std::function<void()> fn;
+                    {
+                        std::unique_lock<std::mutex> lk(mu_);
+                        cv_.wait(lk, [this] { return !q_.empty(); });
+                        fn = std::move(q_.front());
+                        q_.pop_front();
+                    }
+                    fn();
+                }
+            });
+            threads_.back().detach();
+        }
+    }
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::deque<std::function<void()>> q_;
+    std::vector<std::thread> threads_;
+};
+
+void copy_rows_serial(unsigned char* dst, size_t dst_pitch, const unsigned char* src, ptrdiff_t src_pitch, size_t row_bytes, int rows)
+{
+    if (static_cast<ptrdiff_t>(dst_pitch) == src_pitch && dst_pitch == row_bytes) {
+        memcpy(dst, src, row_bytes * static_cast<size_t>(rows));
+        return;
+    }
+    for (int y = 0; y < rows; ++y)
+        memcpy(dst + static_cast<size_t>(y) * dst_pitch, src + static_cast<ptrdiff_t>(y) * src_pitch, row_bytes);
+}
+
+} // namespace
+
+void copy_rows(unsigned char* dst, size_t dst_pitch, const unsigned char* src, ptrdiff_t src_pitch, size_t row_bytes, int rows)
+{
+    const size_t total = row_bytes * static_cast<size_t>(rows);
+    constexpr size_t kPart = static_cast<size_t>(1) << 20;
+    CopyPool& pool = CopyPool::get();
+    const int parts = static_cast<int>(std::min<size_t>(pool.helpers() + 1, total / kPart));
+    if (parts < 2 || rows < parts) {
+        copy_rows_serial(dst, dst_pitch, src, src_pitch, row_bytes, rows);
+        return;
+    }
+    struct Latch {
+        std::mutex mu;
+        std::condition_variable cv;
+        int left;
+    } latch;
+    latch.left = parts - 1;
+    const int per = (rows + parts - 1) / parts;
+    for (int p = 1; p < parts; ++p) {
+        const int r0 = p * per, r1 = std::min(rows, r0 + per);
+        pool.run([=, &latch] {
+            if (r1 > r0)
+                copy_rows_serial(dst + static_cast<size_t>(r0) * dst_pitch, dst_pitch, src + static_cast<ptrdiff_t>(r0) * src_pitch, src_pitch,
+                                 row_bytes, r1 - r0);
+            std::lock_guard<std::mutex> lk(latch.mu);
+            if (--latch.left == 0)
+                latch.cv.notify_one();
+        });
+    }
+    copy_rows_serial(dst, dst_pitch, src, src_pitch, row_bytes, std::min(rows, per));
+    std::unique_lock<std::mutex> lk(latch.mu);
+    latch.cv.wait(lk, [&] { return latch.left == 0; });
+}
+
+} // namespace jinc_hostmem

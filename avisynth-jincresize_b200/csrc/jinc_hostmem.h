@@ -1,0 +1,48 @@
+// jinc_hostmem.h -- what the frame pipeline knows about the caller's host buffers (not part of the public ABI).
+//
+// The reference's GetFrame works in place on AviSynth's frame buffers (src/JincResize.cpp:603-630).  A GPU path has to
+// move them over PCIe, and the DMA engines only run at full rate -- and only overlap with the caller -- from page-locked
+// memory.  A host recycles its frame buffers (AviSynth's frame cache, the mini-host's pool), so the pipeline remembers
+// every buffer it has seen: buffers the caller allocated page-locked are used directly; pageable buffers are staged
+// through the slot's pinned mirror the first time and registered (cudaHostRegister) when they come back, after which
+// they are used directly too.  Registered memory is capped and evicted least-recently-used.
+#ifndef JINC_HOSTMEM_H
+#define JINC_HOSTMEM_H
+
+#include <cstddef>
+#include <cstdint>
+
+#include "jinc_b200.h"
+
+namespace jinc_hostmem {
+
+struct Range {
+    const unsigned char* lo;
+    const unsigned char* hi; // one past the last byte
+};
+
+// Ranges held against eviction between acquire() and release().
+struct Pin {
+    int n = 0;
+    void* entry[JINC_MAX_PLANES] = {};
+};
+
+// True when every range is page-locked (allocated so by the caller, or registered here -- now, if `may_register` and the
+// buffer has been seen before); the ranges are then pinned against eviction until release().  False: stage the frame.
+bool acquire(const Range* ranges, int n, bool may_register, Pin* pin);
+void release(Pin* pin);
+// true when any of the pinned ranges is page-locked by a registration made here (as opposed to by the caller)
+bool registered_here(const Pin* pin);
+// A transfer through ranges this module registered did not arrive (the host freed and re-mapped the memory behind the
+// registration): forget those registrations and never register the addresses again.  Call before release().
+void distrust(Pin* pin);
+// statistics: bytes currently registered here, number of cudaHostRegister calls so far
+size_t registered_bytes();
+long registrations();
+
+// rows of one plane, host to host; large planes are split over a small pool of helper threads
+void copy_rows(unsigned char* dst, size_t dst_pitch, const unsigned char* src, ptrdiff_t src_pitch, size_t row_bytes, int rows);
+
+} // namespace jinc_hostmem
+
+#endif

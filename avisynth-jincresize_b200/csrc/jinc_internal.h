@@ -119,6 +119,7 @@ struct jinc_table {
     PeriodicPlan periodic;
     int fast_path = JINC_PATH_GENERAL;
     int ix0 = 0, ix1 = 0, iy0 = 0, iy1 = 0; // interior rectangle run by the fast path (empty if none)
+    float build_ms = 0.f;                   // host wall time of jinc_table_create
 };
 
 // jinc_lut.cpp

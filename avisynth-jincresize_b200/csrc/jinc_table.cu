@@ -14,6 +14,7 @@
 // Bit-exactness rules: positions are a sequential float accumulation (one thread per axis),
 // every float/double operation uses an explicit round-to-nearest intrinsic so nvcc cannot contract a*b+c into
 // an FMA, and the block normaliser is a sequential float sum in row-major order.
+#include <chrono>
 #include <climits>
 #include <cmath>
 #include <cstring>
@@ -451,6 +452,10 @@ int jinc_table_build_device(jinc_table* t, const double* lut)
     int32_t* d_nrank = nullptr;
     if (int rc = dev_alloc(&d_nrank, 2))
         return rc;
+    struct FreeOnExit {
+        int32_t*& p;
+        ~FreeOnExit() { cudaFree(p); }
+    } free_nrank{d_nrank};
     const int n_of[2] = {s.dst_w, s.dst_h}, src_of[2] = {s.src_w, s.src_h}, quant_of[2] = {s.quant_x, s.quant_y};
     AxisKernelArgs args[2];
     for (int k = 0; k < 2; ++k) {
@@ -466,10 +471,8 @@ int jinc_table_build_device(jinc_table* t, const double* lut)
         rc = rc ? rc : dev_alloc(&a.rep, 256);
         rc = rc ? rc : dev_alloc(&a.rank_of, 256);
         rc = rc ? rc : dev_alloc(&a.rep_d2, (size_t)quant_of[k] * s.fs);
-        if (rc) {
-            cudaFree(d_nrank);
+        if (rc)
             return rc;
-        }
         args[k] = AxisKernelArgs{a.pos, a.start, a.qint, a.phase, a.rank, a.border, a.rep, a.rank_of, a.rep_d2,
                                  d_nrank + k, a.n, src_of[k], quant_of[k], s.fs, s.pos0[k], s.pos_step[k], s.support,
                                  s.filt_step[k]};
@@ -495,7 +498,6 @@ int jinc_table_build_device(jinc_table* t, const double* lut)
         JINC_CUDA(cudaMemcpyAsync(t->h_pos[k].data(), t->ax[k].pos, n * sizeof(float), cudaMemcpyDeviceToHost, st));
     }
     JINC_CUDA(cudaStreamSynchronize(st));
-    cudaFree(d_nrank);
     t->ax[0].n_rank = h_nrank[0];
     t->ax[1].n_rank = h_nrank[1];
 
@@ -655,6 +657,7 @@ extern "C" int jinc_table_create(jinc_ctx* ctx, const jinc_table_params* p, jinc
     if (!(p->radius > 0.0) || !(p->crop_w > 0.0) || !(p->crop_h > 0.0))
         return jinc_fail(JINC_E_INVALID, "jinc_table_create: radius and crop size must be positive");
 
+    const auto t_begin = std::chrono::steady_clock::now();
     auto* t = new jinc_table();
     t->ctx = ctx;
     t->params = *p;
@@ -673,6 +676,7 @@ extern "C" int jinc_table_create(jinc_ctx* ctx, const jinc_table_params* p, jinc
         jinc_table_destroy(t);
         return rc;
     }
+    t->build_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
     *out = t;
     return JINC_OK;
 }
@@ -721,6 +725,7 @@ extern "C" int jinc_table_get_info(const jinc_table* t, jinc_table_info* info)
     info->interior_y0 = t->iy0;
     info->interior_y1 = t->iy1;
     info->filter_support = t->sc.support;
+    info->build_ms = t->build_ms;
     return JINC_OK;
 }
 

@@ -15,7 +15,7 @@ from . import paths
 MAX_PLANES = 4
 MAX_DEVICES = 16
 CPLACE = {"mpeg2": 0, "mpeg1": 1, "topleft": 2}
-PATH_NAMES = {0: "general", 1: "up2x", 2: "down_int"}
+PATH_NAMES = {0: "general", 1: "up2x", 2: "down_int", 3: "periodic", 4: "piecewise"}
 
 
 class JincError(RuntimeError):
@@ -32,7 +32,7 @@ class TableInfo(C.Structure):
     _fields_ = [("filter_size", C.c_int32), ("n_phase_x", C.c_int32), ("n_phase_y", C.c_int32),
                 ("n_border_cols", C.c_int32), ("n_border_rows", C.c_int32), ("fast_path", C.c_int32),
                 ("interior_x0", C.c_int32), ("interior_x1", C.c_int32), ("interior_y0", C.c_int32),
-                ("interior_y1", C.c_int32), ("filter_support", C.c_float)]
+                ("interior_y1", C.c_int32), ("filter_support", C.c_float), ("build_ms", C.c_float)]
 
 
 class FilterParams(C.Structure):
@@ -41,7 +41,11 @@ class FilterParams(C.Structure):
                 ("quant_x", C.c_int32), ("quant_y", C.c_int32), ("tap", C.c_int32), ("blur", C.c_double),
                 ("cplace", C.c_int32), ("n_planes", C.c_int32), ("sub_w", C.c_int32), ("sub_h", C.c_int32),
                 ("sample_bytes", C.c_int32), ("bits", C.c_int32), ("n_devices", C.c_int32),
-                ("devices", C.c_int32 * MAX_DEVICES), ("slots_per_device", C.c_int32)]
+                ("devices", C.c_int32 * MAX_DEVICES), ("slots_per_device", C.c_int32), ("flags", C.c_int32)]
+
+FLAG_NO_HOST_REGISTER = 1
+FLAG_DST_PADDING_WRITABLE = 2
+E_BUSY = -5
 
 
 class Frame(C.Structure):
@@ -58,7 +62,8 @@ EXPORTS = [
     "jinc_filter_destroy", "jinc_filter_table", "jinc_filter_num_tables", "jinc_filter_num_devices",
     "jinc_filter_process", "jinc_filter_submit", "jinc_filter_wait", "jinc_filter_process_split",
     "jinc_filter_kernel_launches", "jinc_filter_process_device", "jinc_filter_process_device_batch",
-    "jinc_plan_frame_owner", "jinc_plan_row_bands",
+    "jinc_plan_frame_owner", "jinc_plan_row_bands", "jinc_filter_num_slots", "jinc_filter_try_submit",
+    "jinc_filter_process_bands", "jinc_host_buffer_stats", "jinc_filter_live_count",
 ]
 
 _lib = None
@@ -105,6 +110,13 @@ def lib():
         L.jinc_filter_process_device_batch.restype = ci
         L.jinc_filter_process_device_batch.argtypes = [vp, ci, C.POINTER(Frame), ci, ci, ci, vp]
         L.jinc_filter_kernel_launches.restype, L.jinc_filter_kernel_launches.argtypes = C.c_int64, [vp]
+        L.jinc_filter_num_slots.restype, L.jinc_filter_num_slots.argtypes = ci, [vp]
+        L.jinc_filter_try_submit.restype = ci
+        L.jinc_filter_try_submit.argtypes = [vp, C.POINTER(Frame), C.POINTER(C.c_int64)]
+        L.jinc_filter_process_bands.restype, L.jinc_filter_process_bands.argtypes = ci, [vp, C.POINTER(Frame), ci]
+        L.jinc_host_buffer_stats.restype = None
+        L.jinc_host_buffer_stats.argtypes = [C.POINTER(C.c_int64)] * 5
+        L.jinc_filter_live_count.restype = ci
         L.jinc_plan_frame_owner.restype, L.jinc_plan_frame_owner.argtypes = ci, [C.c_int64, ci]
         L.jinc_plan_row_bands.restype = ci
         L.jinc_plan_row_bands.argtypes = [ci, ci, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
@@ -119,6 +131,18 @@ def _check(rc: int):
 
 def device_count() -> int:
     return lib().jinc_device_count()
+
+
+def live_filters() -> int:
+    return lib().jinc_filter_live_count()
+
+
+def host_buffer_stats() -> dict:
+    """Process-wide bookkeeping of the frame pipeline's view of caller buffers (jinc_host_buffer_stats)."""
+    v = [C.c_int64() for _ in range(5)]
+    lib().jinc_host_buffer_stats(*[C.byref(x) for x in v])
+    return dict(zip(("registered_bytes", "registrations", "direct_src_frames", "direct_dst_frames", "staged_frames"),
+                    (x.value for x in v)))
 
 
 def frame_owner(frame: int, n_parts: int) -> int:
@@ -240,7 +264,7 @@ class Filter:
 
     def __init__(self, *, src_w, src_h, target_w, target_h, n_planes, sample_bytes, bits, sub_w=0, sub_h=0,
                  src_left=0.0, src_top=0.0, src_width=None, src_height=None, quant_x=256, quant_y=256, tap=3,
-                 blur=0.0, cplace="mpeg2", devices=None, slots_per_device=0):
+                 blur=0.0, cplace="mpeg2", devices=None, slots_per_device=0, flags=0):
         f32 = lambda v: float(np.float32(v))  # script floats are 32-bit
         p = FilterParams()
         p.src_w, p.src_h, p.target_w, p.target_h = src_w, src_h, target_w, target_h
@@ -252,9 +276,10 @@ class Filter:
         p.n_planes, p.sub_w, p.sub_h, p.sample_bytes, p.bits = n_planes, sub_w, sub_h, sample_bytes, bits
         devices = list(devices) if devices is not None else []
         p.n_devices = len(devices)
-        for i, d in enumerate(devices):
+        for i, d in enumerate(devices[:MAX_DEVICES]):
             p.devices[i] = d
         p.slots_per_device = slots_per_device
+        p.flags = flags
         self.params = p
         h = C.c_void_p()
         _check(lib().jinc_filter_create(C.byref(p), C.byref(h)))
@@ -288,6 +313,10 @@ class Filter:
         return lib().jinc_filter_num_devices(self.handle)
 
     @property
+    def num_slots(self) -> int:
+        return lib().jinc_filter_num_slots(self.handle)
+
+    @property
     def kernel_launches(self) -> int:
         return lib().jinc_filter_kernel_launches(self.handle)
 
@@ -303,11 +332,16 @@ class Filter:
     def alloc_dst(self):
         return [np.zeros(dst, dtype=self.dtype) for _, dst in self.plane_shapes()]
 
-    def process(self, src_planes, dst_planes=None, split=False):
+    def process(self, src_planes, dst_planes=None, split=False, bands=0):
+        """One frame through jinc_filter_process; split=True: jinc_filter_process_split (one row band per GPU);
+        bands=n: jinc_filter_process_bands with n row bands."""
         dst_planes = dst_planes if dst_planes is not None else self.alloc_dst()
         fr = self._frame(src_planes, dst_planes)
-        fn = lib().jinc_filter_process_split if split else lib().jinc_filter_process
-        _check(fn(self.handle, C.byref(fr)))
+        if bands:
+            _check(lib().jinc_filter_process_bands(self.handle, C.byref(fr), bands))
+        else:
+            fn = lib().jinc_filter_process_split if split else lib().jinc_filter_process
+            _check(fn(self.handle, C.byref(fr)))
         return dst_planes
 
     def process_raw(self, frame: Frame):
@@ -332,6 +366,16 @@ class Filter:
     def submit_raw(self, frame: Frame) -> int:
         t = C.c_int64()
         _check(lib().jinc_filter_submit(self.handle, C.byref(frame), C.byref(t)))
+        return t.value
+
+    def try_submit(self, src_planes, dst_planes):
+        """Ticket, or None when every in-flight slot is taken (JINC_E_BUSY)."""
+        fr = self._frame(src_planes, dst_planes)
+        t = C.c_int64()
+        rc = lib().jinc_filter_try_submit(self.handle, C.byref(fr), C.byref(t))
+        if rc == E_BUSY:
+            return None
+        _check(rc)
         return t.value
 
     def wait(self, ticket: int):

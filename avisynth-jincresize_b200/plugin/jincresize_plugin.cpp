@@ -9,19 +9,26 @@
 //   * alias functions forward only the optional arguments that were given, by name, plus tap (:1007-1040);
 //   * cplace defaults from frame 0's _ChromaLocation (:725-742);
 //   * output frames inherit the source frame's properties; _ChromaLocation is written for 4:2:0/4:2:2/4:1:1 (:613-625).
+//   * opt's validation, including the CPU-feature errors of opt=1/2/3 (:747-756), although opt selects nothing here;
+//   * the output _ChromaLocation is what the reference writes: always 2 for 4:2:0 / 4:2:2 / 4:1:1 clips, because the
+//     reference never stores the parsed cplace in its instance (src/JincResize.h:41, src/JincResize.cpp:617-625, 715).
+//     JINCRESIZE_B200_CHROMALOC=actual writes the cplace actually used instead (what the reference's README documents).
 // Deliberate differences (DESIGN.md "Boundary"):
 //   * threads / opt / initial_capacity / initial_factor are accepted and validated but select nothing: there is one
-//     GPU path.  opt's CPU-feature errors (:751-756) cannot occur and are not produced;
+//     GPU path;
 //   * one instance serves all Prefetch threads (MT_NICE_FILTER): concurrent get_frame calls take different in-flight
 //     slots of the GPU pipeline, which is what overlaps copies and kernels.  The reference asks for
-//     MT_MULTI_INSTANCE (:649-652), i.e. one private table set per thread;
-//   * the output _ChromaLocation is the cplace actually used.  The reference intends the same (:617-625) but never
-//     stores the parsed cplace in the instance, so it always writes 2; set JINCRESIZE_B200_COMPAT_CHROMALOC=1 to
-//     reproduce that.
+//     MT_MULTI_INSTANCE (:649-652), i.e. one private table set per thread; JINCRESIZE_B200_MTMODE=2 reports that mode
+//     instead, and is cheap here because instances created with identical arguments share ONE GPU filter (tables,
+//     slots, streams) through a process-wide reference-counted cache.
+// Environment: JINCRESIZE_B200_DEVICES ("0,1,..." or "all"; default: device 0), JINCRESIZE_B200_SLOTS,
+// JINCRESIZE_B200_HOSTREG=0 (never page-lock the host's frame buffers), JINCRESIZE_B200_CHROMALOC, JINCRESIZE_B200_MTMODE.
 #include <algorithm>
 #include <cctype>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 
 #include "avisynth_c.h"
@@ -31,12 +38,53 @@ namespace {
 
 struct Instance {
     jinc_filter* filter = nullptr;
+    std::string key; // entry of the shared-filter cache
     int n_planes = 0;
     bool rgb = false;
     bool writes_chromaloc = false;
     int chromaloc = 0;
-    std::string error; // storage for fi->error
 };
+
+// Filters shared between instances created with identical parameters (every Prefetch thread of an MT_MULTI_INSTANCE
+// host, or the same call twice in a script): jinc_filter is thread-safe, so one set of tables and slots serves all.
+struct Shared {
+    jinc_filter* filter = nullptr;
+    int refs = 0;
+};
+std::mutex g_cache_mu;
+std::map<std::string, Shared> g_cache;
+
+jinc_filter* cache_acquire(const jinc_filter_params& p, std::string* key, std::string* err)
+{
+    key->assign(reinterpret_cast<const char*>(&p), sizeof(p));
+    std::lock_guard<std::mutex> lk(g_cache_mu); // construction is serialised: a second thread finds the first one's filter
+    Shared& e = g_cache[*key];
+    if (!e.filter) {
+        if (jinc_filter_create(&p, &e.filter) != JINC_OK) {
+            *err = jinc_last_error();
+            g_cache.erase(*key);
+            return nullptr;
+        }
+    }
+    ++e.refs;
+    return e.filter;
+}
+
+void cache_release(const std::string& key)
+{
+    jinc_filter* dead = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        auto it = g_cache.find(key);
+        if (it == g_cache.end())
+            return;
+        if (--it->second.refs == 0) {
+            dead = it->second.filter;
+            g_cache.erase(it);
+        }
+    }
+    jinc_filter_destroy(dead);
+}
 
 // positions inside the JincResize argument array (src/JincResize.cpp:656-674)
 enum Arg {
@@ -65,8 +113,9 @@ AVS_VideoFrame* AVSC_CC get_frame(AVS_FilterInfo* fi, int n)
         fr.dst_pitch[i] = avs_get_pitch_p(dst, ids[i]);
     }
     if (jinc_filter_process(inst->filter, &fr) != JINC_OK) {
-        inst->error = std::string("JincResize: ") + jinc_last_error();
-        fi->error = inst->error.c_str();
+        // the text lives in the environment's string heap: concurrent failing callers never share storage
+        const std::string msg = std::string("JincResize: ") + jinc_last_error();
+        fi->error = avs_save_string(fi->env, msg.c_str(), -1);
         avs_release_video_frame(src);
         avs_release_video_frame(dst);
         return nullptr;
@@ -81,7 +130,7 @@ void AVSC_CC free_filter(AVS_FilterInfo* fi)
 {
     auto* inst = static_cast<Instance*>(fi->user_data);
     if (inst) {
-        jinc_filter_destroy(inst->filter);
+        cache_release(inst->key);
         delete inst;
     }
     fi->user_data = nullptr;
@@ -89,7 +138,10 @@ void AVSC_CC free_filter(AVS_FilterInfo* fi)
 
 int AVSC_CC set_cache_hints(AVS_FilterInfo*, int cachehints, int)
 {
-    return cachehints == AVS_CACHE_GET_MTMODE ? AVS_MT_NICE_FILTER : 0;
+    if (cachehints != AVS_CACHE_GET_MTMODE)
+        return 0;
+    const char* m = getenv("JINCRESIZE_B200_MTMODE");
+    return (m && *m == '2') ? AVS_MT_MULTI_INSTANCE : AVS_MT_NICE_FILTER;
 }
 
 AVS_Value fail(AVS_Clip* clip, const char* msg)
@@ -160,8 +212,15 @@ AVS_Value AVSC_CC create_jincresize(AVS_ScriptEnvironment* env, AVS_Value args, 
         return fail(clip, "JincResize: topleft must be used only for 4:2:0 chroma subsampling.");
 
     const int opt = given(A_OPT) ? avs_as_int(arg(A_OPT)) : -1;
+    const int cpu_flags = avs_get_cpu_flags(env);
     if (opt > 3)
         return fail(clip, "JincResize: opt higher than 3 is not allowed.");
+    if (opt == 3 && !(cpu_flags & AVS_CPUF_AVX512F))
+        return fail(clip, "JincResize: opt=3 requires AVX-512F.");
+    if (opt == 2 && !(cpu_flags & AVS_CPUF_AVX2))
+        return fail(clip, "JincResize: opt=2 requires AVX2.");
+    if (opt == 1 && !(cpu_flags & AVS_CPUF_SSE4_1))
+        return fail(clip, "JincResize: opt=1 requires SSE4.1.");
     const int threads = given(A_THREADS) ? avs_as_int(arg(A_THREADS)) : 0;
     if (threads < 0 || threads > 1)
         return fail(clip, "JincResize: threads must be either 0 or 1.");
@@ -205,8 +264,12 @@ AVS_Value AVSC_CC create_jincresize(AVS_ScriptEnvironment* env, AVS_Value args, 
     const bool one_table = p.n_planes == 1 || avs_is_444(vi) || avs_is_rgb(vi); // :824-827
     p.sub_w = one_table ? 0 : avs_get_plane_width_subsampling(vi, AVS_PLANAR_U);
     p.sub_h = one_table ? 0 : avs_get_plane_height_subsampling(vi, AVS_PLANAR_U);
-    // GPUs: all visible ones unless JINCRESIZE_B200_DEVICES="0,1,..." narrows the set
-    if (const char* devs = getenv("JINCRESIZE_B200_DEVICES")) {
+    // GPUs: device 0 unless JINCRESIZE_B200_DEVICES names others ("0,1,..." or "all"): every GPU of a filter gets its own
+    // tables, streams and pinned frame slots, which a script with several JincResize calls should not pay eightfold
+    const char* devs = getenv("JINCRESIZE_B200_DEVICES");
+    if (!devs || !*devs) {
+        p.devices[p.n_devices++] = 0;
+    } else if (strcmp(devs, "all") != 0) {
         const char* s = devs;
         while (*s && p.n_devices < JINC_MAX_DEVICES) {
             char* end = nullptr;
@@ -219,12 +282,17 @@ AVS_Value AVSC_CC create_jincresize(AVS_ScriptEnvironment* env, AVS_Value args, 
     }
     if (const char* slots = getenv("JINCRESIZE_B200_SLOTS"))
         p.slots_per_device = atoi(slots);
+    // AviSynth+ frame buffers: the padding inside a plane's pitch belongs to the frame; recycled buffers may be page-locked
+    p.flags = JINC_FILTER_DST_PADDING_WRITABLE;
+    if (const char* hr = getenv("JINCRESIZE_B200_HOSTREG"))
+        if (*hr == '0')
+            p.flags |= JINC_FILTER_NO_HOST_REGISTER;
 
     const bool subsampled_family = avs_is_420(vi) || avs_is_422(vi) || avs_is_yv411(vi);
 
-    jinc_filter* filter = nullptr;
-    if (jinc_filter_create(&p, &filter) != JINC_OK) {
-        std::string msg = jinc_last_error();
+    std::string key, msg;
+    jinc_filter* filter = cache_acquire(p, &key, &msg);
+    if (!filter) {
         if (msg.rfind("JincResize:", 0) != 0)
             msg = "JincResize: " + msg;
         return fail(clip, avs_save_string(env, msg.c_str(), -1));
@@ -232,11 +300,15 @@ AVS_Value AVSC_CC create_jincresize(AVS_ScriptEnvironment* env, AVS_Value args, 
 
     auto* inst = new Instance();
     inst->filter = filter;
+    inst->key = key;
     inst->n_planes = p.n_planes;
     inst->rgb = avs_is_rgb(vi) != 0;
     inst->writes_chromaloc = subsampled_family;
-    const char* compat = getenv("JINCRESIZE_B200_COMPAT_CHROMALOC");
-    inst->chromaloc = (compat && *compat == '1') ? 2 : p.cplace;
+    // the reference always writes 2 (see the header comment); "actual" writes the cplace that was used
+    const char* cl = getenv("JINCRESIZE_B200_CHROMALOC");
+    const char* old = getenv("JINCRESIZE_B200_COMPAT_CHROMALOC"); // round-1 name of the switch: 0 = actual
+    const bool actual = (cl && strcmp(cl, "actual") == 0) || (!cl && old && *old == '0');
+    inst->chromaloc = actual ? p.cplace : 2;
 
     vi->width = target_w;
     vi->height = target_h;

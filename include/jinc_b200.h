@@ -23,7 +23,7 @@ extern "C" {
 
 #define JINC_API __attribute__((visibility("default")))
 
-#define JINC_ABI_VERSION 1
+#define JINC_ABI_VERSION 2
 #define JINC_LUT_SAMPLES 1024 /* src/JincResize.cpp:795 `samples` */
 #define JINC_MAX_PLANES 4
 #define JINC_MAX_DEVICES 16
@@ -33,7 +33,8 @@ enum {
     JINC_E_INVALID = -1, /* bad argument */
     JINC_E_CUDA = -2,    /* CUDA runtime/driver error, or no device */
     JINC_E_NOMEM = -3,
-    JINC_E_UNSUPPORTED = -4
+    JINC_E_UNSUPPORTED = -4,
+    JINC_E_BUSY = -5     /* jinc_filter_try_submit: every in-flight slot is taken */
 };
 
 /* chroma sample location (src/JincResize.cpp:715-745; README "cplace") */
@@ -91,6 +92,8 @@ typedef struct jinc_table_info {
     int32_t fast_path;     /* JINC_PATH_* chosen for the interior */
     int32_t interior_x0, interior_x1, interior_y0, interior_y1; /* output rectangle run by the fast path */
     float filter_support;  /* src/JincResize.cpp:355 */
+    float build_ms;        /* host wall time of jinc_table_create: LUT + device kernels + plans (the reference's
+                              generate_coeff_table_c call, src/JincResize.cpp:829,864) */
 } jinc_table_info;
 
 JINC_API int jinc_table_create(jinc_ctx* ctx, const jinc_table_params* p, jinc_table** out);
@@ -146,7 +149,22 @@ typedef struct jinc_filter_params {
     int32_t n_devices;          /* 0 => all visible devices */
     int32_t devices[JINC_MAX_DEVICES];
     int32_t slots_per_device;   /* frames in flight per GPU (0 => 3..8, by frame size) */
+    int32_t flags;              /* JINC_FILTER_* */
 } jinc_filter_params;
+
+/* jinc_filter_params.flags */
+enum {
+    /* Never page-lock the caller's frame buffers.  By default a pageable buffer that comes back (hosts recycle their
+     * frame buffers) is registered with cudaHostRegister and from then on moved by DMA directly, without the staging
+     * copy.  A host that FREES a buffer while it is registered leaves a stale registration behind; arrival of every
+     * directly written destination frame is verified and the registration dropped on a miss, but a host that wants no
+     * part of this sets the flag (the plugin: JINCRESIZE_B200_HOSTREG=0). */
+    JINC_FILTER_NO_HOST_REGISTER = 1,
+    /* The padding bytes inside the destination planes' pitch belong to the frame (true for AviSynth+ frame buffers):
+     * a destination frame whose planes are packed like the pipeline's own may then move with ONE device-to-host
+     * transfer that also covers the padding. */
+    JINC_FILTER_DST_PADDING_WRITABLE = 2
+};
 
 typedef struct jinc_frame {
     const void* src[JINC_MAX_PLANES]; /* host pointers (pageable or pinned) */
@@ -157,16 +175,24 @@ typedef struct jinc_frame {
 
 JINC_API int jinc_filter_create(const jinc_filter_params* p, jinc_filter** out);
 JINC_API void jinc_filter_destroy(jinc_filter* f);
+/* filter objects alive in this process (leak checks; the plugin shares one filter between identical instances) */
+JINC_API int jinc_filter_live_count(void);
 /* table k (0 = luma/all planes, 1 = subsampled chroma) on the filter's first device; NULL if absent */
 JINC_API const jinc_table* jinc_filter_table(const jinc_filter* f, int k);
 JINC_API int jinc_filter_num_tables(const jinc_filter* f);
 JINC_API int jinc_filter_num_devices(const jinc_filter* f);
+/* in-flight slots over all GPUs: how many jinc_filter_submit calls can be outstanding before one blocks */
+JINC_API int jinc_filter_num_slots(const jinc_filter* f);
 /* Synchronous: stage -> H2D -> kernels -> D2H -> dst.  Thread-safe: concurrent callers take different
  * in-flight slots (round-robin over the filter's GPUs), which is how frames overlap. */
 JINC_API int jinc_filter_process(jinc_filter* f, const jinc_frame* frame);
 /* Asynchronous pair: submit returns a ticket at once (blocking only when every slot is busy); wait blocks
  * until that frame's dst planes are complete.  src/dst memory must stay valid until wait returns. */
 JINC_API int jinc_filter_submit(jinc_filter* f, const jinc_frame* frame, int64_t* ticket);
+/* as jinc_filter_submit, but returns JINC_E_BUSY instead of blocking when every slot is taken (a single-threaded
+ * producer that submits more than jinc_filter_num_slots() frames before waiting would otherwise block itself) */
+JINC_API int jinc_filter_try_submit(jinc_filter* f, const jinc_frame* frame, int64_t* ticket);
+/* each ticket is waited on exactly once; a second wait on it fails with JINC_E_INVALID */
 JINC_API int jinc_filter_wait(jinc_filter* f, int64_t ticket);
 /* The partition rules, host-only (usable without a GPU; multi-process drivers use the same rules across ranks):
  *   frames  -- frame n of a clip belongs to part n % n_parts (what jinc_filter_submit's round-robin does);
@@ -178,8 +204,13 @@ JINC_API int jinc_plan_frame_owner(int64_t frame, int n_parts);
 JINC_API int jinc_plan_row_bands(int target_h, int n_parts, int32_t* y_begin, int32_t* y_end);
 
 /* Row-band split of ONE frame across all of the filter's GPUs (each GPU gets a band of output rows plus
- * the source rows its windows reach; no GPU<->GPU traffic). */
+ * the source rows its windows reach; no GPU<->GPU traffic).  = jinc_filter_process_bands(f, frame, number of GPUs);
+ * with one GPU it is jinc_filter_process. */
 JINC_API int jinc_filter_process_split(jinc_filter* f, const jinc_frame* frame);
+/* The same with an explicit band count: band i of jinc_plan_row_bands(target_h, n_bands) runs on GPU i % G through
+ * its own in-flight slot (own streams and buffers), so with n_bands > G -- or on ONE GPU -- the bands of a frame also
+ * overlap their transfers with each other's kernels.  The result is byte-identical to jinc_filter_process. */
+JINC_API int jinc_filter_process_bands(jinc_filter* f, const jinc_frame* frame, int n_bands);
 /* Device-resident frame: the kernels of jinc_filter_process without staging or PCIe copies.  `frame` holds DEVICE
  * pointers on the filter's GPU `device_index` (destination planes 16-byte aligned, pitch multiple of 16).
  * table_mask selects which tables run (bit 0: luma/shared table, bit 1: subsampled-chroma table); parts selects the
@@ -189,11 +220,18 @@ enum { JINC_PART_INTERIOR = 1, JINC_PART_BORDER = 2, JINC_PART_ALL = 3 };
 JINC_API int jinc_filter_process_device(jinc_filter* f, int device_index, const jinc_frame* frame, int table_mask,
                                         int parts, void* stream);
 /* Same for a BATCH of device-resident frames: one launch per table covers every frame of the batch (grid.y = frame).
- * This is the throughput path for callers that keep many frames on the GPU (bench.py's kernel-only leg). */
+ * This is the throughput path for callers that keep many frames on the GPU (bench.py's kernel-only leg).  Calls may
+ * use different streams: the small device array of plane pointers a launch reads is not reused before that launch
+ * has finished. */
 JINC_API int jinc_filter_process_device_batch(jinc_filter* f, int device_index, const jinc_frame* frames, int n_frames,
                                               int table_mask, int parts, void* stream);
 /* kernels launched so far by this filter (all devices) */
 JINC_API int64_t jinc_filter_kernel_launches(const jinc_filter* f);
+/* host-buffer bookkeeping of the frame pipeline (process-wide): bytes of caller memory currently page-locked by
+ * cudaHostRegister, number of registrations made, frames that moved without a staging copy on the source / on the
+ * destination side, frames staged.  Any pointer may be NULL. */
+JINC_API void jinc_host_buffer_stats(int64_t* registered_bytes, int64_t* registrations, int64_t* direct_src_frames,
+                                     int64_t* direct_dst_frames, int64_t* staged_frames);
 
 #ifdef __cplusplus
 }

@@ -210,8 +210,9 @@ class Clip:
                 planes.append(raw[:, :rs].copy().view(self.fmt.dtype))
             props = {}
             v = C.c_int64()
-            if lib.mh_frame_prop_int(self.env.handle, f, b"_ChromaLocation", C.byref(v)):
-                props["_ChromaLocation"] = v.value
+            for key in ("_ChromaLocation", "_Matrix", "_Primaries", "_Transfer", "_ColorRange", "_FieldBased"):
+                if lib.mh_frame_prop_int(self.env.handle, f, key.encode(), C.byref(v)):
+                    props[key] = v.value
             return planes, props
         finally:
             lib.avs_release_video_frame(f)

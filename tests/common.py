@@ -105,6 +105,29 @@ SMALL_CASES = [
 ]
 
 
+# The five BASELINE.json configs at their full sizes (config 1 is small already): (name, format, src, dst, kwargs)
+FULL_CASES = [
+    ("config1", ah.YV12, 640, 360, 1280, 720, dict(tap=3)),
+    ("config2", ah.YUV420P8, 1920, 1080, 3840, 2160, dict(tap=3, cplace="MPEG2")),
+    ("config3", ah.YUV444P16, 1920, 1080, 3840, 2160, dict(tap=4, src_left=10.3, src_top=6.7, quant_x=256, quant_y=256)),
+    ("config4", ah.RGBPS, 3840, 2160, 7680, 4320, dict(tap=8)),
+    ("config5", ah.YUV420P10, 7680, 4320, 1920, 1080, dict(tap=6, blur=0.9)),
+]
+
+
+def oracle_tables(fmt: ah.Format, w, h, tw, th, **kw):
+    """The oracle's coefficient tables of a filter (one, or luma + chroma)."""
+    from oracle import cpu as oc
+
+    sw, sh = fmt.subsampling
+    pp = oc.plane_params(w, h, tw, th, src_left=kw.get("src_left", 0.0), src_top=kw.get("src_top", 0.0),
+                         src_width=kw.get("src_width"), src_height=kw.get("src_height"),
+                         quant_x=kw.get("quant_x", 256), quant_y=kw.get("quant_y", 256), tap=kw.get("tap", 3),
+                         sub_w=sw, sub_h=sh, cplace=kw.get("cplace", "mpeg2"))
+    lut = oc.make_lut(kw.get("tap", 3), kw.get("blur", 0.0))
+    return [oc.Table(p, lut) for p in pp]
+
+
 def oracle_frame(fmt: ah.Format, w, h, tw, th, planes, **kw):
     """Reference result via the CPU oracle (oracle/jinc_oracle.c): returns (out_planes, tables)."""
     from oracle import cpu as oc
@@ -132,4 +155,5 @@ def make_filter(fmt: ah.Format, w, h, tw, th, devices=(0,), **kw):
                        src_left=kw.get("src_left", 0.0), src_top=kw.get("src_top", 0.0), src_width=kw.get("src_width"),
                        src_height=kw.get("src_height"), quant_x=kw.get("quant_x", 256), quant_y=kw.get("quant_y", 256),
                        tap=kw.get("tap", 3), blur=kw.get("blur", 0.0), cplace=kw.get("cplace", "mpeg2"),
-                       devices=list(devices) if devices is not None else None)
+                       devices=list(devices) if devices is not None else None, flags=kw.get("flags", 0),
+                       slots_per_device=kw.get("slots_per_device", 0))

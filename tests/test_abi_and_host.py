@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol(capi):
     lib = capi.lib()
     for s in declared:
         assert hasattr(lib, s), s
-    assert lib.jinc_abi_version() == 1
+    assert lib.jinc_abi_version() == 2
 
 
 def test_no_oracle_on_the_product_path():
@@ -104,6 +104,32 @@ ERROR_CASES = [
     (dict(initial_factor=0.5), "JincResize: initial_factor must be eqaul to or greater than 1.0."),
     (dict(initial_capacity=0), "JincResize: initial_capacity must be greater than 0."),
 ]
+
+
+OPT_CASES = [
+    # (opt, CPU flags the host reports, expected error or None) -- src/JincResize.cpp:747-756
+    (3, 0x2000 | 0x400, "JincResize: opt=3 requires AVX-512F."),
+    (2, 0x400, "JincResize: opt=2 requires AVX2."),
+    (1, 0x20, "JincResize: opt=1 requires SSE4.1."),
+]
+
+
+@pytest.mark.parametrize("opt,flags,msg", OPT_CASES)
+def test_plugin_opt_cpu_feature_errors_match_reference(native_built, have_ref, opt, flags, msg):
+    """opt selects nothing on the GPU path, but a script that asks for a SIMD level the host CPU lacks gets the
+    reference's error, word for word (checked before any GPU work, so this runs without a GPU)."""
+    from minihost import avs_host as ah
+    from jinc_b200 import paths
+
+    libs = [paths.b200_plugin()] + ([oref.REF_PLUGIN] if have_ref else [])
+    for lib in libs:
+        env = ah.Env()
+        env.load_plugin(lib)
+        env.set_cpu_flags(flags)
+        src = env.source(ah.Format("y", 8), 64, 64, [[np.zeros((64, 64), np.uint8)]])
+        with pytest.raises(ah.AvsError) as e:
+            env.invoke("JincResize", src, 96, 96, opt=opt)
+        assert str(e.value) == msg, lib
 
 
 @pytest.mark.parametrize("kw,msg", ERROR_CASES)

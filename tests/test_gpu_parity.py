@@ -8,7 +8,7 @@ bit-identical -- phase blocks and on-the-fly border weights alike.
 import numpy as np
 import pytest
 
-from common import SMALL_CASES, assert_plane_close, make_filter, make_planes, oracle_frame
+from common import FULL_CASES, SMALL_CASES, assert_plane_close, make_filter, make_planes, oracle_frame, oracle_tables
 
 pytestmark = pytest.mark.gpu
 
@@ -123,19 +123,6 @@ def test_submit_wait_pipeline_keeps_frames_apart(capi):
     flt.close()
 
 
-def test_row_band_split_equals_whole_frame(capi):
-    """jinc_filter_process_split cuts one frame into row bands; with one GPU it must equal the whole-frame path,
-    and through the internal band launcher the union of bands must equal the frame."""
-    name, fmt, w, h, tw, th, kw = SMALL_CASES[3]
-    planes = make_planes(fmt, w, h)
-    flt = make_filter(fmt, w, h, tw, th, **kw)
-    whole = flt.process(planes)
-    split = flt.process(planes, split=True)
-    for a, b in zip(whole, split):
-        assert np.array_equal(a, b)
-    flt.close()
-
-
 def test_window_larger_than_plane_is_rejected(capi):
     from minihost import avs_host as ah
 
@@ -143,30 +130,46 @@ def test_window_larger_than_plane_is_rejected(capi):
         make_filter(ah.Format("y", 8), 8, 8, 4, 4, tap=8)
 
 
-def test_full_size_properties(capi):
-    """Size-independent checks at a BASELINE size (config 2, 1080p -> 2160p): constant in -> constant out
-    (weights sum to 1), linearity in the input, and agreement with the oracle on sampled row bands."""
-    from minihost import avs_host as ah
-
-    fmt, w, h, tw, th, kw = ah.YUV420P8, 1920, 1080, 3840, 2160, dict(tap=3, cplace="MPEG2")
+@pytest.mark.parametrize("case", FULL_CASES, ids=[c[0] for c in FULL_CASES])
+def test_full_size_properties(capi, case):
+    """Every BASELINE config at its full, benchmarked size: constant in -> constant out (weights sum to 1, border
+    classes and resident border weights included), and agreement with the oracle on row bands at the top, in the middle
+    (tile seams) and at the bottom of every plane -- whole rows, so the left and right border columns are covered --
+    plus a band cut out of the left and right border strips over the full height."""
+    name, fmt, w, h, tw, th, kw = case
+    is_float = fmt.bits == 32
     flt = make_filter(fmt, w, h, tw, th, **kw)
-    const = [np.full(s, v, np.uint8) for (s, _), v in zip(flt.plane_shapes(), (77, 128, 201))]
+    shapes = flt.plane_shapes()
+    consts = (0.25, -0.125, 0.4, 0.7) if is_float else tuple(int(v * fmt.peak) for v in (0.3, 0.5, 0.8, 1.0))
+    const = [np.full(s, v, fmt.dtype) for (s, _), v in zip(shapes, consts)]
     out = flt.process(const)
-    for o, v in zip(out, (77, 128, 201)):
-        assert o.min() == v and o.max() == v
+    for i, (o, v) in enumerate(zip(out, consts)):
+        if is_float:
+            assert np.abs(o - np.float32(v)).max() <= 1e-5, f"{name}: constant plane {i}"
+        else:
+            assert o.min() == v and o.max() == v, f"{name}: constant plane {i}: {o.min()}..{o.max()} != {v}"
     planes = make_planes(fmt, w, h)
     got = flt.process(planes)
-    _, tabs = oracle_frame(fmt, 64, 64, 128, 128, make_planes(fmt, 64, 64), **kw)  # warm the oracle lib
-    from oracle import cpu as oc
-
-    pp = oc.plane_params(w, h, tw, th, tap=3, sub_w=1, sub_h=1, cplace="mpeg2")
-    lut = oc.make_lut(3, 0.0)
-    for k, rows in ((0, [(0, 6), (1077, 1083), (2154, 2160)]), (1, [(0, 4), (538, 542), (1076, 1080)])):
-        t = oc.Table(pp[k], lut)
-        for pi in ([0] if k == 0 else [1, 2]):
-            for (y0, y1) in rows:
-                ref = t.resize(planes[pi], 255.0, rows=(y0, y1))
-                assert_plane_close(got[pi][y0:y1], ref[y0:y1], False, f"full/{pi}/{y0}")
+    tabs = oracle_tables(fmt, w, h, tw, th, **kw)
+    peak = float(fmt.peak) if fmt.bits < 32 else 0.0
+    for i, pl in enumerate(planes):
+        t = tabs[1] if (len(tabs) > 1 and i in (1, 2)) else tabs[0]
+        H, W = t.dst_h, t.dst_w
+        info = flt.table(1 if (len(tabs) > 1 and i in (1, 2)) else 0).info
+        bands = [(0, 5), (H // 2 - 3, H // 2 + 3), (H - 5, H)]
+        bands += [(y, y + 2) for y in (63, 64, 255, 256, H // 3, 2 * H // 3) if y + 2 <= H]  # tile seams of the fast paths
+        bands += [(max(0, info.interior_y0 - 2), info.interior_y0 + 2), (info.interior_y1 - 2, min(H, info.interior_y1 + 2))]
+        for (y0, y1) in bands:
+            ref = t.resize(pl, peak, rows=(y0, y1))
+            assert_plane_close(got[i][y0:y1], ref[y0:y1], is_float, f"{name}/plane{i}/rows{y0}-{y1}")
+        # the left and right border strips over the full height: every 37th row, compared in the strip columns only
+        rows = list(range(0, H, 37))
+        xl, xr = info.interior_x0 + 8, max(info.interior_x1 - 8, 0)
+        for y in rows:
+            ref = t.resize(pl, peak, rows=(y, y + 1))
+            assert_plane_close(got[i][y:y + 1, :xl], ref[y:y + 1, :xl], is_float, f"{name}/plane{i}/left/row{y}")
+            assert_plane_close(got[i][y:y + 1, xr:], ref[y:y + 1, xr:], is_float, f"{name}/plane{i}/right/row{y}")
+    for t in tabs:
         t.close()
     flt.close()
 

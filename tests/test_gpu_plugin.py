@@ -47,15 +47,18 @@ def test_plugin_frames_match_reference_plugin(envs, case):
         rclip = theirs.invoke("JincResize", rsrc, tw, th, opt=0, **kw)
     for n in range(3):
         got, props = clip.get_frame(n)
+        rprops = None
         if rclip is not None:
-            ref, _ = rclip.get_frame(n)
+            ref, rprops = rclip.get_frame(n)
         else:
             ref, _ = oracle_frame(fmt, w, h, tw, th, frames[n], **kw)
         for i, (g, r) in enumerate(zip(got, ref)):
             assert_plane_close(g, r, fmt.bits == 32, f"{name}/frame{n}/plane{i}")
+        # frame properties: identical to the reference plugin's (which writes _ChromaLocation = 2 whatever cplace was used)
+        if rprops is not None:
+            assert props == rprops
         if fmt.family in ("420", "422", "411", "yuva420", "yuva422"):
-            want = {"mpeg2": 0, "mpeg1": 1, "topleft": 2}[kw.get("cplace", "mpeg2").lower()]
-            assert props["_ChromaLocation"] == want
+            assert props["_ChromaLocation"] == 2
         else:
             assert "_ChromaLocation" not in props
     for c in (clip, src, rclip, rsrc):
@@ -75,7 +78,76 @@ def test_cplace_defaults_from_frame_property(envs):
         ref, _ = oracle_frame(fmt, w, h, 192, 128, planes, tap=3, cplace=name)
         for g, r in zip(got, ref):
             assert_plane_close(g, r, False, f"cplace-from-prop/{name}")
-        assert props["_ChromaLocation"] == loc
+        assert props["_ChromaLocation"] == 2  # as the reference: src/JincResize.cpp:617-625 with d->cplace never set
+
+
+def test_chroma_location_property_in_both_modes(envs, monkeypatch):
+    """Default: the output _ChromaLocation is what the reference plugin writes (always 2 for subsampled clips -- its
+    instance never stores the parsed cplace).  JINCRESIZE_B200_CHROMALOC=actual writes the cplace that was used, which
+    is what the reference's README documents.  Both are pinned here, the default against the reference plugin itself."""
+    from minihost import avs_host as ah
+
+    ours, theirs = envs
+    planes420 = make_planes(ah.YV12, 96, 64)
+    f422 = ah.Format("422", 10)
+    planes422 = make_planes(f422, 96, 64)
+    for fmt, planes, places in ((ah.YV12, planes420, ("mpeg2", "mpeg1", "topleft")), (f422, planes422, ("MPEG2", "MPEG1"))):
+        for cp in places:
+            monkeypatch.delenv("JINCRESIZE_B200_CHROMALOC", raising=False)
+            src = ours.source(fmt, 96, 64, [planes], props={"_ChromaLocation": 1, "_Matrix": 6})
+            _, props = ours.invoke("JincResize", src, 144, 96, cplace=cp).get_frame(0)
+            assert props == {"_ChromaLocation": 2, "_Matrix": 6}
+            if theirs is not None:
+                rsrc = theirs.source(fmt, 96, 64, [planes], props={"_ChromaLocation": 1, "_Matrix": 6})
+                _, rprops = theirs.invoke("JincResize", rsrc, 144, 96, cplace=cp, opt=0).get_frame(0)
+                assert props == rprops
+            monkeypatch.setenv("JINCRESIZE_B200_CHROMALOC", "actual")
+            src = ours.source(fmt, 96, 64, [planes], props={"_ChromaLocation": 1, "_Matrix": 6})
+            _, props = ours.invoke("JincResize", src, 144, 96, cplace=cp).get_frame(0)
+            assert props == {"_ChromaLocation": {"mpeg2": 0, "mpeg1": 1, "topleft": 2}[cp.lower()], "_Matrix": 6}
+    monkeypatch.delenv("JINCRESIZE_B200_CHROMALOC", raising=False)
+    # a 4:4:4 clip carries the source's value through untouched in either mode
+    f444 = ah.Format("444", 8)
+    src = ours.source(f444, 96, 64, [make_planes(f444, 96, 64)], props={"_ChromaLocation": 1})
+    _, props = ours.invoke("JincResize", src, 144, 96).get_frame(0)
+    assert props == {"_ChromaLocation": 1}
+
+
+def test_identical_instances_share_one_gpu_filter(envs, monkeypatch):
+    """MT_MULTI_INSTANCE hosts build one instance per Prefetch thread (the reference's mode, src/JincResize.cpp:649-652).
+    Instances created with identical arguments share one GPU filter through the plugin's reference-counted cache, so
+    that mode costs no extra tables or slots; JINCRESIZE_B200_MTMODE=2 makes the plugin report it."""
+    from jinc_b200 import capi
+    from minihost import avs_host as ah
+
+    ours, _ = envs
+    fmt, w, h = ah.YV12, 96, 64
+    planes = make_planes(fmt, w, h)
+    n0 = capi.live_filters()
+    src = ours.source(fmt, w, h, [planes])
+    clips = [ours.invoke("Jinc36Resize", src, 192, 128) for _ in range(4)]
+    assert capi.live_filters() == n0 + 1
+    other = ours.invoke("Jinc64Resize", src, 192, 128)
+    assert capi.live_filters() == n0 + 2
+    ref, _ = oracle_frame(fmt, w, h, 192, 128, planes, tap=3)
+    for c in clips:
+        got, _ = c.get_frame(0)
+        for g, r in zip(got, ref):
+            assert_plane_close(g, r, False, "shared filter")
+    assert clips[0].mt_mode == 1
+    monkeypatch.setenv("JINCRESIZE_B200_MTMODE", "2")
+    assert clips[0].mt_mode == 2
+    monkeypatch.delenv("JINCRESIZE_B200_MTMODE")
+    for c in clips[:3]:
+        c.release()
+    assert capi.live_filters() == n0 + 2  # the last sharer keeps the filter alive
+    got, _ = clips[3].get_frame(0)
+    for g, r in zip(got, ref):
+        assert_plane_close(g, r, False, "last sharer")
+    clips[3].release()
+    other.release()
+    src.release()
+    assert capi.live_filters() == n0
 
 
 def test_prefetch_threads_share_one_instance(envs):
