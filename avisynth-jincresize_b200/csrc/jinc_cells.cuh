@@ -1,0 +1,276 @@
+// jinc_cells.cuh -- interior kernel for rational ratios P:Q whose phase pattern is piecewise periodic (3:2 = 720p -> 1080p,
+// 4:3, 3x, 4x, shifts at 1:1, ...); included by jinc_cells_<type>.cu, which instantiates launch_cells for one sample type.
+//
+// Replaces JincResize::resize_plane_c (src/JincResize.cpp:560-587) for the pixels whose coefficient block the reference
+// finds through factor_map (:431-435, 517-518).  With crop/dst = Q/P output P*c + p of a row reads the window at
+// Q*c + off[p] with the phase block of residue p -- exactly so when Q/P is a dyadic fraction (the periodic paths), and
+// PIECEWISE so otherwise: the reference accumulates positions in float (:363, 524-528), the quantised phase of a residue
+// drifts, and every few dozen cells it steps to the next phase index (1280 -> 1920: 15 phases per axis over 31 runs).
+// The table build cuts each axis into CHUNKS of up to 4 cells inside which every residue keeps its phase block and its
+// origins advance by exactly Q per cell (jinc_table.cu, build_cells_axis).
+//
+// One thread owns one x-chunk x one y-chunk and walks the P x P residue pairs one after the other: the 4 x 4 outputs of
+// a pair share ONE weight block, held in registers (FS*FS floats, read once per pass from L1/L2), and their windows
+// overlap, so a row of Q*3 + FS source values feeds 4 x FS FMAs of up to 4 output rows.  The source footprint of the
+// whole tile (32 x-chunks x WARPS y-chunks, all residues) is staged ONCE into shared memory as floats, columns
+// de-interleaved by (c mod 4Q) so that the lanes of a warp -- consecutive chunks, 4Q columns apart -- read consecutive
+// words.  The row loop is fully unrolled: every shared-memory address is a per-pass register plus an immediate.
+#ifndef JINC_CELLS_CUH
+#define JINC_CELLS_CUH
+
+#include <climits>
+
+#include "jinc_resample.cuh"
+
+namespace jinc_rs {
+
+template <int FS, int Q>
+struct CellsGeom {
+    static constexpr int NX = JINC_CELLS_NX, NY = JINC_CELLS_NY;
+    static constexpr int WARPS = jinc_cells_warps(Q);
+    static constexpr int THREADS = 32 * WARPS;
+    static constexpr int FSP = (FS + 3) & ~3;
+    static constexpr int SPAN = Q * (NX - 1) + FS; // columns a thread reads per source row
+    static constexpr int NROW = Q * (NY - 1) + FS; // source rows a thread walks per pass
+    static constexpr int D = Q * NX;               // column de-interleave modulus
+    static constexpr int FW = jinc_cells_footprint(Q, FS, NX, 32);    // staged columns (worst case, checked by the table build)
+    static constexpr int FH = jinc_cells_footprint(Q, FS, NY, WARPS); // staged rows
+    static constexpr int SUB = (FW + D - 1) / D;
+    static constexpr int ROW = D * SUB;
+    static constexpr size_t SMEM = (size_t)FH * ROW * sizeof(float);
+};
+
+struct CellsArgs {
+    FrameSet fr;
+    StripArgs st;
+    const int32_t* cx_cell; // per x-chunk: first cell, cells, then per residue the window origin and phase rank
+    const int32_t* cx_n;
+    const int32_t* cx_org;
+    const int32_t* cx_rank;
+    const int32_t* cy_cell;
+    const int32_t* cy_n;
+    const int32_t* cy_org;
+    const int32_t* cy_rank;
+    const float* wblocks; // phase blocks [block][FS][wstride]
+    int wstride;
+    int Px, Py, x0, y0, n_rank_x;
+    int n_cx;                   // x-chunks
+    int cyk_begin, cyk_end;     // y-chunks of this launch (row band)
+    int cell_y_begin, cell_y_end; // cell rows to produce
+    int src_w, src_h;
+    int tiles_x, tiles_per_plane, interior_blocks, strip_blocks, strip_shift;
+    unsigned tiles_x_magic, tiles_per_plane_magic;
+};
+
+constexpr int CL_STRIP_SPT = 4;
+constexpr int CL_STRIP_MAX_PW = 64;
+
+template <typename T, int FS, int Q>
+__global__ void __launch_bounds__((CellsGeom<FS, Q>::THREADS), 2) resample_cells(const __grid_constant__ CellsArgs a)
+{
+    using G = CellsGeom<FS, Q>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* __restrict__ tile = reinterpret_cast<float*>(smem_raw);
+
+    unsigned role_id;
+    if (block_role(blockIdx.x, (unsigned)a.strip_blocks, a.strip_shift, role_id)) {
+        strip_block<T, FS, G::THREADS, CL_STRIP_SPT>(a.st, a.fr, role_id, tile);
+        return;
+    }
+    const int plane = (int)div_by(role_id, a.tiles_per_plane_magic);
+    const int tidx = role_id - plane * a.tiles_per_plane;
+    const int tile_y = (int)div_by((unsigned)tidx, a.tiles_x_magic), tile_x = tidx - tile_y * a.tiles_x;
+    const PlanePtrs& pp = frame_ptrs(a.fr);
+    const T* __restrict__ src = static_cast<const T*>(pp.src[plane]);
+    T* __restrict__ dst = static_cast<T*>(pp.dst[plane]);
+    const int sp = (int)pp.src_pitch[plane];
+    const long long dp = pp.dst_pitch[plane];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int Px = a.Px, Py = a.Py;
+
+    // ---- footprint origin of the tile: the smallest origin of its first chunks (origins grow with the chunk index)
+    const int cxk0 = tile_x * 32, cyk0 = a.cyk_begin + tile_y * G::WARPS;
+    int lo_x = INT_MAX, lo_y = INT_MAX;
+    for (int p = 0; p < Px; ++p)
+        lo_x = min(lo_x, __ldg(a.cx_org + cxk0 * Px + p));
+    for (int p = 0; p < Py; ++p)
+        lo_y = min(lo_y, __ldg(a.cy_org + cyk0 * Py + p));
+
+    // ---- stage the footprint once, converted to float; a warp takes rows, a lane the columns lane + 32 q.  Two rows of
+    //      loads are in flight before the first store.
+    {
+        constexpr int CQ = (G::FW + 31) / 32;
+        int gx[CQ], so[CQ];
+#pragma unroll
+        for (int q = 0; q < CQ; ++q) {
+            const int c = lane + 32 * q;
+            gx[q] = min(max(lo_x + c, 0), a.src_w - 1); // columns outside the plane only feed chunks that do not exist
+            so[q] = (c % G::D) * G::SUB + c / G::D;
+        }
+        for (int r0 = warp; r0 < G::FH; r0 += 2 * G::WARPS) {
+            T v[2][CQ];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int r = min(r0 + u * G::WARPS, G::FH - 1);
+                const T* __restrict__ srow = src + (long long)min(max(lo_y + r, 0), a.src_h - 1) * sp;
+#pragma unroll
+                for (int q = 0; q < CQ; ++q)
+                    v[u][q] = __ldg(srow + gx[q]);
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int r = r0 + u * G::WARPS;
+                if (r < G::FH) {
+#pragma unroll
+                    for (int q = 0; q < CQ; ++q)
+                        if (G::FW % 32 == 0 || lane + 32 * q < G::FW)
+                            tile[r * G::ROW + so[q]] = sample_to_float(v[u][q]);
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    const int cxk = cxk0 + lane, cyk = cyk0 + warp;
+    if (cxk >= a.n_cx || cyk >= a.cyk_end)
+        return;
+    const int ncx = __ldg(a.cx_n + cxk), ncy = __ldg(a.cy_n + cyk);
+    const int cell_x = __ldg(a.cx_cell + cxk), cell_y = __ldg(a.cy_cell + cyk);
+
+#pragma unroll 1
+    for (int py = 0; py < Py; ++py) {
+        const int oy = __ldg(a.cy_org + cyk * Py + py) - lo_y;
+        const int ry = __ldg(a.cy_rank + cyk * Py + py);
+#pragma unroll 1
+        for (int px = 0; px < Px; ++px) {
+            const int ox = __ldg(a.cx_org + cxk * Px + px) - lo_x;
+            const int rx = __ldg(a.cx_rank + cxk * Px + px);
+
+            // the pair's weight block, in registers for the whole pass
+            float w[FS][FS];
+            {
+                const float* __restrict__ wb = a.wblocks + (size_t)(ry * a.n_rank_x + rx) * (unsigned)(FS * a.wstride);
+                if (a.wstride == G::FSP) {
+#pragma unroll
+                    for (int ly = 0; ly < FS; ++ly) {
+#pragma unroll
+                        for (int q4 = 0; q4 < G::FSP / 4; ++q4) {
+                            const float4 t = __ldg(reinterpret_cast<const float4*>(wb + ly * G::FSP) + q4);
+                            const float tv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                if (4 * q4 + e < FS)
+                                    w[ly][4 * q4 + e] = tv[e];
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int ly = 0; ly < FS; ++ly)
+#pragma unroll
+                        for (int lx = 0; lx < FS; ++lx)
+                            w[ly][lx] = __ldg(wb + ly * a.wstride + lx);
+                }
+            }
+
+            // shared-memory word of column ox + k in the pass's first row
+            int addr[G::SPAN];
+            {
+                const int m0 = ox % G::D, q0 = ox / G::D;
+                const int base = oy * G::ROW + q0;
+#pragma unroll
+                for (int k = 0; k < G::SPAN; ++k)
+                    addr[k] = base + ((m0 + k) % G::D) * G::SUB + (m0 + k) / G::D;
+            }
+
+            float acc[G::NY][G::NX];
+#pragma unroll
+            for (int j = 0; j < G::NY; ++j)
+#pragma unroll
+                for (int i = 0; i < G::NX; ++i)
+                    acc[j][i] = 0.f;
+
+#pragma unroll
+            for (int r = 0; r < G::NROW; ++r) {
+                float s[G::SPAN];
+#pragma unroll
+                for (int k = 0; k < G::SPAN; ++k)
+                    s[k] = tile[addr[k] + r * G::ROW];
+#pragma unroll
+                for (int j = 0; j < G::NY; ++j) {
+                    const int ly = r - Q * j; // weight row of output row j (a constant after unrolling)
+                    if (ly >= 0 && ly < FS) {
+#pragma unroll
+                        for (int lx = 0; lx < FS; ++lx)
+#pragma unroll
+                            for (int i = 0; i < G::NX; ++i)
+                                acc[j][i] = fmaf(s[Q * i + lx], w[ly][lx], acc[j][i]);
+                    }
+                }
+            }
+
+            // ---- this residue pair's samples of the chunk: every Px-th column of every Py-th row
+#pragma unroll
+            for (int j = 0; j < G::NY; ++j) {
+                const int cy = cell_y + j;
+                if (j < ncy && cy >= a.cell_y_begin && cy < a.cell_y_end) {
+                    T* __restrict__ o = dst + (long long)(a.y0 + Py * cy + py) * dp + (a.x0 + Px * cell_x + px);
+#pragma unroll
+                    for (int i = 0; i < G::NX; ++i)
+                        if (i < ncx)
+                            o[i * Px] = finish<T>(acc[j][i], a.fr.peak);
+                }
+            }
+        }
+    }
+}
+
+template <typename T, int FS, int Q>
+int launch_cells_cfg(const jinc_table* t, CellsArgs& a, int n_frames, cudaStream_t st, const Rect* rects, int n_rects)
+{
+    using G = CellsGeom<FS, Q>;
+    auto kern = resample_cells<T, FS, Q>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
+    if (e != cudaSuccess)
+        return jinc_fail(JINC_E_CUDA, "cudaFuncSetAttribute(cells smem %zu): %s", G::SMEM, cudaGetErrorString(e));
+    const long long strip_blocks =
+        n_rects > 0 ? set_strip_rects(a.st, rects, n_rects, G::THREADS * CL_STRIP_SPT, CL_STRIP_MAX_PW, G::SMEM) * a.fr.n_planes : 0;
+    a.tiles_x = (a.n_cx + 31) / 32;
+    a.tiles_per_plane = a.tiles_x * ((a.cyk_end - a.cyk_begin + G::WARPS - 1) / G::WARPS);
+    a.tiles_x_magic = div_magic((unsigned)a.tiles_x);
+    a.tiles_per_plane_magic = div_magic((unsigned)a.tiles_per_plane);
+    if (a.interior_blocks)
+        a.interior_blocks = a.tiles_per_plane * a.fr.n_planes;
+    if (a.interior_blocks + strip_blocks == 0)
+        return 2;
+    a.strip_blocks = (int)strip_blocks;
+    a.strip_shift = strip_role_shift(a.interior_blocks, strip_blocks);
+    dim3 grid((unsigned)(a.interior_blocks + strip_blocks), n_frames, 1);
+    kern<<<grid, G::THREADS, G::SMEM, st>>>(a);
+    e = cudaGetLastError();
+    if (e != cudaSuccess)
+        return jinc_fail(JINC_E_CUDA, "resample_cells launch failed: %s", cudaGetErrorString(e));
+    (void)t;
+    return JINC_OK;
+}
+
+// 0 launched, 2 nothing to do, 1 unsupported geometry, <0 error
+template <typename T>
+int launch_cells(const jinc_table* t, CellsArgs& a, int n_frames, cudaStream_t st, const Rect* rects, int n_rects)
+{
+    switch (t->cells.Q * 100 + t->sc.fs) {
+#define JINC_CELLS_CASE(Q_, FS_) \
+    case Q_ * 100 + FS_: return launch_cells_cfg<T, FS_, Q_>(t, a, n_frames, st, rects, n_rects);
+        JINC_CELLS_CASE(1, 7) // tap 3: 3x, 4x, 5x ..., and shifts at 1:1
+        JINC_CELLS_CASE(1, 9) // tap 4
+        JINC_CELLS_CASE(2, 7) // tap 3: 3:2 (720p -> 1080p, 1440p -> 2160p), 5:2
+        JINC_CELLS_CASE(2, 9) // tap 4
+        JINC_CELLS_CASE(3, 7) // tap 3: 4:3 (1080p -> 1440p), 5:3
+        JINC_CELLS_CASE(3, 9) // tap 4
+#undef JINC_CELLS_CASE
+    default: return 1;
+    }
+}
+
+} // namespace jinc_rs
+
+#endif

@@ -114,7 +114,15 @@ struct Slot {
     jinc_hostmem::Pin src_pin, dst_pin;
     Sentinel sentinel[JINC_MAX_PLANES * kSentinelsPerPlane];
     int n_sentinels = 0;
+    // probe words of the uploaded source, read back when the source moved through a registration made here
+    uint32_t* d_probe = nullptr;
+    uint32_t* h_probe = nullptr; // pinned
+    uint32_t probe_seed = 0;
+    bool probe_active = false;
+    int src_row0[JINC_MAX_PLANES] = {}, src_row1[JINC_MAX_PLANES] = {}; // source rows uploaded per plane
 };
+
+constexpr int kRedoStaged = 1; // finish_frame: a registration turned out stale -- run the frame again through the mirrors
 
 struct DeviceState {
     jinc_ctx* ctx = nullptr;
@@ -169,6 +177,7 @@ struct jinc_filter {
     int64_t next_ticket = 0; // under mu
     std::atomic<int64_t> rr{0};
     std::atomic<int64_t> launches{0};
+    bool registers = false; // counted as a client of the host-buffer registry
 };
 
 namespace {
@@ -275,14 +284,16 @@ bool plane_range(const void* base, ptrdiff_t pitch, size_t row_bytes, int rows, 
     return true;
 }
 
-// Enqueue H2D + kernels + D2H for output rows [y0,y1) (luma rows) of `frame` on slot s.
-int enqueue_frame(jinc_filter* f, Slot* s, const jinc_frame* frame, int y0_luma, int y1_luma, bool whole)
+// Enqueue H2D + kernels + D2H for output rows [y0,y1) (luma rows) of `frame` on slot s.  staged_only: do not address the
+// caller's memory by DMA at all (the retry after a stale registration was found).
+int enqueue_frame(jinc_filter* f, Slot* s, const jinc_frame* frame, int y0_luma, int y1_luma, bool whole, bool staged_only = false)
 {
     DeviceState& d = f->devs[s->dev_index];
     JINC_CUDA(cudaSetDevice(d.ctx->device));
     const int sb = f->p.sample_bytes;
     const int np = f->p.n_planes;
-    const bool may_register = !(f->p.flags & JINC_FILTER_NO_HOST_REGISTER);
+    const bool may_register = (f->p.flags & JINC_FILTER_HOST_REGISTER) != 0;
+    s->probe_active = false;
     const bool padding_ok = (f->p.flags & JINC_FILTER_DST_PADDING_WRITABLE) != 0;
     s->pending = *frame;
     s->n_sentinels = 0;
@@ -307,11 +318,13 @@ int enqueue_frame(jinc_filter* f, Slot* s, const jinc_frame* frame, int y0_luma,
             sy0[i] = std::max(lo, 0);
             sy1[i] = std::min(hi, pl.src_h);
         }
+        s->src_row0[i] = sy0[i];
+        s->src_row1[i] = sy1[i];
     }
 
     // ---- source planes -> device
     jinc_hostmem::Range rs[JINC_MAX_PLANES];
-    bool src_direct = true, src_packed = whole;
+    bool src_direct = !staged_only, src_packed = whole;
     for (int i = 0; i < np; ++i) {
         const PlaneLayout& pl = f->planes[i];
         src_direct = src_direct && plane_range(frame->src[i], frame->src_pitch[i], static_cast<size_t>(pl.src_w) * sb, pl.src_h, &rs[i]);
@@ -322,6 +335,7 @@ int enqueue_frame(jinc_filter* f, Slot* s, const jinc_frame* frame, int y0_luma,
     src_direct = src_direct && jinc_hostmem::acquire(rs, np, may_register, &s->src_pin);
     if (src_direct) {
         g_direct_src.fetch_add(1, std::memory_order_relaxed);
+        s->probe_active = jinc_hostmem::registered_here(&s->src_pin);
         if (src_packed) {
             // the caller's planes are packed exactly like the slot (AviSynth+ frame buffers are): one transfer per frame
             const PlaneLayout& last = f->planes[np - 1];
@@ -359,6 +373,14 @@ int enqueue_frame(jinc_filter* f, Slot* s, const jinc_frame* frame, int y0_luma,
             JINC_CUDA(cudaMemcpyAsync(s->d_src, s->h_src, f->src_bytes, cudaMemcpyHostToDevice, s->stream));
     }
 
+    if (s->probe_active) {
+        s->probe_seed = static_cast<uint32_t>(fresh_nonce());
+        if (int rc = jinc_launch_probe(s->d_src, static_cast<uint32_t>(f->src_bytes / 4), s->probe_seed, s->d_probe, s->stream))
+            return rc;
+        f->launches.fetch_add(1);
+        JINC_CUDA(cudaMemcpyAsync(s->h_probe, s->d_probe, JINC_PROBE_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+    }
+
     // ---- kernels: planes that share a table go out in one launch
     for (int k = 0; k < f->n_tables; ++k) {
         const void* src[JINC_MAX_PLANES];
@@ -388,7 +410,7 @@ int enqueue_frame(jinc_filter* f, Slot* s, const jinc_frame* frame, int y0_luma,
 
     // ---- destination planes -> host
     jinc_hostmem::Range rd[JINC_MAX_PLANES];
-    bool dst_direct = true, dst_packed = whole, dst_tight = true;
+    bool dst_direct = !staged_only, dst_packed = whole, dst_tight = true;
     for (int i = 0; i < np; ++i) {
         const PlaneLayout& pl = f->planes[i];
         const size_t row_bytes = static_cast<size_t>(pl.dst_w) * sb;
@@ -460,6 +482,31 @@ int finish_frame(jinc_filter* f, Slot* s, int y0_luma, int y1_luma, bool whole)
     JINC_CUDA(cudaSetDevice(d.ctx->device));
     JINC_CUDA(cudaEventSynchronize(s->done));
     const int sb = f->p.sample_bytes;
+    if (s->probe_active) {
+        // what the GPU received through the registration against what the caller's memory holds now
+        const uint32_t n_words = static_cast<uint32_t>(f->src_bytes / 4);
+        bool same = true;
+        for (int k = 0; k < JINC_PROBE_WORDS && same; ++k) {
+            const size_t off = static_cast<size_t>(jinc_probe_index(s->probe_seed, static_cast<uint32_t>(k), n_words)) * 4;
+            for (int i = 0; i < f->p.n_planes; ++i) {
+                const PlaneLayout& pl = f->planes[i];
+                if (off < pl.src_off || off >= pl.src_off + pl.src_pitch * pl.src_h)
+                    continue;
+                const size_t row = (off - pl.src_off) / pl.src_pitch, col = (off - pl.src_off) % pl.src_pitch;
+                if (col + 4 <= static_cast<size_t>(pl.src_w) * sb && static_cast<int>(row) >= s->src_row0[i] && static_cast<int>(row) < s->src_row1[i])
+                    same = memcmp(static_cast<const unsigned char*>(s->pending.src[i]) + static_cast<ptrdiff_t>(row) * s->pending.src_pitch[i] + col,
+                                  &s->h_probe[k], 4) == 0;
+                break;
+            }
+        }
+        s->probe_active = false;
+        if (!same) {
+            jinc_hostmem::distrust(&s->src_pin);
+            if (s->dst_direct && s->n_sentinels > 0)
+                jinc_hostmem::distrust(&s->dst_pin); // same host, same habits: take no chances with this frame
+            return kRedoStaged;
+        }
+    }
     bool from_mirror = !s->dst_direct;
     if (s->dst_direct && s->n_sentinels > 0) {
         bool arrived = true;
@@ -490,6 +537,23 @@ int finish_frame(jinc_filter* f, Slot* s, int y0_luma, int y1_luma, bool whole)
                                 static_cast<ptrdiff_t>(pl.dst_pitch), static_cast<size_t>(pl.dst_w) * sb, b - a);
     }
     return JINC_OK;
+}
+
+// finish_frame, and when a stale registration was found, the frame again through the pinned mirrors
+int complete_frame(jinc_filter* f, Slot* s, int y0_luma, int y1_luma, bool whole)
+{
+    int rc = finish_frame(f, s, y0_luma, y1_luma, whole);
+    if (rc != kRedoStaged)
+        return rc;
+    const jinc_frame frame = s->pending;
+    jinc_hostmem::release(&s->src_pin);
+    jinc_hostmem::release(&s->dst_pin);
+    rc = enqueue_frame(f, s, &frame, y0_luma, y1_luma, whole, true);
+    if (rc != JINC_OK) {
+        cudaStreamSynchronize(s->stream);
+        return rc;
+    }
+    return finish_frame(f, s, y0_luma, y1_luma, whole);
 }
 
 int check_frame(const jinc_filter* f, const jinc_frame* frame)
@@ -538,6 +602,8 @@ extern "C" void jinc_filter_destroy(jinc_filter* f)
         cudaFree(s->d_dst);
         cudaFreeHost(s->h_src);
         cudaFreeHost(s->h_dst);
+        cudaFree(s->d_probe);
+        cudaFreeHost(s->h_probe);
         if (s->done)
             cudaEventDestroy(s->done);
         if (s->stream)
@@ -557,6 +623,8 @@ extern "C" void jinc_filter_destroy(jinc_filter* f)
         jinc_table_destroy(d.tables[1]);
         jinc_ctx_destroy(d.ctx);
     }
+    if (f->registers)
+        jinc_hostmem::client_remove();
     delete f;
     g_live_filters.fetch_sub(1);
 }
@@ -601,6 +669,10 @@ extern "C" int jinc_filter_create(const jinc_filter_params* p, jinc_filter** out
     std::unique_ptr<jinc_filter, void (*)(jinc_filter*)> f(new jinc_filter(), jinc_filter_destroy);
     g_live_filters.fetch_add(1);
     f->p = *p;
+    if (p->flags & JINC_FILTER_HOST_REGISTER) {
+        jinc_hostmem::client_add();
+        f->registers = true;
+    }
     f->peak = (p->sample_bytes == 4) ? 0.f : static_cast<float>((1 << p->bits) - 1); // :793
     derive_table_params(*p, f->tparams, &f->n_tables);
 
@@ -655,7 +727,9 @@ extern "C" int jinc_filter_create(const jinc_filter_params* p, jinc_filter** out
             if (cudaMalloc(reinterpret_cast<void**>(&s->d_src), so) != cudaSuccess ||
                 cudaMalloc(reinterpret_cast<void**>(&s->d_dst), dof) != cudaSuccess ||
                 cudaHostAlloc(reinterpret_cast<void**>(&s->h_src), so, cudaHostAllocPortable) != cudaSuccess ||
-                cudaHostAlloc(reinterpret_cast<void**>(&s->h_dst), dof, cudaHostAllocPortable) != cudaSuccess) {
+                cudaHostAlloc(reinterpret_cast<void**>(&s->h_dst), dof, cudaHostAllocPortable) != cudaSuccess ||
+                cudaMalloc(reinterpret_cast<void**>(&s->d_probe), JINC_PROBE_WORDS * sizeof(uint32_t)) != cudaSuccess ||
+                cudaHostAlloc(reinterpret_cast<void**>(&s->h_probe), JINC_PROBE_WORDS * sizeof(uint32_t), cudaHostAllocPortable) != cudaSuccess) {
                 const char* msg = cudaGetErrorString(cudaGetLastError());
                 return jinc_fail(JINC_E_NOMEM, "JincResize: failed to allocate frame buffers (%zu + %zu bytes): %s", so, dof, msg);
             }
@@ -699,7 +773,7 @@ extern "C" int jinc_filter_process(jinc_filter* f, const jinc_frame* frame)
     Slot* s = acquire_slot(f, true);
     int rc = enqueue_frame(f, s, frame, 0, f->p.target_h, true);
     if (rc == JINC_OK)
-        rc = finish_frame(f, s, 0, f->p.target_h, true);
+        rc = complete_frame(f, s, 0, f->p.target_h, true);
     else
         cudaStreamSynchronize(s->stream);
     release_slot(f, s);
@@ -840,7 +914,7 @@ extern "C" int jinc_filter_wait(jinc_filter* f, int64_t ticket)
     if (!s)
         return jinc_fail(JINC_E_INVALID, "jinc_filter_wait: unknown ticket %lld (never issued, or already waited on)",
                          static_cast<long long>(ticket));
-    const int rc = finish_frame(f, s, 0, f->p.target_h, true);
+    const int rc = complete_frame(f, s, 0, f->p.target_h, true);
     release_slot(f, s);
     return rc;
 }
@@ -887,7 +961,7 @@ extern "C" int jinc_filter_process_bands(jinc_filter* f, const jinc_frame* frame
     auto finish_oldest = [&]() {
         InFlight& b = fifo[head++];
         if (rc == JINC_OK)
-            rc = finish_frame(f, b.s, b.y0, b.y1, false);
+            rc = complete_frame(f, b.s, b.y0, b.y1, false);
         else
             cudaStreamSynchronize(b.s->stream);
         release_slot(f, b.s);

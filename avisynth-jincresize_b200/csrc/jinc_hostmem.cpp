@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdlib>
 #include <cstring>
@@ -32,6 +33,7 @@ struct Entry {
     int users = 0;
     bool poisoned = false;
     uint64_t tick = 0;
+    double last_use = 0.0; // seconds (steady clock)
 };
 
 std::mutex g_mu;
@@ -40,7 +42,17 @@ size_t g_reg_bytes = 0;
 uint64_t g_tick = 0;
 long g_registrations = 0;
 
+int g_clients = 0;        // live filters that asked for registration
+double g_last_sweep = 0.0;
+
 constexpr size_t kMaxEntries = 4096;
+constexpr double kIdleSeconds = 2.0;  // a registration not used for this long is dropped (the host may have retired the buffer)
+constexpr double kSweepEvery = 0.25;
+
+double now_s()
+{
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 constexpr uintptr_t kGroupGap = 64 << 10; // planes closer than this belong to one allocation
 
 size_t budget_bytes()
@@ -102,6 +114,22 @@ bool make_room_locked(size_t need)
         victim->sightings = 0;
     }
     return true;
+}
+
+// g_mu held: registrations that have not been used for a while are dropped -- a buffer the host still recycles is seen
+// again within a frame time or so, one it has retired (or freed) must not stay page-locked
+void sweep_locked(double now)
+{
+    if (now - g_last_sweep < kSweepEvery)
+        return;
+    g_last_sweep = now;
+    for (auto& kv : g_entries) {
+        Entry* e = kv.second;
+        if (e->state == Entry::REGISTERED && e->users == 0 && now - e->last_use > kIdleSeconds) {
+            unregister_locked(e);
+            e->sightings = 1; // registered again the next time it comes back
+        }
+    }
 }
 
 // g_mu held: forget buffers that never came back once the table grows
@@ -189,7 +217,9 @@ bool acquire(const Range* ranges, int n, bool may_register, Pin* pin)
     }
 
     Entry* got[JINC_MAX_PLANES];
+    const double now = now_s();
     std::unique_lock<std::mutex> lk(g_mu);
+    sweep_locked(now);
     for (int g = 0; g < ng; ++g) {
         Entry* e = nullptr;
         auto it = g_entries.find(glo[g]);
@@ -214,6 +244,7 @@ bool acquire(const Range* ranges, int n, bool may_register, Pin* pin)
         }
         ++e->sightings;
         e->tick = ++g_tick;
+        e->last_use = now;
         if (e->state == Entry::SEEN && may_register && e->sightings >= 2 && !e->poisoned) {
             e->state = Entry::REGISTERING;
             lk.unlock();
@@ -233,13 +264,39 @@ bool acquire(const Range* ranges, int n, bool may_register, Pin* pin)
     return true;
 }
 
+void client_add()
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    ++g_clients;
+}
+
+void client_remove()
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (--g_clients > 0)
+        return;
+    // the last filter that registers caller memory is gone: nothing stays page-locked behind the host's back
+    for (auto it = g_entries.begin(); it != g_entries.end();) {
+        Entry* e = it->second;
+        if (e->users == 0 && e->state != Entry::REGISTERING) {
+            unregister_locked(e);
+            delete e;
+            it = g_entries.erase(it);
+        } else {
+            ++it;
+        }
+    }
+}
+
 void release(Pin* pin)
 {
     if (pin->n == 0)
         return;
+    const double now = now_s();
     std::lock_guard<std::mutex> lk(g_mu);
     for (int g = 0; g < pin->n; ++g) {
         Entry* e = static_cast<Entry*>(pin->entry[g]);
+        e->last_use = now;
         if (--e->users == 0 && e->poisoned) {
             unregister_locked(e);
             e->state = Entry::REFUSED;

@@ -5,7 +5,14 @@
 // memory.  A host recycles its frame buffers (AviSynth's frame cache, the mini-host's pool), so the pipeline remembers
 // every buffer it has seen: buffers the caller allocated page-locked are used directly; pageable buffers are staged
 // through the slot's pinned mirror the first time and registered (cudaHostRegister) when they come back, after which
-// they are used directly too.  Registered memory is capped and evicted least-recently-used.
+// they are used directly too.  Registered memory is capped and evicted least-recently-used; a registration that has
+// not been used for two seconds is dropped, and everything is unregistered when the last registering filter goes.
+//
+// Registration is OPT-IN (JINC_FILTER_HOST_REGISTER) because it rests on a promise only the host can make: a buffer
+// that was registered must not be freed while it still is.  A stale registration sends DMA to the buffer's former
+// physical pages and makes unrelated CUDA calls that touch the re-used address range fail.  The pipeline therefore
+// checks every transfer through a registration it made (arrival sentinels in destination planes, probe words read back
+// from source planes) and drops the registration -- redoing the frame through the staged path -- on a miss.
 #ifndef JINC_HOSTMEM_H
 #define JINC_HOSTMEM_H
 
@@ -31,6 +38,9 @@ struct Pin {
 // buffer has been seen before); the ranges are then pinned against eviction until release().  False: stage the frame.
 bool acquire(const Range* ranges, int n, bool may_register, Pin* pin);
 void release(Pin* pin);
+// filters that may register caller memory; when the last one goes every registration is dropped
+void client_add();
+void client_remove();
 // true when any of the pinned ranges is page-locked by a registration made here (as opposed to by the caller)
 bool registered_here(const Pin* pin);
 // A transfer through ranges this module registered did not arrive (the host freed and re-mapped the memory behind the

@@ -19,9 +19,11 @@ int jinc_fail(int code, const char* fmt, ...) __attribute__((format(printf, 2, 3
 #define JINC_CUDA(call)                                                                                     \
     do {                                                                                                    \
         cudaError_t err_ = (call);                                                                          \
-        if (err_ != cudaSuccess)                                                                            \
+        if (err_ != cudaSuccess) {                                                                          \
+            cudaGetLastError(); /* reported here: must not resurface at the next launch check */            \
             return jinc_fail(JINC_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(err_), __FILE__, \
                              __LINE__);                                                                     \
+        }                                                                                                   \
     } while (0)
 
 // ---------------------------------------------------------------- context
@@ -93,6 +95,33 @@ struct PeriodicPlan {
     int wblock[4][4] = {};                // [py][px] -> phase-block index
 };
 
+// Piecewise-periodic rational ratio (jinc_cells.cuh): crop/dst = Q/P on both axes.  Each axis is cut into CHUNKS of up to
+// JINC_CELLS_N* cells (a cell = P consecutive outputs) inside which every residue p keeps its phase rank and its window
+// origins advance by exactly Q per cell.
+constexpr int JINC_CELLS_NX = 4, JINC_CELLS_NY = 4;
+constexpr int jinc_cells_warps(int q) { return q >= 3 ? 4 : 8; } // y-chunks per tile (one per warp)
+// samples staged along one axis for a tile of `chunks` chunks of n cells: the chunks' cells, the window, and slack for the
+// residues' origin offsets and one irregular origin step
+constexpr int jinc_cells_footprint(int q, int fs, int n, int chunks) { return q * n * chunks + fs + q + 2; }
+constexpr bool jinc_cells_instantiated(int q, int fs) { return q >= 1 && q <= 3 && (fs == 7 || fs == 9); }
+
+struct CellsAxis {
+    int P = 0, Q = 0;
+    int first = 0, ncells = 0; // first output of cell 0, number of cells
+    int n_chunks = 0;
+    std::vector<int32_t> cell, n, org, rank; // per chunk: first cell, cells; per (chunk, residue): window origin, phase rank
+    int32_t* d_cell = nullptr;
+    int32_t* d_n = nullptr;
+    int32_t* d_org = nullptr;
+    int32_t* d_rank = nullptr;
+};
+
+struct CellsPlan {
+    bool ok = false;
+    int Q = 0;
+    CellsAxis ax[2];
+};
+
 struct jinc_table {
     jinc_ctx* ctx = nullptr;
     jinc_table_params params{};
@@ -117,6 +146,7 @@ struct jinc_table {
     Up2xPlan up2x;
     DownPlan down;
     PeriodicPlan periodic;
+    CellsPlan cells;
     int fast_path = JINC_PATH_GENERAL;
     int ix0 = 0, ix1 = 0, iy0 = 0, iy1 = 0; // interior rectangle run by the fast path (empty if none)
     float build_ms = 0.f;                   // host wall time of jinc_table_create
@@ -144,5 +174,23 @@ int jinc_pack_plane_ptrs(void* out, int sample_bytes, int n_planes, const void* 
 int jinc_launch_resize_batch(jinc_ctx* ctx, const jinc_table* t, int sample_bytes, float peak, int n_planes,
                              const void* d_frame_ptrs, int n_frames, cudaStream_t stream, int* launches, int parts);
 int jinc_debug_pixel_weights(const jinc_table* t, int x, int y, float* out);
+// probe words of a device buffer: d_out[k] = 32-bit word jinc_probe_index(seed, k, n_words) of d_buf, k < JINC_PROBE_WORDS
+constexpr int JINC_PROBE_WORDS = 256;
+#ifdef __CUDACC__
+#define JINC_HOST_DEVICE __host__ __device__
+#else
+#define JINC_HOST_DEVICE
+#endif
+JINC_HOST_DEVICE inline uint32_t jinc_probe_index(uint32_t seed, uint32_t k, uint32_t n_words)
+{
+    uint32_t x = seed + k * 0x9E3779B9u;
+    x ^= x >> 16;
+    x *= 0x7feb352du;
+    x ^= x >> 15;
+    x *= 0x846ca68bu;
+    x ^= x >> 16;
+    return static_cast<uint32_t>((static_cast<uint64_t>(x) * n_words) >> 32);
+}
+int jinc_launch_probe(const void* d_buf, uint32_t n_words, uint32_t seed, uint32_t* d_out, cudaStream_t stream);
 
 #endif

@@ -1,35 +1,11 @@
-// jinc_resize.cu -- EWA resampling kernels for sm_100a and their launcher.
+// jinc_resize.cu -- the general (any ratio) resample kernel and the launcher that picks a kernel family per table.
 //
 // Replaces JincResize::resize_plane_c<T,thr,subsampled> (src/JincResize.cpp:536-601) and the three SIMD copies of
-// its inner loop.  Every output sample is  sum_{ly,lx} src[start_y+ly][start_x+lx] * w[ly][lx]  over an fs x fs
-// window, followed for integer formats by clamp to [0,peak] and round-half-even (:581-582); float is raw (:583-584).
-//
-// One launch covers ALL planes that share a coefficient table, for a whole BATCH of frames, interior and border
-// together; blocks take one of two roles:
-//
-//   interior tile
-//       exact 2x upscale (jinc_up2x.cuh, every "JincNNResize(2w,2h)" use): the table has 2x2 phase classes.  A thread
-//       owns TX=4 source-aligned cells x 2 cell rows = 8x4 output samples in 16 float2 accumulators.  The source tile
-//       lives in shared memory as VERTICAL PAIRS {S[r][c], S[r+1][c]} so one packed FFMA2 (fma.rn.f32x2, new on sm_100)
-//       updates the same phase of two cell rows with a single scalar weight.  Weights arrive as kernel parameters
-//       (constant bank) and reach the FMA pipe through uniform registers (LDCU -> FFMA2 R, R, UR, R): they cost no
-//       shared-memory or register-file bandwidth.  Pair columns are de-interleaved by (c & 3) so a warp's LDS.64 is
-//       bank-conflict free.
-//       integer-ratio downscale and the passes of the periodic 2:3 / 4:3 paths (jinc_down.cuh): polyphase columns,
-//       vertical tap pairing, raw sample pairs in shared memory.
-//   strip patch (512 output samples of the border strips; strip_block below)
-//       One thread = 4 output samples that share a border row or column (hence, normally, one weight block): the
-//       patch's source footprint is staged in shared memory as floats, weights are read as float4 rows from the
-//       per-class border blocks or the padded phase blocks.  Border pixels that fold into no class fall back to
-//       resident per-pixel weights or to the reference's formula evaluated per tap (exact LUT index, divided by the
-//       stored per-pixel normaliser, :443-514).
-//
-// General ratios (no fast path) run resample_strips in jinc_resize.cu: the same patch scheme over the whole plane, one
-// block covering the patch in every plane of the table.
-//
-// This translation unit holds the general (any ratio) kernel and the launcher; the exact-2x and integer-ratio
-// downscale kernels live in jinc_up2x_*.cu / jinc_down_*.cu (one per sample type, so the build runs in parallel).
-#include "jinc_resample.cuh"
+// its inner loop.  The layout of the kernels, the block roles of a merged launch and the strip role for border pixels
+// are described once, in jinc_resample.cuh; the kernel families live in jinc_up2x.cuh (exact 2x), jinc_down.cuh
+// (integer-ratio downscale and the exactly periodic 2:3 path) and jinc_cells.cuh (rational ratios with piecewise-periodic
+// phases), each instantiated once per sample type in its own translation unit so that the build runs in parallel.
+#include "jinc_cells.cuh"
 
 using namespace jinc_rs;
 
@@ -297,6 +273,61 @@ int launch_typed(const jinc_table* t, const FrameSet& fr, int n_frames, int y_be
             }
         }
     }
+    if (t->fast_path == JINC_PATH_CELLS && t->cells.ok) {
+        const CellsAxis &ax = t->cells.ax[0], &ay = t->cells.ax[1];
+        // cell rows whose Py output rows lie inside [y_begin, y_end)
+        const int cb = (std::max(y_begin, ay.first) - ay.first + ay.P - 1) / ay.P;
+        const int ce = (std::min(y_end, ay.first + ay.P * ay.ncells) - ay.first) / ay.P;
+        if (ce > cb) {
+            const int fy0 = ay.first + ay.P * cb, fy1 = ay.first + ay.P * ce;
+            if (parts & JINC_PART_BORDER) {
+                rects[n_rects++] = Rect{0, y_begin, W, fy0};
+                rects[n_rects++] = Rect{0, fy1, W, y_end};
+                rects[n_rects++] = Rect{0, fy0, t->ix0, fy1};
+                rects[n_rects++] = Rect{t->ix1, fy0, W, fy1};
+            }
+            CellsArgs a;
+            memset(&a, 0, sizeof(a));
+            a.fr = fr;
+            a.st = sa;
+            a.cx_cell = ax.d_cell;
+            a.cx_n = ax.d_n;
+            a.cx_org = ax.d_org;
+            a.cx_rank = ax.d_rank;
+            a.cy_cell = ay.d_cell;
+            a.cy_n = ay.d_n;
+            a.cy_org = ay.d_org;
+            a.cy_rank = ay.d_rank;
+            a.wblocks = t->d_weights_p ? t->d_weights_p : t->d_weights;
+            a.wstride = t->d_weights_p ? ((t->sc.fs + 3) & ~3) : t->sc.fs;
+            a.Px = ax.P;
+            a.Py = ay.P;
+            a.x0 = ax.first;
+            a.y0 = ay.first;
+            a.n_rank_x = t->ax[0].n_rank;
+            a.n_cx = ax.n_chunks;
+            // y-chunks holding cell rows of [cb, ce): chunk k covers cells [cell[k], cell[k] + n[k])
+            int k0 = 0, k1 = ay.n_chunks;
+            while (k0 < k1 && ay.cell[k0] + ay.n[k0] <= cb)
+                ++k0;
+            while (k1 > k0 && ay.cell[k1 - 1] >= ce)
+                --k1;
+            a.cyk_begin = k0;
+            a.cyk_end = k1;
+            a.cell_y_begin = cb;
+            a.cell_y_end = ce;
+            a.src_w = t->sc.src_w;
+            a.src_h = t->sc.src_h;
+            a.interior_blocks = (parts & JINC_PART_INTERIOR) ? 1 : 0; // resolved to the tile count by the launcher
+            const int rc = launch_cells<T>(t, a, n_frames, st, rects, n_rects);
+            if (rc != 1) {
+                if (rc == 0)
+                    ++*launches;
+                return rc == 2 ? JINC_OK : rc;
+            }
+            n_rects = 0;
+        }
+    }
     if (t->fast_path == JINC_PATH_PERIODIC && periodic_supported(t)) {
         const PeriodicPlan& u = t->periodic;
         // cells whose P output rows lie inside [y_begin, y_end)
@@ -485,6 +516,20 @@ int jinc_launch_resize(jinc_ctx* ctx, const jinc_table* t, int sample_bytes, flo
 {
     return jinc_launch_resize_planes(ctx, t, sample_bytes, peak, 1, &d_src, &src_pitch, &d_dst, &dst_pitch, y_begin, y_end,
                                      stream, launches, JINC_PART_ALL);
+}
+
+// Probe words of a freshly uploaded source buffer, read back so the host can compare them with the caller's memory
+// (stale-registration check of the frame pipeline; no pixel is computed here).
+__global__ void probe_kernel(const uint32_t* __restrict__ buf, uint32_t n_words, uint32_t seed, uint32_t* __restrict__ out)
+{
+    out[threadIdx.x] = buf[jinc_probe_index(seed, threadIdx.x, n_words)];
+}
+
+int jinc_launch_probe(const void* d_buf, uint32_t n_words, uint32_t seed, uint32_t* d_out, cudaStream_t stream)
+{
+    probe_kernel<<<1, JINC_PROBE_WORDS, 0, stream>>>(static_cast<const uint32_t*>(d_buf), n_words, seed, d_out);
+    JINC_CUDA(cudaGetLastError());
+    return JINC_OK;
 }
 
 int jinc_debug_pixel_weights(const jinc_table* t, int x, int y, float* out)

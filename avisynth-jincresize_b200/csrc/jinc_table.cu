@@ -285,7 +285,8 @@ void derive_scalars(const jinc_table_params& p, TableScalars& s)
     s.idx_scale = (JINC_LUT_SAMPLES - 1) / s.radius2;
 }
 
-// Longest run [a,b) of non-border indices.
+// The run [a,b) of non-border indices.  Border flags are monotone along an axis (windows are clamped only at the two ends:
+// src/JincResize.cpp:395-418), so the first run found is the only one.
 void interior_run(const std::vector<uint8_t>& border, int& a, int& b)
 {
     const int n = static_cast<int>(border.size());
@@ -341,6 +342,96 @@ bool axis_periodic(const std::vector<int32_t>& start, const std::vector<int32_t>
             return true;
     }
     return false;
+}
+
+// Piecewise-periodic structure of one axis over the interior run [a,b): the smallest P (cell = P outputs) for which
+// start[i+P] - start[i] is one constant Q almost everywhere, then chunks of up to N cells inside which every residue
+// keeps its rank and its origins advance by exactly Q per cell.  False when the axis has no such structure or the
+// chunks come out too short to be worth a thread each.
+bool build_cells_axis(const std::vector<int32_t>& start, const std::vector<int32_t>& rank, int a, int b, int N, CellsAxis& out)
+{
+    for (int P = 1; P <= 8; ++P) {
+        const int n = b - a - P;
+        if (n < 8 * P)
+            continue;
+        std::unordered_map<int, int> hist;
+        for (int i = a; i + P < b; ++i)
+            ++hist[start[i + P] - start[i]];
+        int Q = 0, best = 0;
+        for (auto& kv : hist)
+            if (kv.second > best) {
+                best = kv.second;
+                Q = kv.first;
+            }
+        if (Q < 1 || best < n - n / 50)
+            continue;
+        out = CellsAxis();
+        out.P = P;
+        out.Q = Q;
+        out.first = a;
+        out.ncells = (b - a) / P;
+        int c = 0;
+        while (c < out.ncells) {
+            int len = 1;
+            while (len < N && c + len < out.ncells) {
+                bool same = true;
+                for (int p = 0; p < P && same; ++p) {
+                    const int i0 = a + P * (c + len - 1) + p, i1 = i0 + P;
+                    same = rank[i1] == rank[i0] && start[i1] == start[i0] + Q;
+                }
+                if (!same)
+                    break;
+                ++len;
+            }
+            out.cell.push_back(c);
+            out.n.push_back(len);
+            for (int p = 0; p < P; ++p) {
+                out.org.push_back(start[a + P * c + p]);
+                out.rank.push_back(rank[a + P * c + p]);
+            }
+            c += len;
+        }
+        out.n_chunks = static_cast<int>(out.cell.size());
+        return out.ncells >= 8 && static_cast<long long>(out.n_chunks) * N * 3 <= static_cast<long long>(out.ncells) * 4 + 8 * N;
+    }
+    return false;
+}
+
+// every window of `per_tile` consecutive chunks (tiles start anywhere on the y axis: row bands) must fit the footprint the
+// kernel stages: from the smallest origin of the first chunk to the end of the last chunk's last window
+bool cells_footprints_fit(const CellsAxis& ax, int fs, int per_tile, int limit, bool any_start)
+{
+    for (int k0 = 0; k0 < ax.n_chunks; k0 += any_start ? 1 : per_tile) {
+        const int k1 = std::min(ax.n_chunks, k0 + per_tile);
+        int lo = INT_MAX, hi = INT_MIN;
+        for (int p = 0; p < ax.P; ++p)
+            lo = std::min(lo, ax.org[(size_t)k0 * ax.P + p]);
+        for (int k = k0; k < k1; ++k)
+            for (int p = 0; p < ax.P; ++p) {
+                const int o = ax.org[(size_t)k * ax.P + p];
+                if (o < lo)
+                    return false; // origins must not run backwards inside a tile
+                hi = std::max(hi, o + ax.Q * (ax.n[k] - 1) + fs);
+            }
+        if (hi - lo > limit)
+            return false;
+    }
+    return true;
+}
+
+int upload_cells_axis(CellsAxis& ax, cudaStream_t st)
+{
+    int rc = dev_alloc(&ax.d_cell, ax.cell.size());
+    rc = rc ? rc : dev_alloc(&ax.d_n, ax.n.size());
+    rc = rc ? rc : dev_alloc(&ax.d_org, ax.org.size());
+    rc = rc ? rc : dev_alloc(&ax.d_rank, ax.rank.size());
+    if (rc)
+        return rc;
+    JINC_CUDA(cudaMemcpyAsync(ax.d_cell, ax.cell.data(), ax.cell.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    JINC_CUDA(cudaMemcpyAsync(ax.d_n, ax.n.data(), ax.n.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    JINC_CUDA(cudaMemcpyAsync(ax.d_org, ax.org.data(), ax.org.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    JINC_CUDA(cudaMemcpyAsync(ax.d_rank, ax.rank.data(), ax.rank.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    return JINC_OK;
 }
 
 void plan_fast_paths(jinc_table* t)
@@ -401,6 +492,26 @@ void plan_fast_paths(jinc_table* t)
             t->iy1 = d.y0 + d.ny;
         }
         return; // an integer ratio also looks periodic (P = 2, Q = 2q): it is the polyphase kernel's own case
+    }
+    // rational ratios with piecewise-periodic phases (exactly periodic ones included): chunked cells
+    {
+        CellsPlan& u = t->cells;
+        const int fs = t->sc.fs;
+        if (build_cells_axis(t->h_start[0], t->h_rank[0], ax_a[0], ax_b[0], JINC_CELLS_NX, u.ax[0]) &&
+            build_cells_axis(t->h_start[1], t->h_rank[1], ax_a[1], ax_b[1], JINC_CELLS_NY, u.ax[1]) && u.ax[0].Q == u.ax[1].Q &&
+            jinc_cells_instantiated(u.ax[0].Q, fs) &&
+            cells_footprints_fit(u.ax[0], fs, 32, jinc_cells_footprint(u.ax[0].Q, fs, JINC_CELLS_NX, 32), false) &&
+            cells_footprints_fit(u.ax[1], fs, jinc_cells_warps(u.ax[1].Q),
+                                 jinc_cells_footprint(u.ax[1].Q, fs, JINC_CELLS_NY, jinc_cells_warps(u.ax[1].Q)), true)) {
+            u.Q = u.ax[0].Q;
+            u.ok = true;
+            t->fast_path = JINC_PATH_CELLS;
+            t->ix0 = u.ax[0].first;
+            t->ix1 = u.ax[0].first + u.ax[0].P * u.ax[0].ncells;
+            t->iy0 = u.ax[1].first;
+            t->iy1 = u.ax[1].first + u.ax[1].P * u.ax[1].ncells;
+            return;
+        }
     }
     int Px = 0, Qx = 0, Py = 0, Qy = 0;
     if (axis_periodic(t->h_start[0], t->h_rank[0], ax_a[0], ax_b[0], Px, Qx) &&
@@ -615,6 +726,12 @@ int jinc_table_build_device(jinc_table* t, const double* lut)
         }
     }
     plan_fast_paths(t);
+    if (t->cells.ok) {
+        if (int rc = upload_cells_axis(t->cells.ax[0], st))
+            return rc;
+        if (int rc = upload_cells_axis(t->cells.ax[1], st))
+            return rc;
+    }
     // the fast paths take their (few) phase blocks as kernel parameters: keep a host copy of those
     if (n_blocks > 0 && n_blocks <= 16) {
         t->h_weights.resize(n_blocks * taps);
@@ -696,6 +813,12 @@ extern "C" void jinc_table_destroy(jinc_table* t)
         cudaFree(a.rep);
         cudaFree(a.rank_of);
         cudaFree(a.rep_d2);
+    }
+    for (CellsAxis& c : t->cells.ax) {
+        cudaFree(c.d_cell);
+        cudaFree(c.d_n);
+        cudaFree(c.d_org);
+        cudaFree(c.d_rank);
     }
     cudaFree(t->d_lut);
     cudaFree(t->d_weights);

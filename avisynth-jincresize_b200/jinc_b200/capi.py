@@ -43,7 +43,7 @@ class FilterParams(C.Structure):
                 ("sample_bytes", C.c_int32), ("bits", C.c_int32), ("n_devices", C.c_int32),
                 ("devices", C.c_int32 * MAX_DEVICES), ("slots_per_device", C.c_int32), ("flags", C.c_int32)]
 
-FLAG_NO_HOST_REGISTER = 1
+FLAG_HOST_REGISTER = 1
 FLAG_DST_PADDING_WRITABLE = 2
 E_BUSY = -5
 

@@ -283,10 +283,10 @@ AVS_Value AVSC_CC create_jincresize(AVS_ScriptEnvironment* env, AVS_Value args, 
     if (const char* slots = getenv("JINCRESIZE_B200_SLOTS"))
         p.slots_per_device = atoi(slots);
     // AviSynth+ frame buffers: the padding inside a plane's pitch belongs to the frame; recycled buffers may be page-locked
-    p.flags = JINC_FILTER_DST_PADDING_WRITABLE;
+    p.flags = JINC_FILTER_DST_PADDING_WRITABLE | JINC_FILTER_HOST_REGISTER;
     if (const char* hr = getenv("JINCRESIZE_B200_HOSTREG"))
         if (*hr == '0')
-            p.flags |= JINC_FILTER_NO_HOST_REGISTER;
+            p.flags &= ~JINC_FILTER_HOST_REGISTER;
 
     const bool subsampled_family = avs_is_420(vi) || avs_is_422(vi) || avs_is_yv411(vi);
 

@@ -80,7 +80,9 @@ enum {
     JINC_PATH_GENERAL = 0,   /* one thread per output sample, weights gathered per sample */
     JINC_PATH_UP2X = 1,      /* exact 2x upscale: 2x2 phase classes, register-tiled FFMA2 kernel */
     JINC_PATH_DOWN_INT = 2,  /* integer-ratio downscale: one phase, polyphase register-tiled kernel */
-    JINC_PATH_PERIODIC = 3   /* exactly periodic rational ratio (2:3, e.g. 1080p -> 720p): P x P passes of the polyphase kernel */
+    JINC_PATH_PERIODIC = 3,  /* exactly periodic rational ratio (2:3, e.g. 1080p -> 720p): P x P passes of the polyphase kernel */
+    JINC_PATH_CELLS = 4      /* rational ratio P:Q with piecewise-periodic phases (3:2 = 720p -> 1080p, 4:3, 3x, 4x): one
+                                thread per chunk of cells, one weight block per residue pair held in registers */
 };
 
 typedef struct jinc_table_info {
@@ -154,12 +156,16 @@ typedef struct jinc_filter_params {
 
 /* jinc_filter_params.flags */
 enum {
-    /* Never page-lock the caller's frame buffers.  By default a pageable buffer that comes back (hosts recycle their
-     * frame buffers) is registered with cudaHostRegister and from then on moved by DMA directly, without the staging
-     * copy.  A host that FREES a buffer while it is registered leaves a stale registration behind; arrival of every
-     * directly written destination frame is verified and the registration dropped on a miss, but a host that wants no
-     * part of this sets the flag (the plugin: JINCRESIZE_B200_HOSTREG=0). */
-    JINC_FILTER_NO_HOST_REGISTER = 1,
+    /* Page-lock the caller's frame buffers.  A pageable buffer is staged through the pipeline's pinned mirror when it
+     * is first seen; with this flag a buffer that comes back (hosts recycle their frame buffers) is registered with
+     * cudaHostRegister and from then on moved by DMA directly.  The caller promises that such buffers are recycled, not
+     * freed, while filters with this flag exist: a stale registration sends DMA to the buffer's former pages and makes
+     * unrelated CUDA calls on the re-used address range fail.  The pipeline checks every transfer through its own
+     * registrations (arrival sentinels in destination planes, probe words read back from source planes), drops a
+     * registration that fails and redoes that frame through the staged path; registrations idle for two seconds are
+     * dropped, and all of them when the last such filter is destroyed.  Memory the caller allocated page-locked is
+     * always used directly, flag or not.  The plugin sets the flag unless JINCRESIZE_B200_HOSTREG=0. */
+    JINC_FILTER_HOST_REGISTER = 1,
     /* The padding bytes inside the destination planes' pitch belong to the frame (true for AviSynth+ frame buffers):
      * a destination frame whose planes are packed like the pipeline's own may then move with ONE device-to-host
      * transfer that also covers the padding. */

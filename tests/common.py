@@ -112,6 +112,9 @@ FULL_CASES = [
     ("config3", ah.YUV444P16, 1920, 1080, 3840, 2160, dict(tap=4, src_left=10.3, src_top=6.7, quant_x=256, quant_y=256)),
     ("config4", ah.RGBPS, 3840, 2160, 7680, 4320, dict(tap=8)),
     ("config5", ah.YUV420P10, 7680, 4320, 1920, 1080, dict(tap=6, blur=0.9)),
+    # the rational ratios of bench.py's workloads 6 and 9 at full size: the phase of a residue steps every few dozen cells
+    ("720p_to_1080p", ah.YUV420P8, 1280, 720, 1920, 1080, dict(tap=3)),
+    ("1080p_to_1440p_tap4", ah.Format("444", 10), 1920, 1080, 2560, 1440, dict(tap=4)),
 ]
 
 

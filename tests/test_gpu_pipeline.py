@@ -266,12 +266,12 @@ def _frame_buffer(shapes_bytes):
 
 def test_recycled_pageable_buffers_get_registered(capi):
     """A pageable frame buffer that comes back is page-locked by the pipeline and from then on moved without the staging
-    copy (packed AviSynth-style buffers: one transfer per frame and direction); results do not change.  With
-    JINC_FILTER_NO_HOST_REGISTER every frame stays staged."""
+    copy (packed AviSynth-style buffers: one transfer per frame and direction); results do not change.  Without
+    JINC_FILTER_HOST_REGISTER every frame stays staged."""
     _, fmt, w, h, tw, th, kw = CASES["c2_420p8_2x_tap3_mpeg2"]
     planes = make_planes(fmt, w, h, "noise", seed=21)
     ref, _ = oracle_frame(fmt, w, h, tw, th, planes, **kw)
-    for flags, expect_direct in ((capi.FLAG_DST_PADDING_WRITABLE, True), (capi.FLAG_NO_HOST_REGISTER, False)):
+    for flags, expect_direct in ((capi.FLAG_DST_PADDING_WRITABLE | capi.FLAG_HOST_REGISTER, True), (0, False)):
         flt = make_filter(fmt, w, h, tw, th, flags=flags, **kw)
         shapes = flt.plane_shapes()
         sraw, sviews = _frame_buffer([(s[0], s[1]) for s, _ in shapes])
@@ -297,60 +297,82 @@ def test_recycled_pageable_buffers_get_registered(capi):
         del sraw, draw
 
 
-def test_stale_registration_is_detected(capi):
-    """The host frees a registered destination buffer and maps fresh memory at the same address (what a frame cache
-    does under memory pressure).  The stale registration would send the transfer to the old physical pages; the arrival
-    check notices, the registration is dropped, and the frame is delivered through the staged path."""
-    import mmap
+class _Mapping:
+    """A frame buffer in its own anonymous mapping that can be torn down and re-created AT THE SAME ADDRESS with fresh
+    pages -- what a host's frame cache does when it frees a buffer and the next allocation lands where it was."""
 
-    libc = C.CDLL(None, use_errno=True)
-    libc.mmap.restype = C.c_void_p
-    libc.mmap.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_long]
-    libc.munmap.argtypes = [C.c_void_p, C.c_size_t]
-    MAP_FIXED = 0x10
+    def __init__(self, sizes):
+        import mmap
 
-    _, fmt, w, h, tw, th, kw = CASES["c1_yv12_2x_tap3"]
-    planes = make_planes(fmt, w, h, "noise", seed=33)
-    ref, _ = oracle_frame(fmt, w, h, tw, th, planes, **kw)
-    flt = make_filter(fmt, w, h, tw, th, **kw)
-    shapes = flt.plane_shapes()
-    sizes = [(d[0], d[1]) for _, d in shapes]
-    total = sum(r * ((c + 63) // 64 * 64) for r, c in sizes)
-    length = (total + 2 * mmap.PAGESIZE) // mmap.PAGESIZE * mmap.PAGESIZE
-    prot, flags = mmap.PROT_READ | mmap.PROT_WRITE, mmap.MAP_PRIVATE | mmap.MAP_ANONYMOUS
-    addr = libc.mmap(None, length, prot, flags, -1, 0)
-    assert addr not in (None, C.c_void_p(-1).value)
+        self.libc = C.CDLL(None, use_errno=True)
+        self.libc.mmap.restype = C.c_void_p
+        self.libc.mmap.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_long]
+        self.libc.munmap.argtypes = [C.c_void_p, C.c_size_t]
+        self.sizes = sizes
+        total = sum(r * ((c + 63) // 64 * 64) for r, c in sizes)
+        self.length = (total + 2 * mmap.PAGESIZE) // mmap.PAGESIZE * mmap.PAGESIZE
+        self.prot, self.flags = mmap.PROT_READ | mmap.PROT_WRITE, mmap.MAP_PRIVATE | mmap.MAP_ANONYMOUS
+        self.addr = self.libc.mmap(None, self.length, self.prot, self.flags, -1, 0)
+        assert self.addr not in (None, C.c_void_p(-1).value)
 
-    def views():
+    def views(self, dtype=np.uint8):
         out, off = [], 0
-        for r, c in sizes:
+        for r, c in self.sizes:
             pitch = (c + 63) // 64 * 64
-            buf = (C.c_uint8 * (pitch * r)).from_address(addr + off)
-            out.append(np.frombuffer(buf, np.uint8).reshape(r, pitch)[:, :c])
+            buf = (C.c_uint8 * (pitch * r)).from_address(self.addr + off)
+            out.append(np.frombuffer(buf, np.uint8).reshape(r, pitch)[:, :c].view(dtype))
             off += pitch * r
         return out
 
-    dv = views()
-    for it in range(3):  # staged, registered, direct
-        flt.process(planes, dv)
-        for g, r in zip(dv, ref):
-            assert_plane_close(g, r, False, "stale/before")
+    def remap(self):
+        assert self.libc.munmap(self.addr, self.length) == 0
+        again = self.libc.mmap(self.addr, self.length, self.prot, self.flags | 0x10, -1, 0)  # MAP_FIXED
+        assert again == self.addr
+
+    def close(self):
+        self.libc.munmap(self.addr, self.length)
+
+
+@pytest.mark.parametrize("side", ["dst", "src"])
+def test_stale_registration_is_detected(capi, side):
+    """The host frees a registered frame buffer and fresh memory is mapped at the same address (what a frame cache does
+    under memory pressure).  A transfer through the stale registration reaches the buffer's FORMER physical pages: a
+    destination frame would never arrive, a source frame would be an old one.  The pipeline's checks (arrival
+    sentinels / probe words) notice, the registration is dropped for good, and the frame is redone through the staged
+    path -- the caller gets the right frame every time."""
+    _, fmt, w, h, tw, th, kw = CASES["c1_yv12_2x_tap3"]
+    planes = make_planes(fmt, w, h, "noise", seed=33)
+    ref, _ = oracle_frame(fmt, w, h, tw, th, planes, **kw)
+    flt = make_filter(fmt, w, h, tw, th, flags=capi.FLAG_HOST_REGISTER, **kw)
+    shapes = flt.plane_shapes()
+    m = _Mapping([(d[0], d[1]) for _, d in shapes] if side == "dst" else [(s[0], s[1]) for s, _ in shapes])
+
+    def run(src_planes, want, tag):
+        if side == "dst":
+            dv = m.views()
+            flt.process(src_planes, dv)
+            got = dv
+        else:
+            sv = m.views()
+            for v, p in zip(sv, src_planes):
+                v[:] = p
+            got = flt.process(sv)
+        for i, (g, r) in enumerate(zip(got, want)):
+            assert_plane_close(g, r, False, f"stale/{side}/{tag}/plane{i}")
+
     st0 = capi.host_buffer_stats()
-    assert st0["registered_bytes"] >= total
-    del dv
-    assert libc.munmap(addr, length) == 0
-    again = libc.mmap(addr, length, prot, flags | MAP_FIXED, -1, 0)
-    assert again == addr
-    dv = views()
+    for it in range(3):  # staged, registered, direct
+        run(planes, ref, f"before{it}")
+    st1 = capi.host_buffer_stats()
+    assert st1["registrations"] > st0["registrations"] and st1["registered_bytes"] > 0
+    m.remap()
     planes2 = make_planes(fmt, w, h, "noise", seed=34)
     ref2, _ = oracle_frame(fmt, w, h, tw, th, planes2, **kw)
     for it in range(3):
-        flt.process(planes2, dv)
-        for i, (g, r) in enumerate(zip(dv, ref2)):
-            assert_plane_close(g, r, False, f"stale/after{it}/plane{i}")
+        run(planes2, ref2, f"after{it}")
     flt.close()
-    del dv
-    libc.munmap(addr, length)
+    m.close()
+    assert capi.host_buffer_stats()["registered_bytes"] == 0  # the last registering filter took every registration with it
 
 
 # ------------------------------------------------------------------------------------------ more than one GPU
