@@ -40,28 +40,6 @@ struct CellsGeom {
     static constexpr size_t SMEM = (size_t)FH * ROW * sizeof(float);
 };
 
-struct CellsArgs {
-    FrameSet fr;
-    StripArgs st;
-    const int32_t* cx_cell; // per x-chunk: first cell, cells, then per residue the window origin and phase rank
-    const int32_t* cx_n;
-    const int32_t* cx_org;
-    const int32_t* cx_rank;
-    const int32_t* cy_cell;
-    const int32_t* cy_n;
-    const int32_t* cy_org;
-    const int32_t* cy_rank;
-    const float* wblocks; // phase blocks [block][FS][wstride]
-    int wstride;
-    int Px, Py, x0, y0, n_rank_x;
-    int n_cx;                   // x-chunks
-    int cyk_begin, cyk_end;     // y-chunks of this launch (row band)
-    int cell_y_begin, cell_y_end; // cell rows to produce
-    int src_w, src_h;
-    int tiles_x, tiles_per_plane, interior_blocks, strip_blocks, strip_shift;
-    unsigned tiles_x_magic, tiles_per_plane_magic;
-};
-
 constexpr int CL_STRIP_SPT = 4;
 constexpr int CL_STRIP_MAX_PW = 64;
 
@@ -253,22 +231,31 @@ int launch_cells_cfg(const jinc_table* t, CellsArgs& a, int n_frames, cudaStream
     return JINC_OK;
 }
 
+// One source step Q per translation unit (jinc_cells_<type>_q<Q>.cu), so the unrolled kernels build in parallel.
 // 0 launched, 2 nothing to do, 1 unsupported geometry, <0 error
-template <typename T>
-int launch_cells(const jinc_table* t, CellsArgs& a, int n_frames, cudaStream_t st, const Rect* rects, int n_rects)
+template <typename T, int Q>
+int launch_cells_q(const jinc_table* t, CellsArgs& a, int n_frames, cudaStream_t st, const Rect* rects, int n_rects)
 {
-    switch (t->cells.Q * 100 + t->sc.fs) {
-#define JINC_CELLS_CASE(Q_, FS_) \
-    case Q_ * 100 + FS_: return launch_cells_cfg<T, FS_, Q_>(t, a, n_frames, st, rects, n_rects);
-        JINC_CELLS_CASE(1, 7) // tap 3: 3x, 4x, 5x ..., and shifts at 1:1
-        JINC_CELLS_CASE(1, 9) // tap 4
-        JINC_CELLS_CASE(2, 7) // tap 3: 3:2 (720p -> 1080p, 1440p -> 2160p), 5:2
-        JINC_CELLS_CASE(2, 9) // tap 4
-        JINC_CELLS_CASE(3, 7) // tap 3: 4:3 (1080p -> 1440p), 5:3
-        JINC_CELLS_CASE(3, 9) // tap 4
-#undef JINC_CELLS_CASE
-    default: return 1;
+    switch (t->sc.fs) {
+    case 5: // tap 2
+        if constexpr (jinc_cells_instantiated(Q, 5))
+            return launch_cells_cfg<T, 5, Q>(t, a, n_frames, st, rects, n_rects);
+        break;
+    case 7: // tap 3 at upscale ratios
+        if constexpr (jinc_cells_instantiated(Q, 7))
+            return launch_cells_cfg<T, 7, Q>(t, a, n_frames, st, rects, n_rects);
+        break;
+    case 9: // tap 4 at upscale ratios; tap 3 at 3:4
+        if constexpr (jinc_cells_instantiated(Q, 9))
+            return launch_cells_cfg<T, 9, Q>(t, a, n_frames, st, rects, n_rects);
+        break;
+    case 11: // tap 5
+        if constexpr (jinc_cells_instantiated(Q, 11))
+            return launch_cells_cfg<T, 11, Q>(t, a, n_frames, st, rects, n_rects);
+        break;
+    default: break;
     }
+    return 1;
 }
 
 } // namespace jinc_rs

@@ -1,0 +1,6 @@
+// piecewise-periodic rational-ratio kernels, source step 2 per cell, for uint16_t planes
+#include "jinc_cells.cuh"
+
+namespace jinc_rs {
+template int launch_cells_q<uint16_t, 2>(const jinc_table*, CellsArgs&, int, cudaStream_t, const Rect*, int);
+}

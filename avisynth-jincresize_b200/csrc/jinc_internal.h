@@ -103,7 +103,10 @@ constexpr int jinc_cells_warps(int q) { return q >= 3 ? 4 : 8; } // y-chunks per
 // samples staged along one axis for a tile of `chunks` chunks of n cells: the chunks' cells, the window, and slack for the
 // residues' origin offsets and one irregular origin step
 constexpr int jinc_cells_footprint(int q, int fs, int n, int chunks) { return q * n * chunks + fs + q + 2; }
-constexpr bool jinc_cells_instantiated(int q, int fs) { return q >= 1 && q <= 3 && (fs == 7 || fs == 9); }
+constexpr bool jinc_cells_instantiated(int q, int fs)
+{
+    return (q >= 1 && q <= 4 && (fs == 7 || fs == 9)) || ((q == 1 || q == 2) && (fs == 5 || fs == 11));
+}
 
 struct CellsAxis {
     int P = 0, Q = 0;

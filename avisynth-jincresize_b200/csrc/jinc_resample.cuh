@@ -924,6 +924,48 @@ template <typename T>
 int launch_down(const jinc_table* t, DownArgs& a, int q, const int* wblocks, bool want_strips, int n_frames, cudaStream_t st,
                 const Rect* rects, int n_rects);
 
+// ------------------------------------------------------------------------------------------ chunked-cells kernel (jinc_cells.cuh)
+
+struct CellsArgs {
+    FrameSet fr;
+    StripArgs st;
+    const int32_t* cx_cell; // per x-chunk: first cell, cells, then per residue the window origin and phase rank
+    const int32_t* cx_n;
+    const int32_t* cx_org;
+    const int32_t* cx_rank;
+    const int32_t* cy_cell;
+    const int32_t* cy_n;
+    const int32_t* cy_org;
+    const int32_t* cy_rank;
+    const float* wblocks; // phase blocks [block][FS][wstride]
+    int wstride;
+    int Px, Py, x0, y0, n_rank_x;
+    int n_cx;                   // x-chunks
+    int cyk_begin, cyk_end;     // y-chunks of this launch (row band)
+    int cell_y_begin, cell_y_end; // cell rows to produce
+    int src_w, src_h;
+    int tiles_x, tiles_per_plane, interior_blocks, strip_blocks, strip_shift;
+    unsigned tiles_x_magic, tiles_per_plane_magic;
+};
+
+// defined in jinc_cells.cuh, instantiated in jinc_cells_<type>_q<Q>.cu (one source step Q per translation unit)
+template <typename T, int Q>
+int launch_cells_q(const jinc_table* t, CellsArgs& a, int n_frames, cudaStream_t st, const Rect* rects, int n_rects);
+
+// Q = 1: 3x, 4x, 5x ... and shifts at 1:1;  Q = 2: 3:2 (720p -> 1080p, 1440p -> 2160p), 5:2, 9:2;  Q = 3: 4:3 (1080p -> 1440p),
+// 5:3;  Q = 4: 5:4, 9:4 (480p -> 1080p), and the 3:4 downscale (1440p -> 1080p)
+template <typename T>
+int launch_cells(const jinc_table* t, CellsArgs& a, int n_frames, cudaStream_t st, const Rect* rects, int n_rects)
+{
+    switch (t->cells.Q) {
+    case 1: return launch_cells_q<T, 1>(t, a, n_frames, st, rects, n_rects);
+    case 2: return launch_cells_q<T, 2>(t, a, n_frames, st, rects, n_rects);
+    case 3: return launch_cells_q<T, 3>(t, a, n_frames, st, rects, n_rects);
+    case 4: return launch_cells_q<T, 4>(t, a, n_frames, st, rects, n_rects);
+    default: return 1;
+    }
+}
+
 inline bool periodic_supported(const jinc_table* t)
 {
     const PeriodicPlan& u = t->periodic;

@@ -5,7 +5,7 @@
 // are described once, in jinc_resample.cuh; the kernel families live in jinc_up2x.cuh (exact 2x), jinc_down.cuh
 // (integer-ratio downscale and the exactly periodic 2:3 path) and jinc_cells.cuh (rational ratios with piecewise-periodic
 // phases), each instantiated once per sample type in its own translation unit so that the build runs in parallel.
-#include "jinc_cells.cuh"
+#include "jinc_resample.cuh"
 
 using namespace jinc_rs;
 
@@ -25,14 +25,17 @@ constexpr size_t GEN_SMEM = (size_t)96 << 10; // staging space (two blocks per S
 // owns 4 outputs of one row and applies each float4 of weights to the same output of all NP planes (and the 4 outputs
 // run interleaved), which divides the weight traffic per sample by NP.  Falls back to the per-plane strip role when
 // the NP source footprints do not fit in shared memory or a sample has no vector-readable block.
-template <typename T, int NP>
+// FSC > 0 fixes the window size at compile time (taps 3 and 4 at upscale ratios): the weight row of an output is then
+// read with back-to-back vector loads -- both halves of every 32-byte sector are consumed at once instead of coming back
+// from L2 a second time after the other streams of the block have pushed it out of L1 -- and the tap loops unroll.
+template <typename T, int NP, int FSC>
 __global__ void __launch_bounds__(STRIP_THREADS) resample_strips(const __grid_constant__ GeneralArgs ga)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* __restrict__ tile = reinterpret_cast<float*>(smem_raw);
     const StripArgs& a = ga.st;
     constexpr int SPT = GEN_SPT, THREADS = STRIP_THREADS;
-    const int fs = a.fs;
+    const int fs = FSC > 0 ? FSC : a.fs;
     const unsigned pid = blockIdx.x;
     const unsigned pyi = div_by(pid, a.patches_x_magic[0]), pxi = pid - pyi * a.patches_x[0];
     const int pwl = a.pw_log2[0];
@@ -110,34 +113,67 @@ __global__ void __launch_bounds__(STRIP_THREADS) resample_strips(const __grid_co
             acc[k][pl] = 0.f;
     }
     const int wq = meta[0].wstride / 4; // the same for every block of the table
-    for (int ly = 0; ly < fs; ++ly) {
-        for (int q = 0; q < wq; ++q) {
-            float4 t[SPT];
-#pragma unroll
-            for (int k = 0; k < SPT; ++k)
-                t[k] = __ldg(w4[k] + q);
-            const int lx = 4 * q;
+    if constexpr (FSC > 0) {
+        constexpr int WQ = (FSC + 3) / 4;
+#pragma unroll 1
+        for (int ly = 0; ly < FSC; ++ly) {
 #pragma unroll
             for (int k = 0; k < SPT; ++k) {
+                float4 t[WQ]; // the whole weight row of output k: consecutive vector loads
 #pragma unroll
-                for (int pl = 0; pl < NP; ++pl) {
-                    const float* __restrict__ s = sp[k] + pl * n + lx;
-                    float v = acc[k][pl];
-                    v = fmaf(s[0], t[k].x, v);
-                    if (lx + 1 < fs)
-                        v = fmaf(s[1], t[k].y, v);
-                    if (lx + 2 < fs)
-                        v = fmaf(s[2], t[k].z, v);
-                    if (lx + 3 < fs)
-                        v = fmaf(s[3], t[k].w, v);
-                    acc[k][pl] = v;
+                for (int q = 0; q < WQ; ++q)
+                    t[q] = __ldg(w4[k] + q);
+#pragma unroll
+                for (int q = 0; q < WQ; ++q) {
+                    const int lx = 4 * q;
+#pragma unroll
+                    for (int pl = 0; pl < NP; ++pl) {
+                        const float* __restrict__ s = sp[k] + pl * n + lx;
+                        float v = acc[k][pl];
+                        v = fmaf(s[0], t[q].x, v);
+                        if (lx + 1 < FSC)
+                            v = fmaf(s[1], t[q].y, v);
+                        if (lx + 2 < FSC)
+                            v = fmaf(s[2], t[q].z, v);
+                        if (lx + 3 < FSC)
+                            v = fmaf(s[3], t[q].w, v);
+                        acc[k][pl] = v;
+                    }
                 }
+                w4[k] += WQ;
+                sp[k] += fw;
             }
         }
+    } else {
+        for (int ly = 0; ly < fs; ++ly) {
+            for (int q = 0; q < wq; ++q) {
+                float4 t[SPT];
 #pragma unroll
-        for (int k = 0; k < SPT; ++k) {
-            w4[k] += wq;
-            sp[k] += fw;
+                for (int k = 0; k < SPT; ++k)
+                    t[k] = __ldg(w4[k] + q);
+                const int lx = 4 * q;
+#pragma unroll
+                for (int k = 0; k < SPT; ++k) {
+#pragma unroll
+                    for (int pl = 0; pl < NP; ++pl) {
+                        const float* __restrict__ s = sp[k] + pl * n + lx;
+                        float v = acc[k][pl];
+                        v = fmaf(s[0], t[k].x, v);
+                        if (lx + 1 < fs)
+                            v = fmaf(s[1], t[k].y, v);
+                        if (lx + 2 < fs)
+                            v = fmaf(s[2], t[k].z, v);
+                        if (lx + 3 < fs)
+                            v = fmaf(s[3], t[k].w, v);
+                        acc[k][pl] = v;
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < SPT; ++k) {
+                w4[k] += wq;
+                sp[k] += fw;
+            }
         }
     }
 #pragma unroll
@@ -151,14 +187,25 @@ __global__ void __launch_bounds__(STRIP_THREADS) resample_strips(const __grid_co
     }
 }
 
+template <typename T, int NP, int FSC>
+cudaError_t launch_general_fs(const GeneralArgs& ga, unsigned blocks, int n_frames, cudaStream_t st)
+{
+    cudaError_t e = cudaFuncSetAttribute(resample_strips<T, NP, FSC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEN_SMEM);
+    if (e != cudaSuccess)
+        return e;
+    resample_strips<T, NP, FSC><<<dim3(blocks, n_frames), STRIP_THREADS, GEN_SMEM, st>>>(ga);
+    return cudaGetLastError();
+}
+
 template <typename T, int NP>
 cudaError_t launch_general_np(const GeneralArgs& ga, unsigned blocks, int n_frames, cudaStream_t st)
 {
-    cudaError_t e = cudaFuncSetAttribute(resample_strips<T, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEN_SMEM);
-    if (e != cudaSuccess)
-        return e;
-    resample_strips<T, NP><<<dim3(blocks, n_frames), STRIP_THREADS, GEN_SMEM, st>>>(ga);
-    return cudaGetLastError();
+    // the unrolled variants need the padded weight rows (16-byte vectors) the table build provides for these sizes
+    if (ga.st.weights_p && ga.st.fs == 7)
+        return launch_general_fs<T, NP, 7>(ga, blocks, n_frames, st);
+    if (ga.st.weights_p && ga.st.fs == 9)
+        return launch_general_fs<T, NP, 9>(ga, blocks, n_frames, st);
+    return launch_general_fs<T, NP, 0>(ga, blocks, n_frames, st);
 }
 
 // weights of one output pixel exactly as the reference defines them (introspection for parity tests)
