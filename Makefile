@@ -6,6 +6,8 @@
 #                                                     /root/reference is mounted; never copied into the repo)
 #   avisynth-jincresize_b200/libjinc_b200.so          sm_100a kernels + the C ABI of include/jinc_b200.h
 #   avisynth-jincresize_b200/libjincresize_b200.so    the AviSynth+ C plugin (drop-in for the reference .so)
+#   avisynth-jincresize_b200/libvsjincresize_b200.so  the VapourSynth (API 4) front-end over the same C ABI
+#   minihost/libvs_minihost.so                        VapourSynth core stand-in (tests)
 #   avisynth-jincresize_b200/fma_peak                 FP32-FMA-pipe microbenchmark (roofline denominator)
 
 CXX       ?= g++
@@ -16,6 +18,8 @@ REF       ?= /root/reference/src
 
 PKG   := avisynth-jincresize_b200
 HOSTI := -Iminihost/include -Iminihost
+# VapourSynth headers: the clean-room restatement by default; point VSINC at a real SDK for a production build
+VSINC ?= minihost/include
 CXXFLAGS_COMMON := -std=c++17 -fPIC -fvisibility=hidden -Wall -Wno-unused-function
 
 ARCH  := -gencode arch=compute_100a,code=sm_100a
@@ -28,8 +32,8 @@ CUDA_OBJS := $(CUDA_SRCS:.cu=.o) $(CUDA_HOST_SRCS:.cpp=.o)
 
 .PHONY: all host cuda ref clean
 all: host cuda ref
-host: minihost/libavs_minihost.so oracle/libjinc_oracle.so
-cuda: $(PKG)/libjinc_b200.so $(PKG)/libjincresize_b200.so $(PKG)/fma_peak
+host: minihost/libavs_minihost.so minihost/libvs_minihost.so oracle/libjinc_oracle.so
+cuda: $(PKG)/libjinc_b200.so $(PKG)/libjincresize_b200.so $(PKG)/libvsjincresize_b200.so $(PKG)/fma_peak
 
 ifneq ($(wildcard $(REF)/JincResize.cpp),)
 ref: oracle/_ref/libjincresize_ref.so
@@ -40,6 +44,9 @@ endif
 
 minihost/libavs_minihost.so: minihost/minihost.cpp minihost/minihost.h minihost/include/avisynth_c.h
 	$(CXX) $(CXXFLAGS_COMMON) -O2 $(HOSTI) -shared -o $@ minihost/minihost.cpp -ldl -lpthread
+
+minihost/libvs_minihost.so: minihost/vs_minihost.cpp minihost/include/VapourSynth4.h
+	$(CXX) $(CXXFLAGS_COMMON) -O2 -Iminihost/include -shared -o $@ minihost/vs_minihost.cpp -ldl -lpthread
 
 oracle/libjinc_oracle.so: oracle/jinc_oracle.c oracle/jinc_oracle.h
 	$(CC) -std=c11 -O2 -fPIC -Wall -Werror=implicit-function-declaration -ffp-contract=off -shared -o $@ oracle/jinc_oracle.c -lm
@@ -69,6 +76,10 @@ $(PKG)/libjinc_b200.so: $(CUDA_OBJS)
 
 $(PKG)/libjincresize_b200.so: $(PKG)/plugin/jincresize_plugin.cpp include/jinc_b200.h minihost/include/avisynth_c.h $(PKG)/libjinc_b200.so
 	$(CXX) $(CXXFLAGS_COMMON) -O2 $(HOSTI) -Iinclude -shared -o $@ $(PKG)/plugin/jincresize_plugin.cpp \
+	    -L$(PKG) -ljinc_b200 -Wl,-rpath,'$$ORIGIN' -lpthread
+
+$(PKG)/libvsjincresize_b200.so: $(PKG)/vapoursynth/vsjincresize_plugin.cpp include/jinc_b200.h $(VSINC)/VapourSynth4.h $(PKG)/libjinc_b200.so
+	$(CXX) $(CXXFLAGS_COMMON) -O2 -I$(VSINC) -Iinclude -shared -o $@ $(PKG)/vapoursynth/vsjincresize_plugin.cpp \
 	    -L$(PKG) -ljinc_b200 -Wl,-rpath,'$$ORIGIN' -lpthread
 
 $(PKG)/fma_peak: $(PKG)/tools/fma_peak.cu

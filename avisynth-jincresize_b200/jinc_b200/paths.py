@@ -15,5 +15,10 @@ def b200_plugin() -> str:
     return os.path.join(PKG_DIR, "libjincresize_b200.so")
 
 
+def vs_plugin() -> str:
+    """the VapourSynth (API 4) plugin"""
+    return os.path.join(PKG_DIR, "libvsjincresize_b200.so")
+
+
 def fma_peak_tool() -> str:
     return os.path.join(PKG_DIR, "fma_peak")
