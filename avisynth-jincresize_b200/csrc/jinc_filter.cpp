@@ -96,7 +96,7 @@ struct Sentinel {
     unsigned char* at = nullptr;
     uint64_t value = 0;
 };
-constexpr int kSentinelsPerPlane = 4;
+constexpr int kSentinelsPerPlane = 2;
 
 struct Slot {
     enum State { FREE, BUSY, WAITING };
@@ -114,6 +114,13 @@ struct Slot {
     jinc_hostmem::Pin src_pin, dst_pin;
     Sentinel sentinel[JINC_MAX_PLANES * kSentinelsPerPlane];
     int n_sentinels = 0;
+    // the unlocked head and tail of a registered destination buffer arrive in the pinned mirror and are copied out by the CPU
+    struct Fixup {
+        unsigned char* dst;
+        const unsigned char* src;
+        size_t n;
+    } fixup[2 * JINC_MAX_PLANES + 2];
+    int n_fixups = 0;
     // probe words of the uploaded source, read back when the source moved through a registration made here
     uint32_t* d_probe = nullptr;
     uint32_t* h_probe = nullptr; // pinned
@@ -322,35 +329,102 @@ int enqueue_frame(jinc_filter* f, Slot* s, const jinc_frame* frame, int y0_luma,
         s->src_row1[i] = sy1[i];
     }
 
+    // One contiguous extent between the caller's memory and the device buffer.  Only the page-locked part of the caller's
+    // buffer is addressed by DMA; the (sub-page) head and tail of a buffer registered here go through the slot's pinned
+    // mirror, which has the device buffer's layout.
+    auto h2d = [&](unsigned char* dev, const unsigned char* host, size_t n) -> cudaError_t {
+        size_t a = 0, b = 0;
+        jinc_hostmem::direct_part(s->src_pin, host, n, &a, &b);
+        unsigned char* mir = s->h_src + (dev - s->d_src);
+        cudaError_t e = cudaSuccess;
+        if (b <= a) {
+            memcpy(mir, host, n);
+            return cudaMemcpyAsync(dev, mir, n, cudaMemcpyHostToDevice, s->stream);
+        }
+        if (a > 0) {
+            memcpy(mir, host, a);
+            e = cudaMemcpyAsync(dev, mir, a, cudaMemcpyHostToDevice, s->stream);
+        }
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(dev + a, host + a, b - a, cudaMemcpyHostToDevice, s->stream);
+        if (e == cudaSuccess && b < n) {
+            memcpy(mir + b, host + b, n - b);
+            e = cudaMemcpyAsync(dev + b, mir + b, n - b, cudaMemcpyHostToDevice, s->stream);
+        }
+        return e;
+    };
+    auto d2h = [&](unsigned char* host, const unsigned char* dev, size_t n, bool check_arrival) -> cudaError_t {
+        size_t a = 0, b = 0;
+        jinc_hostmem::direct_part(s->dst_pin, host, n, &a, &b);
+        unsigned char* mir = s->h_dst + (dev - s->d_dst);
+        cudaError_t e = cudaSuccess;
+        if (b <= a) {
+            s->fixup[s->n_fixups++] = Slot::Fixup{host, mir, n};
+            return cudaMemcpyAsync(mir, dev, n, cudaMemcpyDeviceToHost, s->stream);
+        }
+        if (check_arrival && b - a >= 2 * sizeof(uint64_t)) {
+            // arrival check: sentinels at both ends of the directly addressed part must be overwritten by the transfer
+            unsigned char* at[2] = {host + a, host + b - sizeof(uint64_t)};
+            for (unsigned char* q : at) {
+                Sentinel& sn = s->sentinel[s->n_sentinels++];
+                sn.at = q;
+                sn.value = fresh_nonce();
+                memcpy(sn.at, &sn.value, sizeof(sn.value));
+            }
+        }
+        if (a > 0) {
+            s->fixup[s->n_fixups++] = Slot::Fixup{host, mir, a};
+            e = cudaMemcpyAsync(mir, dev, a, cudaMemcpyDeviceToHost, s->stream);
+        }
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(host + a, dev + a, b - a, cudaMemcpyDeviceToHost, s->stream);
+        if (e == cudaSuccess && b < n) {
+            s->fixup[s->n_fixups++] = Slot::Fixup{host + b, mir + b, n - b};
+            e = cudaMemcpyAsync(mir + b, dev + b, n - b, cudaMemcpyDeviceToHost, s->stream);
+        }
+        return e;
+    };
+
     // ---- source planes -> device
     jinc_hostmem::Range rs[JINC_MAX_PLANES];
-    bool src_direct = !staged_only, src_packed = whole;
+    bool src_direct = !staged_only, src_packed = whole, src_same_pitch = true;
     for (int i = 0; i < np; ++i) {
         const PlaneLayout& pl = f->planes[i];
         src_direct = src_direct && plane_range(frame->src[i], frame->src_pitch[i], static_cast<size_t>(pl.src_w) * sb, pl.src_h, &rs[i]);
-        src_packed = src_packed && frame->src_pitch[i] == static_cast<ptrdiff_t>(pl.src_pitch) &&
+        const bool same = frame->src_pitch[i] == static_cast<ptrdiff_t>(pl.src_pitch);
+        src_same_pitch = src_same_pitch && same;
+        src_packed = src_packed && same &&
                      static_cast<const unsigned char*>(frame->src[i]) - static_cast<const unsigned char*>(frame->src[0]) ==
                          static_cast<ptrdiff_t>(pl.src_off);
     }
-    src_direct = src_direct && jinc_hostmem::acquire(rs, np, may_register, &s->src_pin);
+    // memory registered here is moved as whole extents (its unlocked ends are split off), which needs the pipeline's pitch;
+    // memory the caller allocated page-locked may have any pitch (2-D copies)
+    src_direct = src_direct && jinc_hostmem::acquire(rs, np, may_register && src_same_pitch, &s->src_pin);
+    if (src_direct && !src_same_pitch && jinc_hostmem::registered_here(&s->src_pin)) {
+        jinc_hostmem::release(&s->src_pin);
+        src_direct = false;
+    }
     if (src_direct) {
         g_direct_src.fetch_add(1, std::memory_order_relaxed);
         s->probe_active = jinc_hostmem::registered_here(&s->src_pin);
         if (src_packed) {
-            // the caller's planes are packed exactly like the slot (AviSynth+ frame buffers are): one transfer per frame
+            // the caller's planes are packed exactly like the slot (AviSynth+ frame buffers are): one extent per frame
             const PlaneLayout& last = f->planes[np - 1];
             const size_t bytes = last.src_off + last.src_pitch * (last.src_h - 1) + static_cast<size_t>(last.src_w) * sb;
-            JINC_CUDA(cudaMemcpyAsync(s->d_src, frame->src[0], bytes, cudaMemcpyHostToDevice, s->stream));
+            JINC_CUDA(h2d(s->d_src, static_cast<const unsigned char*>(frame->src[0]), bytes));
         } else {
             for (int i = 0; i < np; ++i) {
                 const PlaneLayout& pl = f->planes[i];
                 const int rows = sy1[i] - sy0[i];
                 if (rows <= 0)
                     continue;
-                JINC_CUDA(copy_plane_async(s->d_src + pl.src_off + static_cast<size_t>(sy0[i]) * pl.src_pitch, pl.src_pitch,
-                                           static_cast<const unsigned char*>(frame->src[i]) + static_cast<ptrdiff_t>(sy0[i]) * frame->src_pitch[i],
-                                           static_cast<size_t>(frame->src_pitch[i]), static_cast<size_t>(pl.src_w) * sb, rows, true,
-                                           cudaMemcpyHostToDevice, s->stream));
+                unsigned char* dev = s->d_src + pl.src_off + static_cast<size_t>(sy0[i]) * pl.src_pitch;
+                const unsigned char* host = static_cast<const unsigned char*>(frame->src[i]) + static_cast<ptrdiff_t>(sy0[i]) * frame->src_pitch[i];
+                if (src_same_pitch)
+                    JINC_CUDA(h2d(dev, host, pl.src_pitch * static_cast<size_t>(rows - 1) + static_cast<size_t>(pl.src_w) * sb));
+                else
+                    JINC_CUDA(copy_plane_async(dev, pl.src_pitch, host, static_cast<size_t>(frame->src_pitch[i]), static_cast<size_t>(pl.src_w) * sb,
+                                               rows, false, cudaMemcpyHostToDevice, s->stream));
             }
         }
     } else {
@@ -410,52 +484,46 @@ int enqueue_frame(jinc_filter* f, Slot* s, const jinc_frame* frame, int y0_luma,
 
     // ---- destination planes -> host
     jinc_hostmem::Range rd[JINC_MAX_PLANES];
-    bool dst_direct = !staged_only, dst_packed = whole, dst_tight = true;
+    bool dst_direct = !staged_only, dst_packed = whole, dst_tight = true, dst_same_pitch = true;
     for (int i = 0; i < np; ++i) {
         const PlaneLayout& pl = f->planes[i];
         const size_t row_bytes = static_cast<size_t>(pl.dst_w) * sb;
         dst_direct = dst_direct && plane_range(frame->dst[i], frame->dst_pitch[i], row_bytes, pl.dst_h, &rd[i]);
         dst_tight = dst_tight && frame->dst_pitch[i] == static_cast<ptrdiff_t>(row_bytes);
-        dst_packed = dst_packed && frame->dst_pitch[i] == static_cast<ptrdiff_t>(pl.dst_pitch) &&
+        const bool same = frame->dst_pitch[i] == static_cast<ptrdiff_t>(pl.dst_pitch);
+        dst_same_pitch = dst_same_pitch && same;
+        dst_packed = dst_packed && same &&
                      static_cast<unsigned char*>(frame->dst[i]) - static_cast<unsigned char*>(frame->dst[0]) == static_cast<ptrdiff_t>(pl.dst_off);
     }
-    dst_direct = dst_direct && jinc_hostmem::acquire(rd, np, may_register, &s->dst_pin);
+    // whole extents may be written only where the bytes between rows (and planes) belong to the frame
+    const bool dst_extents = dst_same_pitch && (dst_tight || padding_ok);
+    dst_direct = dst_direct && jinc_hostmem::acquire(rd, np, may_register && dst_extents, &s->dst_pin);
+    const bool dst_ours = dst_direct && jinc_hostmem::registered_here(&s->dst_pin);
+    if (dst_ours && !dst_extents) {
+        jinc_hostmem::release(&s->dst_pin);
+        dst_direct = false;
+    }
     s->dst_direct = dst_direct;
-    const bool carry_padding = dst_tight || padding_ok; // bytes between rows (and planes) may be written
+    s->n_fixups = 0;
     if (dst_direct) {
         g_direct_dst.fetch_add(1, std::memory_order_relaxed);
-        if (jinc_hostmem::registered_here(&s->dst_pin)) {
-            // arrival check: sentinels at the corners of every plane's band must be overwritten by the transfer
-            for (int i = 0; i < np; ++i) {
-                const PlaneLayout& pl = f->planes[i];
-                const size_t row_bytes = static_cast<size_t>(pl.dst_w) * sb;
-                if (oy1[i] <= oy0[i] || row_bytes < sizeof(uint64_t))
-                    continue;
-                const int rows[2] = {oy0[i], oy1[i] - 1};
-                const size_t cols[2] = {0, row_bytes - sizeof(uint64_t)};
-                for (int a = 0; a < 2; ++a)
-                    for (int b = 0; b < 2; ++b) {
-                        Sentinel& q = s->sentinel[s->n_sentinels++];
-                        q.at = static_cast<unsigned char*>(frame->dst[i]) + static_cast<ptrdiff_t>(rows[a]) * frame->dst_pitch[i] + cols[b];
-                        q.value = fresh_nonce();
-                        memcpy(q.at, &q.value, sizeof(q.value));
-                    }
-            }
-        }
-        if (dst_packed && carry_padding) {
+        if (dst_packed && dst_extents) {
             const PlaneLayout& last = f->planes[np - 1];
             const size_t bytes = last.dst_off + last.dst_pitch * (last.dst_h - 1) + static_cast<size_t>(last.dst_w) * sb;
-            JINC_CUDA(cudaMemcpyAsync(frame->dst[0], s->d_dst, bytes, cudaMemcpyDeviceToHost, s->stream));
+            JINC_CUDA(d2h(static_cast<unsigned char*>(frame->dst[0]), s->d_dst, bytes, dst_ours));
         } else {
             for (int i = 0; i < np; ++i) {
                 const PlaneLayout& pl = f->planes[i];
                 const int rows = oy1[i] - oy0[i];
                 if (rows <= 0)
                     continue;
-                JINC_CUDA(copy_plane_async(static_cast<unsigned char*>(frame->dst[i]) + static_cast<ptrdiff_t>(oy0[i]) * frame->dst_pitch[i],
-                                           static_cast<size_t>(frame->dst_pitch[i]), s->d_dst + pl.dst_off + static_cast<size_t>(oy0[i]) * pl.dst_pitch,
-                                           pl.dst_pitch, static_cast<size_t>(pl.dst_w) * sb, rows, carry_padding, cudaMemcpyDeviceToHost,
-                                           s->stream));
+                unsigned char* host = static_cast<unsigned char*>(frame->dst[i]) + static_cast<ptrdiff_t>(oy0[i]) * frame->dst_pitch[i];
+                const unsigned char* dev = s->d_dst + pl.dst_off + static_cast<size_t>(oy0[i]) * pl.dst_pitch;
+                if (dst_extents)
+                    JINC_CUDA(d2h(host, dev, pl.dst_pitch * static_cast<size_t>(rows - 1) + static_cast<size_t>(pl.dst_w) * sb, dst_ours));
+                else
+                    JINC_CUDA(copy_plane_async(host, static_cast<size_t>(frame->dst_pitch[i]), dev, pl.dst_pitch, static_cast<size_t>(pl.dst_w) * sb,
+                                               rows, false, cudaMemcpyDeviceToHost, s->stream));
             }
         }
     } else if (whole) {
@@ -523,8 +591,11 @@ int finish_frame(jinc_filter* f, Slot* s, int y0_luma, int y1_luma, bool whole)
             from_mirror = true;
         }
     }
-    if (!from_mirror)
+    if (!from_mirror) {
+        for (int k = 0; k < s->n_fixups; ++k)
+            memcpy(s->fixup[k].dst, s->fixup[k].src, s->fixup[k].n);
         return JINC_OK;
+    }
     for (int i = 0; i < f->p.n_planes; ++i) {
         const PlaneLayout& pl = f->planes[i];
         const int shift = (pl.table == 1) ? f->p.sub_h : 0;

@@ -9,6 +9,7 @@
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <deque>
@@ -152,8 +153,11 @@ void prune_locked()
 // registers e's range; called WITHOUT g_mu (page-locking a large frame buffer takes milliseconds), e->state is REGISTERING
 bool do_register(Entry* e)
 {
+    // whole pages INSIDE the buffer only: the partial pages at its ends are shared with whatever the host keeps next to it
     const uintptr_t ps = page_size();
-    const uintptr_t lo = e->lo & ~(ps - 1), hi = (e->hi + ps - 1) & ~(ps - 1);
+    const uintptr_t lo = (e->lo + ps - 1) & ~(ps - 1), hi = e->hi & ~(ps - 1);
+    if (hi <= lo || hi - lo < 16 * ps)
+        return false; // not worth a registration
     {
         std::lock_guard<std::mutex> lk(g_mu);
         if (!make_room_locked(hi - lo))
@@ -180,6 +184,9 @@ bool do_register(Entry* e)
     if (err != cudaSuccess) {
         cudaGetLastError();
         g_reg_bytes -= hi - lo;
+        if (getenv("JINCRESIZE_B200_DEBUG"))
+            fprintf(stderr, "jinc_hostmem: cudaHostRegister(%p, %zu) failed: %s\n", reinterpret_cast<void*>(lo), static_cast<size_t>(hi - lo),
+                    cudaGetErrorString(err));
         return false;
     }
     e->reg_lo = lo;
@@ -257,11 +264,32 @@ bool acquire(const Range* ranges, int n, bool may_register, Pin* pin)
         got[g] = e;
     }
     for (int g = 0; g < ng; ++g) {
-        ++got[g]->users;
-        pin->entry[g] = got[g];
+        Entry* e = got[g];
+        ++e->users;
+        pin->entry[g] = e;
+        pin->lo[g] = e->lo;
+        pin->hi[g] = e->hi;
+        pin->dlo[g] = e->state == Entry::REGISTERED ? e->reg_lo : e->lo;
+        pin->dhi[g] = e->state == Entry::REGISTERED ? e->reg_hi : e->hi;
     }
     pin->n = ng;
     return true;
+}
+
+void direct_part(const Pin& pin, const void* p, size_t n, size_t* a, size_t* b)
+{
+    const uintptr_t lo = reinterpret_cast<uintptr_t>(p), hi = lo + n;
+    *a = *b = 0;
+    for (int g = 0; g < pin.n; ++g) {
+        if (lo < pin.lo[g] || hi > pin.hi[g])
+            continue;
+        const uintptr_t x = std::min(std::max(pin.dlo[g], lo), hi), y = std::min(std::max(pin.dhi[g], lo), hi);
+        if (y > x) {
+            *a = x - lo;
+            *b = y - lo;
+        }
+        return;
+    }
 }
 
 void client_add()

@@ -28,11 +28,19 @@ struct Range {
     const unsigned char* hi; // one past the last byte
 };
 
-// Ranges held against eviction between acquire() and release().
+// Ranges held against eviction between acquire() and release(): the buffers (planes closer than 64 KB form one), and of
+// each the part that is page-locked -- all of it for memory the caller allocated page-locked, the pages that lie FULLY
+// INSIDE the buffer for a registration made here (memory next to the caller's buffer is never locked: a CUDA transfer
+// that straddles the edge of a registered range is an error, and those bytes are not ours to lock).
 struct Pin {
     int n = 0;
     void* entry[JINC_MAX_PLANES] = {};
+    uintptr_t lo[JINC_MAX_PLANES] = {}, hi[JINC_MAX_PLANES] = {};   // the buffer
+    uintptr_t dlo[JINC_MAX_PLANES] = {}, dhi[JINC_MAX_PLANES] = {}; // its page-locked part
 };
+
+// The part [*a, *b) (offsets into [0, n)) of host range [p, p + n) that DMA may address directly; *a == *b: none.
+void direct_part(const Pin& pin, const void* p, size_t n, size_t* a, size_t* b);
 
 // True when every range is page-locked (allocated so by the caller, or registered here -- now, if `may_register` and the
 // buffer has been seen before); the ranges are then pinned against eviction until release().  False: stage the frame.

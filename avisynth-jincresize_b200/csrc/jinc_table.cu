@@ -398,8 +398,9 @@ bool build_cells_axis(const std::vector<int32_t>& start, const std::vector<int32
 }
 
 // every window of `per_tile` consecutive chunks (tiles start anywhere on the y axis: row bands) must fit the footprint the
-// kernel stages: from the smallest origin of the first chunk to the end of the last chunk's last window
-bool cells_footprints_fit(const CellsAxis& ax, int fs, int per_tile, int limit, bool any_start)
+// kernel stages: from the smallest origin of the first chunk to the end of the last window a thread READS -- a thread
+// always walks all N cells of its chunk, also the ones a short chunk does not have
+bool cells_footprints_fit(const CellsAxis& ax, int fs, int N, int per_tile, int limit, bool any_start)
 {
     for (int k0 = 0; k0 < ax.n_chunks; k0 += any_start ? 1 : per_tile) {
         const int k1 = std::min(ax.n_chunks, k0 + per_tile);
@@ -411,7 +412,7 @@ bool cells_footprints_fit(const CellsAxis& ax, int fs, int per_tile, int limit, 
                 const int o = ax.org[(size_t)k * ax.P + p];
                 if (o < lo)
                     return false; // origins must not run backwards inside a tile
-                hi = std::max(hi, o + ax.Q * (ax.n[k] - 1) + fs);
+                hi = std::max(hi, o + ax.Q * (N - 1) + fs);
             }
         if (hi - lo > limit)
             return false;
@@ -500,8 +501,8 @@ void plan_fast_paths(jinc_table* t)
         if (build_cells_axis(t->h_start[0], t->h_rank[0], ax_a[0], ax_b[0], JINC_CELLS_NX, u.ax[0]) &&
             build_cells_axis(t->h_start[1], t->h_rank[1], ax_a[1], ax_b[1], JINC_CELLS_NY, u.ax[1]) && u.ax[0].Q == u.ax[1].Q &&
             jinc_cells_instantiated(u.ax[0].Q, fs) &&
-            cells_footprints_fit(u.ax[0], fs, 32, jinc_cells_footprint(u.ax[0].Q, fs, JINC_CELLS_NX, 32), false) &&
-            cells_footprints_fit(u.ax[1], fs, jinc_cells_warps(u.ax[1].Q),
+            cells_footprints_fit(u.ax[0], fs, JINC_CELLS_NX, 32, jinc_cells_footprint(u.ax[0].Q, fs, JINC_CELLS_NX, 32), false) &&
+            cells_footprints_fit(u.ax[1], fs, JINC_CELLS_NY, jinc_cells_warps(u.ax[1].Q),
                                  jinc_cells_footprint(u.ax[1].Q, fs, JINC_CELLS_NY, jinc_cells_warps(u.ax[1].Q)), true)) {
             u.Q = u.ax[0].Q;
             u.ok = true;

@@ -459,9 +459,9 @@ def copy_ceiling(D, host_src, host_dst, dev_src, dev_dst, inflight: int, steps: 
         for f in range(F):
             with torch.cuda.stream(streams[f % inflight]):
                 for h, d in zip(host_src[f], dev_src[f]):
-                    d.copy_(h, non_blocking=True)
+                    d[:, : h.shape[1]].copy_(h, non_blocking=True)
                 for h, d in zip(host_dst[f], dev_dst[f]):
-                    h.copy_(d, non_blocking=True)
+                    h.copy_(d[:, : h.shape[1]], non_blocking=True)
 
     step()
     D.barrier()

@@ -286,6 +286,7 @@ def test_recycled_pageable_buffers_get_registered(capi):
             for i, (g, r) in enumerate(zip(dviews, ref)):
                 assert_plane_close(g, r, False, f"registry/flags{flags}/iter{it}/plane{i}")
         st1 = capi.host_buffer_stats()
+        flt.close()
         direct = st1["direct_dst_frames"] - st0["direct_dst_frames"]
         staged = st1["staged_frames"] - st0["staged_frames"]
         if expect_direct:
@@ -293,7 +294,6 @@ def test_recycled_pageable_buffers_get_registered(capi):
             assert direct == 3 and staged == 1  # first sighting staged, then direct
         else:
             assert st1["registrations"] == st0["registrations"] and direct == 0 and staged == 4
-        flt.close()
         del sraw, draw
 
 
@@ -340,7 +340,7 @@ def test_stale_registration_is_detected(capi, side):
     destination frame would never arrive, a source frame would be an old one.  The pipeline's checks (arrival
     sentinels / probe words) notice, the registration is dropped for good, and the frame is redone through the staged
     path -- the caller gets the right frame every time."""
-    _, fmt, w, h, tw, th, kw = CASES["c1_yv12_2x_tap3"]
+    _, fmt, w, h, tw, th, kw = CASES["c2_420p8_2x_tap3_mpeg2"]
     planes = make_planes(fmt, w, h, "noise", seed=33)
     ref, _ = oracle_frame(fmt, w, h, tw, th, planes, **kw)
     flt = make_filter(fmt, w, h, tw, th, flags=capi.FLAG_HOST_REGISTER, **kw)
