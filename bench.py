@@ -454,14 +454,19 @@ def copy_ceiling(D, host_src, host_dst, dev_src, dev_dst, inflight: int, steps: 
     streams = [torch.cuda.Stream() for _ in range(inflight)]
     F = len(host_src)
     nbytes = sum(t.numel() * t.element_size() for f in range(F) for t in host_src[f] + host_dst[f])
+    # tightly packed device planes, one set per stream: every plane moves as ONE linear transfer (the best a copy can do)
+    tight_src = [[torch.empty_like(h, device="cuda") for h in host_src[0]] for _ in range(inflight)]
+    tight_dst = [[torch.empty_like(h, device="cuda") for h in host_dst[0]] for _ in range(inflight)]
+    del dev_src, dev_dst
 
     def step():
         for f in range(F):
-            with torch.cuda.stream(streams[f % inflight]):
-                for h, d in zip(host_src[f], dev_src[f]):
-                    d[:, : h.shape[1]].copy_(h, non_blocking=True)
-                for h, d in zip(host_dst[f], dev_dst[f]):
-                    h.copy_(d[:, : h.shape[1]], non_blocking=True)
+            k = f % inflight
+            with torch.cuda.stream(streams[k]):
+                for h, d in zip(host_src[f], tight_src[k]):
+                    d.copy_(h, non_blocking=True)
+                for h, d in zip(host_dst[f], tight_dst[k]):
+                    h.copy_(d, non_blocking=True)
 
     step()
     D.barrier()
@@ -493,9 +498,7 @@ def run_plugin_leg(D, cfg, threads: int, steps: int, warm_steps: int):
         f0 += max(F, 3 * threads)
     D.barrier()
     t0 = time.perf_counter()
-    for _ in range(steps):
-        clip.pull(f0, F, threads)
-        f0 += F
+    clip.pull(f0, steps * F, threads)  # the K steps back to back, as a host streams a clip: no barrier between steps
     D.barrier()
     dt = time.perf_counter() - t0
     st1 = capi.host_buffer_stats()
@@ -599,21 +602,20 @@ def measure_config(D, args, cfg, config_id: int, steps: int, warmup: int, full: 
         dst_np = [[t.numpy() for t in hd] for hd in host_dst]
         raw = [flt._frame(s, d) for s, d in zip(src_np, dst_np)]
 
-        def e2e_step():
+        def e2e_steps(k):  # k steps back to back, `inflight` frames in flight throughout
             tickets = []
-            for f in range(F):
-                if len(tickets) >= args.inflight:
-                    flt.wait(tickets.pop(0))
-                tickets.append(flt.submit_raw(raw[f]))
+            for _ in range(k):
+                for f in range(F):
+                    if len(tickets) >= args.inflight:
+                        flt.wait(tickets.pop(0))
+                    tickets.append(flt.submit_raw(raw[f]))
             for t in tickets:
                 flt.wait(t)
 
-        for _ in range(max(1, warmup // 2)):
-            e2e_step()
+        e2e_steps(max(1, warmup // 2))
         D.barrier()
         t0 = time.perf_counter()
-        for _ in range(steps):
-            e2e_step()
+        e2e_steps(steps)
         D.barrier()
         res["pinned_s"] = time.perf_counter() - t0
     if sampler:
@@ -625,9 +627,10 @@ def measure_config(D, args, cfg, config_id: int, steps: int, warmup: int, full: 
     # ---------------- end to end through the plugin (the reference-facing call), pageable frames
     if args.plugin_threads > 0:
         try:
-            dt, construct_s, stats = run_plugin_leg(D, cfg, args.plugin_threads, max(1, min(steps, 10)) if full else max(1, min(steps, 5)),
-                                                    2 if full else 1)
-            res["plugin_s"], res["plugin_steps"] = dt, (max(1, min(steps, 10)) if full else max(1, min(steps, 5)))
+            psteps = max(1, min(steps, 10)) if full else max(1, min(steps, 5))
+            psteps = max(psteps, -(-24 // F))  # a stream of at least 24 frames
+            dt, construct_s, stats = run_plugin_leg(D, cfg, args.plugin_threads, psteps, 2 if full else 1)
+            res["plugin_s"], res["plugin_steps"] = dt, psteps
             res["plugin_construct_ms"], res["plugin_host_buffers"] = construct_s * 1e3, stats
         except Exception as ex:  # the other legs stand on their own
             res["plugin_error"] = str(ex)[:200]
@@ -704,6 +707,7 @@ def run_b200(args, cfg):
                 "launch_ms": dom, "frac": luma_o["flop"] * o["F"] / (dom * 1e-3) / 1e12 / fma_peak,
                 "whole_step_frac": flop_o * o["F"] * steps_o / (o["ms_total"] * 1e-3) / 1e12 / fma_peak,
                 "e2e": (D.world * o["plugin_steps"] * o["F"] * (c["tw"] * c["th"] / 1e6) / o_plugin) if "plugin_s" in o else None,
+                "e2e_host_buffers": o.get("plugin_host_buffers"),
                 "construct_ms": o["construct_ms"], "plugin_construct_ms": o.get("plugin_construct_ms"),
                 "kernel": KERNEL_NAMES.get(o["infos"][0].fast_path, "resample_strips"),
                 "verified": o.get("verified", {}).get("ok")}

@@ -343,7 +343,7 @@ def test_stale_registration_is_detected(capi, side):
     _, fmt, w, h, tw, th, kw = CASES["c2_420p8_2x_tap3_mpeg2"]
     planes = make_planes(fmt, w, h, "noise", seed=33)
     ref, _ = oracle_frame(fmt, w, h, tw, th, planes, **kw)
-    flt = make_filter(fmt, w, h, tw, th, flags=capi.FLAG_HOST_REGISTER, **kw)
+    flt = make_filter(fmt, w, h, tw, th, flags=capi.FLAG_HOST_REGISTER | capi.FLAG_DST_PADDING_WRITABLE, **kw)
     shapes = flt.plane_shapes()
     m = _Mapping([(d[0], d[1]) for _, d in shapes] if side == "dst" else [(s[0], s[1]) for s, _ in shapes])
 
