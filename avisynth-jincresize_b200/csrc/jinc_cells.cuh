@@ -114,6 +114,10 @@ __global__ void __launch_bounds__((CellsGeom<FS, Q>::THREADS), 2) resample_cells
         return;
     const int ncx = __ldg(a.cx_n + cxk), ncy = __ldg(a.cy_n + cyk);
     const int cell_x = __ldg(a.cx_cell + cxk), cell_y = __ldg(a.cy_cell + cyk);
+    // output addressing, once per thread: residue (py, px) of cell (cell_x + i, cell_y + j) is obase[py * dp + px + j * rstep + i * Px]
+    T* __restrict__ const obase = dst + (long long)(a.y0 + Py * cell_y) * dp + (a.x0 + Px * cell_x);
+    const long long rstep = (long long)Py * dp;
+    const bool full = ncx == G::NX && ncy == G::NY && cell_y >= a.cell_y_begin && cell_y + G::NY <= a.cell_y_end;
 
 #pragma unroll 1
     for (int py = 0; py < Py; ++py) {
@@ -187,15 +191,23 @@ __global__ void __launch_bounds__((CellsGeom<FS, Q>::THREADS), 2) resample_cells
             }
 
             // ---- this residue pair's samples of the chunk: every Px-th column of every Py-th row
+            T* __restrict__ o = obase + (long long)py * dp + px;
+            if (full) { // the usual case: no per-sample tests
 #pragma unroll
-            for (int j = 0; j < G::NY; ++j) {
-                const int cy = cell_y + j;
-                if (j < ncy && cy >= a.cell_y_begin && cy < a.cell_y_end) {
-                    T* __restrict__ o = dst + (long long)(a.y0 + Py * cy + py) * dp + (a.x0 + Px * cell_x + px);
+                for (int j = 0; j < G::NY; ++j, o += rstep)
 #pragma unroll
                     for (int i = 0; i < G::NX; ++i)
-                        if (i < ncx)
-                            o[i * Px] = finish<T>(acc[j][i], a.fr.peak);
+                        o[i * Px] = finish<T>(acc[j][i], a.fr.peak);
+            } else {
+#pragma unroll
+                for (int j = 0; j < G::NY; ++j, o += rstep) {
+                    const int cy = cell_y + j;
+                    if (j < ncy && cy >= a.cell_y_begin && cy < a.cell_y_end) {
+#pragma unroll
+                        for (int i = 0; i < G::NX; ++i)
+                            if (i < ncx)
+                                o[i * Px] = finish<T>(acc[j][i], a.fr.peak);
+                    }
                 }
             }
         }

@@ -399,7 +399,7 @@ int enqueue_frame(jinc_filter* f, Slot* s, const jinc_frame* frame, int y0_luma,
     }
     // memory registered here is moved as whole extents (its unlocked ends are split off), which needs the pipeline's pitch;
     // memory the caller allocated page-locked may have any pitch (2-D copies)
-    src_direct = src_direct && jinc_hostmem::acquire(rs, np, may_register && src_same_pitch, &s->src_pin);
+    src_direct = src_direct && jinc_hostmem::acquire(rs, np, may_register && src_same_pitch, d.ctx->device, &s->src_pin);
     if (src_direct && !src_same_pitch && jinc_hostmem::registered_here(&s->src_pin)) {
         jinc_hostmem::release(&s->src_pin);
         src_direct = false;
@@ -497,7 +497,7 @@ int enqueue_frame(jinc_filter* f, Slot* s, const jinc_frame* frame, int y0_luma,
     }
     // whole extents may be written only where the bytes between rows (and planes) belong to the frame
     const bool dst_extents = dst_same_pitch && (dst_tight || padding_ok);
-    dst_direct = dst_direct && jinc_hostmem::acquire(rd, np, may_register && dst_extents, &s->dst_pin);
+    dst_direct = dst_direct && jinc_hostmem::acquire(rd, np, may_register && dst_extents, d.ctx->device, &s->dst_pin);
     const bool dst_ours = dst_direct && jinc_hostmem::registered_here(&s->dst_pin);
     if (dst_ours && !dst_extents) {
         jinc_hostmem::release(&s->dst_pin);

@@ -197,7 +197,67 @@ bool do_register(Entry* e)
 
 } // namespace
 
-bool acquire(const Range* ranges, int n, bool may_register, Pin* pin)
+// ------------------------------------------------------------------------------------------ helper threads
+
+namespace {
+
+class CopyPool {
+public:
+    // the helpers of the staging copies (never destroyed: helper threads may outlive static destructors)
+    static CopyPool& get()
+    {
+        static CopyPool* p = [] {
+            const char* s = getenv("JINCRESIZE_B200_COPY_THREADS");
+            const int hw = static_cast<int>(std::thread::hardware_concurrency());
+            return new CopyPool(s ? atoi(s) : std::min(3, std::max(0, hw / 4 - 1)));
+        }();
+        return *p;
+    }
+    // one thread of its own for registrations: page-locking hundreds of megabytes must not sit in front of a staging copy
+    static CopyPool& registrar()
+    {
+        static CopyPool* p = new CopyPool(1);
+        return *p;
+    }
+    int helpers() const { return static_cast<int>(threads_.size()); }
+    void run(std::function<void()> fn)
+    {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            q_.push_back(std::move(fn));
+        }
+        cv_.notify_one();
+    }
+
+private:
+    explicit CopyPool(int n)
+    {
+        n = std::max(0, std::min(n, 16));
+        for (int i = 0; i < n; ++i) {
+            threads_.emplace_back([this] {
+                for (;;) {
+                    std::function<void()> fn;
+                    {
+                        std::unique_lock<std::mutex> lk(mu_);
+                        cv_.wait(lk, [this] { return !q_.empty(); });
+                        fn = std::move(q_.front());
+                        q_.pop_front();
+                    }
+                    fn();
+                }
+            });
+            threads_.back().detach();
+        }
+    }
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::deque<std::function<void()>> q_;
+    std::vector<std::thread> threads_;
+};
+
+} // namespace
+
+bool acquire(const Range* ranges, int n, bool may_register, int device, Pin* pin)
 {
     pin->n = 0;
     if (n < 1 || n > JINC_MAX_PLANES)
@@ -253,11 +313,20 @@ bool acquire(const Range* ranges, int n, bool may_register, Pin* pin)
         e->tick = ++g_tick;
         e->last_use = now;
         if (e->state == Entry::SEEN && may_register && e->sightings >= 2 && !e->poisoned) {
+            // Page-locking a large frame buffer takes tens of milliseconds: it happens on a helper thread while this
+            // frame is staged like the first one, and the buffer is used directly from its next return on.
             e->state = Entry::REGISTERING;
-            lk.unlock();
-            const bool ok = do_register(e);
-            lk.lock();
-            e->state = ok ? Entry::REGISTERED : Entry::REFUSED;
+            auto task = [e, device] {
+                cudaSetDevice(device);
+                const bool ok = do_register(e);
+                std::lock_guard<std::mutex> lk2(g_mu);
+                e->state = ok ? Entry::REGISTERED : Entry::REFUSED;
+                if (ok && g_clients == 0) { // the last registering filter went away meanwhile
+                    unregister_locked(e);
+                    e->sightings = 0;
+                }
+            };
+            CopyPool::registrar().run(task);
         }
         if (e->state != Entry::EXTERNAL && e->state != Entry::REGISTERED)
             return false;
@@ -367,52 +436,6 @@ long registrations()
 // ------------------------------------------------------------------------------------------ staging copies
 
 namespace {
-
-class CopyPool {
-public:
-    static CopyPool& get()
-    {
-        static CopyPool* p = new CopyPool(); // never destroyed: helper threads may outlive static destructors
-        return *p;
-    }
-    int helpers() const { return static_cast<int>(threads_.size()); }
-    void run(std::function<void()> fn)
-    {
-        {
-            std::lock_guard<std::mutex> lk(mu_);
-            q_.push_back(std::move(fn));
-        }
-        cv_.notify_one();
-    }
-
-private:
-    CopyPool()
-    {
-        const char* s = getenv("JINCRESIZE_B200_COPY_THREADS");
-        const int hw = static_cast<int>(std::thread::hardware_concurrency());
-        int n = s ? atoi(s) : std::min(3, std::max(0, hw / 4 - 1));
-        n = std::max(0, std::min(n, 16));
-        for (int i = 0; i < n; ++i) {
-            threads_.emplace_back([this] {
-                for (;;) {
-                    std::function<void()> fn;
-                    {
-                        std::unique_lock<std::mutex> lk(mu_);
-                        cv_.wait(lk, [this] { return !q_.empty(); });
-                        fn = std::move(q_.front());
-                        q_.pop_front();
-                    }
-                    fn();
-                }
-            });
-            threads_.back().detach();
-        }
-    }
-    std::mutex mu_;
-    std::condition_variable cv_;
-    std::deque<std::function<void()>> q_;
-    std::vector<std::thread> threads_;
-};
 
 void copy_rows_serial(unsigned char* dst, size_t dst_pitch, const unsigned char* src, ptrdiff_t src_pitch, size_t row_bytes, int rows)
 {

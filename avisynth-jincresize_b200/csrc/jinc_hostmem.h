@@ -42,9 +42,10 @@ struct Pin {
 // The part [*a, *b) (offsets into [0, n)) of host range [p, p + n) that DMA may address directly; *a == *b: none.
 void direct_part(const Pin& pin, const void* p, size_t n, size_t* a, size_t* b);
 
-// True when every range is page-locked (allocated so by the caller, or registered here -- now, if `may_register` and the
-// buffer has been seen before); the ranges are then pinned against eviction until release().  False: stage the frame.
-bool acquire(const Range* ranges, int n, bool may_register, Pin* pin);
+// True when every range is page-locked (allocated so by the caller, or registered here); the ranges are then pinned
+// against eviction until release().  False: stage the frame.  With `may_register` a pageable buffer that has been seen
+// before is handed to a helper thread for registration (on CUDA device `device`) and used directly once that is done.
+bool acquire(const Range* ranges, int n, bool may_register, int device, Pin* pin);
 void release(Pin* pin);
 // filters that may register caller memory; when the last one goes every registration is dropped
 void client_add();

@@ -17,7 +17,7 @@ struct GeneralArgs {
 };
 
 constexpr int GEN_SPT = 4;                  // outputs per thread of the general kernel
-constexpr int GEN_MAX_PW = 64;              // its patches are 64 x 16 outputs
+constexpr int GEN_MAX_PW = 128;             // its patches are 128 x 8 outputs: a warp covers ONE output row (consecutive lanes read nearly consecutive shared-memory words)
 constexpr size_t GEN_SMEM = (size_t)96 << 10; // staging space (two blocks per SM)
 
 // General kernel: one block = one patch of 64 x 16 outputs of ALL NP planes that share the table.  Every output has its

@@ -493,9 +493,15 @@ def run_plugin_leg(D, cfg, threads: int, steps: int, warm_steps: int):
     construct_s = time.perf_counter() - t0
     f0 = 0
     st0 = capi.host_buffer_stats()
-    for _ in range(max(1, warm_steps)):  # table build, slot allocation, first touch and registration of the frame pool
+    # warm-up: table build, slot allocation, first touch of the frame pool, and the page-locking of the pool's buffers
+    # (done by a helper thread while the frames that found them pageable are staged) -- until a pull stages nothing
+    for k in range(12):
+        before = capi.host_buffer_stats()
         clip.pull(f0, max(F, 3 * threads), threads)
         f0 += max(F, 3 * threads)
+        after = capi.host_buffer_stats()
+        if k + 1 >= max(1, warm_steps) and after["staged_frames"] == before["staged_frames"] and after["registrations"] == before["registrations"]:
+            break
     D.barrier()
     t0 = time.perf_counter()
     clip.pull(f0, steps * F, threads)  # the K steps back to back, as a host streams a clip: no barrier between steps
