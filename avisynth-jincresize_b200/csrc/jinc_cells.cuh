@@ -6,8 +6,11 @@
 // Q*c + off[p] with the phase block of residue p -- exactly so when Q/P is a dyadic fraction (the periodic paths), and
 // PIECEWISE so otherwise: the reference accumulates positions in float (:363, 524-528), the quantised phase of a residue
 // drifts, and every few dozen cells it steps to the next phase index (1280 -> 1920: 15 phases per axis over 31 runs).
-// The table build cuts each axis into CHUNKS of up to 4 cells inside which every residue keeps its phase block and its
-// origins advance by exactly Q per cell (jinc_table.cu, build_cells_axis).
+// The table build lays a regular grid of 4-cell groups over each axis and cuts it into CHUNKS inside which every residue
+// keeps its phase block and its origins advance by exactly Q per cell: one chunk per group, more where a residue's phase
+// steps inside the group (jinc_table.cu, build_cells_axis).  A thread computes all 4 cells of its group and stores the
+// ones of its chunk, so the lanes of a warp always read shared memory at the same alignment (the two lanes of a split
+// group read the same words: a broadcast, not a bank conflict).
 //
 // One thread owns one x-chunk x one y-chunk and walks the P x P residue pairs one after the other: the 4 x 4 outputs of
 // a pair share ONE weight block, held in registers (FS*FS floats, read once per pass from L1/L2), and their windows
@@ -27,7 +30,7 @@ namespace jinc_rs {
 template <int FS, int Q>
 struct CellsGeom {
     static constexpr int NX = JINC_CELLS_NX, NY = JINC_CELLS_NY;
-    static constexpr int WARPS = jinc_cells_warps(Q);
+    static constexpr int WARPS = jinc_cells_warps(Q, FS);
     static constexpr int THREADS = 32 * WARPS;
     static constexpr int FSP = (FS + 3) & ~3;
     static constexpr int SPAN = Q * (NX - 1) + FS; // columns a thread reads per source row
@@ -44,7 +47,7 @@ constexpr int CL_STRIP_SPT = 4;
 constexpr int CL_STRIP_MAX_PW = 64;
 
 template <typename T, int FS, int Q>
-__global__ void __launch_bounds__((CellsGeom<FS, Q>::THREADS), 2) resample_cells(const __grid_constant__ CellsArgs a)
+__global__ void __launch_bounds__((CellsGeom<FS, Q>::THREADS), (CellsGeom<FS, Q>::THREADS == 128 && FS <= 9 ? 3 : 2)) resample_cells(const __grid_constant__ CellsArgs a)
 {
     using G = CellsGeom<FS, Q>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -112,12 +115,13 @@ __global__ void __launch_bounds__((CellsGeom<FS, Q>::THREADS), 2) resample_cells
     const int cxk = cxk0 + lane, cyk = cyk0 + warp;
     if (cxk >= a.n_cx || cyk >= a.cyk_end)
         return;
-    const int ncx = __ldg(a.cx_n + cxk), ncy = __ldg(a.cy_n + cyk);
-    const int cell_x = __ldg(a.cx_cell + cxk), cell_y = __ldg(a.cy_cell + cyk);
+    const int ncx = __ldg(a.cx_n + cxk), ncy = __ldg(a.cy_n + cyk);     // live cells of the chunk ...
+    const int ix0 = __ldg(a.cx_i0 + cxk), iy0 = __ldg(a.cy_i0 + cyk);   // ... from this cell of the group on
+    const int cell_x = __ldg(a.cx_cell + cxk), cell_y = __ldg(a.cy_cell + cyk); // first cell of the group
     // output addressing, once per thread: residue (py, px) of cell (cell_x + i, cell_y + j) is obase[py * dp + px + j * rstep + i * Px]
     T* __restrict__ const obase = dst + (long long)(a.y0 + Py * cell_y) * dp + (a.x0 + Px * cell_x);
     const long long rstep = (long long)Py * dp;
-    const bool full = ncx == G::NX && ncy == G::NY && cell_y >= a.cell_y_begin && cell_y + G::NY <= a.cell_y_end;
+    const bool full = ncx == G::NX && ncy == G::NY && cell_y >= a.cell_y_begin && cell_y + G::NY <= a.cell_y_end; // then ix0 = iy0 = 0
 
 #pragma unroll 1
     for (int py = 0; py < Py; ++py) {
@@ -202,10 +206,10 @@ __global__ void __launch_bounds__((CellsGeom<FS, Q>::THREADS), 2) resample_cells
 #pragma unroll
                 for (int j = 0; j < G::NY; ++j, o += rstep) {
                     const int cy = cell_y + j;
-                    if (j < ncy && cy >= a.cell_y_begin && cy < a.cell_y_end) {
+                    if (j >= iy0 && j < iy0 + ncy && cy >= a.cell_y_begin && cy < a.cell_y_end) {
 #pragma unroll
                         for (int i = 0; i < G::NX; ++i)
-                            if (i < ncx)
+                            if (i >= ix0 && i < ix0 + ncx)
                                 o[i * Px] = finish<T>(acc[j][i], a.fr.peak);
                     }
                 }

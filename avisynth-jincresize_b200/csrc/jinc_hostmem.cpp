@@ -47,7 +47,7 @@ int g_clients = 0;        // live filters that asked for registration
 double g_last_sweep = 0.0;
 
 constexpr size_t kMaxEntries = 4096;
-constexpr double kIdleSeconds = 2.0;  // a registration not used for this long is dropped (the host may have retired the buffer)
+constexpr double kIdleSeconds = 5.0;  // a registration not used for this long is dropped (the host may have retired the buffer)
 constexpr double kSweepEvery = 0.25;
 
 double now_s()

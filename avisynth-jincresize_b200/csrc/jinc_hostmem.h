@@ -6,7 +6,7 @@
 // every buffer it has seen: buffers the caller allocated page-locked are used directly; pageable buffers are staged
 // through the slot's pinned mirror the first time and registered (cudaHostRegister) when they come back, after which
 // they are used directly too.  Registered memory is capped and evicted least-recently-used; a registration that has
-// not been used for two seconds is dropped, and everything is unregistered when the last registering filter goes.
+// not been used for five seconds is dropped, and everything is unregistered when the last registering filter goes.
 //
 // Registration is OPT-IN (JINC_FILTER_HOST_REGISTER) because it rests on a promise only the host can make: a buffer
 // that was registered must not be freed while it still is.  A stale registration sends DMA to the buffer's former

@@ -95,11 +95,13 @@ struct PeriodicPlan {
     int wblock[4][4] = {};                // [py][px] -> phase-block index
 };
 
-// Piecewise-periodic rational ratio (jinc_cells.cuh): crop/dst = Q/P on both axes.  Each axis is cut into CHUNKS of up to
-// JINC_CELLS_N* cells (a cell = P consecutive outputs) inside which every residue p keeps its phase rank and its window
-// origins advance by exactly Q per cell.
+// Piecewise-periodic rational ratio (jinc_cells.cuh): crop/dst = Q/P on both axes.  Each axis is a regular grid of groups
+// of JINC_CELLS_N* cells (a cell = P consecutive outputs), cut into CHUNKS inside which every residue p keeps its phase
+// rank and its window origins advance by exactly Q per cell: one chunk per group, more where a residue changes rank.
 constexpr int JINC_CELLS_NX = 4, JINC_CELLS_NY = 4;
-constexpr int jinc_cells_warps(int q) { return q >= 3 ? 4 : 8; } // y-chunks per tile (one per warp)
+// y-chunks per tile (one per warp): four where the footprint is tall (Q >= 3) or the weight block needs the registers of a
+// 128-thread block (windows of 9 and more)
+constexpr int jinc_cells_warps(int q, int fs) { return (q >= 3 || fs >= 9) ? 4 : 8; }
 // samples staged along one axis for a tile of `chunks` chunks of n cells: the chunks' cells, the window, and slack for the
 // residues' origin offsets and one irregular origin step
 constexpr int jinc_cells_footprint(int q, int fs, int n, int chunks) { return q * n * chunks + fs + q + 2; }
@@ -112,8 +114,11 @@ struct CellsAxis {
     int P = 0, Q = 0;
     int first = 0, ncells = 0; // first output of cell 0, number of cells
     int n_chunks = 0;
-    std::vector<int32_t> cell, n, org, rank; // per chunk: first cell, cells; per (chunk, residue): window origin, phase rank
+    // per chunk: first cell of its group, first cell of the chunk inside the group, cells of the chunk; per (chunk, residue):
+    // window origin of the GROUP's first cell (extrapolated from the chunk's), phase rank
+    std::vector<int32_t> cell, i0, n, org, rank;
     int32_t* d_cell = nullptr;
+    int32_t* d_i0 = nullptr;
     int32_t* d_n = nullptr;
     int32_t* d_org = nullptr;
     int32_t* d_rank = nullptr;

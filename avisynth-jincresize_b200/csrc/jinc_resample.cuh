@@ -929,11 +929,13 @@ int launch_down(const jinc_table* t, DownArgs& a, int q, const int* wblocks, boo
 struct CellsArgs {
     FrameSet fr;
     StripArgs st;
-    const int32_t* cx_cell; // per x-chunk: first cell, cells, then per residue the window origin and phase rank
+    const int32_t* cx_cell; // per x-chunk: first cell of its group, first live cell, live cells; per residue: origin, phase rank
+    const int32_t* cx_i0;
     const int32_t* cx_n;
     const int32_t* cx_org;
     const int32_t* cx_rank;
     const int32_t* cy_cell;
+    const int32_t* cy_i0;
     const int32_t* cy_n;
     const int32_t* cy_org;
     const int32_t* cy_rank;

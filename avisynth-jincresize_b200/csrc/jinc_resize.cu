@@ -338,10 +338,12 @@ int launch_typed(const jinc_table* t, const FrameSet& fr, int n_frames, int y_be
             a.fr = fr;
             a.st = sa;
             a.cx_cell = ax.d_cell;
+            a.cx_i0 = ax.d_i0;
             a.cx_n = ax.d_n;
             a.cx_org = ax.d_org;
             a.cx_rank = ax.d_rank;
             a.cy_cell = ay.d_cell;
+            a.cy_i0 = ay.d_i0;
             a.cy_n = ay.d_n;
             a.cy_org = ay.d_org;
             a.cy_rank = ay.d_rank;
@@ -353,11 +355,11 @@ int launch_typed(const jinc_table* t, const FrameSet& fr, int n_frames, int y_be
             a.y0 = ay.first;
             a.n_rank_x = t->ax[0].n_rank;
             a.n_cx = ax.n_chunks;
-            // y-chunks holding cell rows of [cb, ce): chunk k covers cells [cell[k], cell[k] + n[k])
+            // y-chunks holding cell rows of [cb, ce): chunk k covers cells [cell[k] + i0[k], cell[k] + i0[k] + n[k])
             int k0 = 0, k1 = ay.n_chunks;
-            while (k0 < k1 && ay.cell[k0] + ay.n[k0] <= cb)
+            while (k0 < k1 && ay.cell[k0] + ay.i0[k0] + ay.n[k0] <= cb)
                 ++k0;
-            while (k1 > k0 && ay.cell[k1 - 1] >= ce)
+            while (k1 > k0 && ay.cell[k1 - 1] + ay.i0[k1 - 1] >= ce)
                 --k1;
             a.cyk_begin = k0;
             a.cyk_end = k1;

@@ -370,29 +370,38 @@ bool build_cells_axis(const std::vector<int32_t>& start, const std::vector<int32
         out.Q = Q;
         out.first = a;
         out.ncells = (b - a) / P;
-        int c = 0;
-        while (c < out.ncells) {
-            int len = 1;
-            while (len < N && c + len < out.ncells) {
-                bool same = true;
-                for (int p = 0; p < P && same; ++p) {
-                    const int i0 = a + P * (c + len - 1) + p, i1 = i0 + P;
-                    same = rank[i1] == rank[i0] && start[i1] == start[i0] + Q;
+        // Chunks live on a REGULAR grid of N-cell groups: a group inside which some residue changes its rank (or an
+        // origin steps irregularly) becomes several chunks, each with the group's origin extrapolated back to the group's
+        // first cell.  A thread computes all N cells of its group and stores the ones of its chunk, so every lane of a warp
+        // reads the same shared-memory alignment (neighbouring lanes of a split group read the same words: a broadcast).
+        for (int c0 = 0; c0 < out.ncells; c0 += N) {
+            const int c1 = std::min(out.ncells, c0 + N);
+            int c = c0;
+            while (c < c1) {
+                int len = 1;
+                while (c + len < c1) {
+                    bool same = true;
+                    for (int p = 0; p < P && same; ++p) {
+                        const int i0 = a + P * (c + len - 1) + p, i1 = i0 + P;
+                        same = rank[i1] == rank[i0] && start[i1] == start[i0] + Q;
+                    }
+                    if (!same)
+                        break;
+                    ++len;
                 }
-                if (!same)
-                    break;
-                ++len;
+                out.cell.push_back(c0);
+                out.i0.push_back(c - c0);
+                out.n.push_back(len);
+                for (int p = 0; p < P; ++p) {
+                    out.org.push_back(start[a + P * c + p] - Q * (c - c0));
+                    out.rank.push_back(rank[a + P * c + p]);
+                }
+                c += len;
             }
-            out.cell.push_back(c);
-            out.n.push_back(len);
-            for (int p = 0; p < P; ++p) {
-                out.org.push_back(start[a + P * c + p]);
-                out.rank.push_back(rank[a + P * c + p]);
-            }
-            c += len;
         }
         out.n_chunks = static_cast<int>(out.cell.size());
-        return out.ncells >= 8 && static_cast<long long>(out.n_chunks) * N * 3 <= static_cast<long long>(out.ncells) * 4 + 8 * N;
+        const long long groups = (out.ncells + N - 1) / N;
+        return out.ncells >= 8 && static_cast<long long>(out.n_chunks) * 3 <= groups * 4 + 8;
     }
     return false;
 }
@@ -423,12 +432,14 @@ bool cells_footprints_fit(const CellsAxis& ax, int fs, int N, int per_tile, int 
 int upload_cells_axis(CellsAxis& ax, cudaStream_t st)
 {
     int rc = dev_alloc(&ax.d_cell, ax.cell.size());
+    rc = rc ? rc : dev_alloc(&ax.d_i0, ax.i0.size());
     rc = rc ? rc : dev_alloc(&ax.d_n, ax.n.size());
     rc = rc ? rc : dev_alloc(&ax.d_org, ax.org.size());
     rc = rc ? rc : dev_alloc(&ax.d_rank, ax.rank.size());
     if (rc)
         return rc;
     JINC_CUDA(cudaMemcpyAsync(ax.d_cell, ax.cell.data(), ax.cell.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    JINC_CUDA(cudaMemcpyAsync(ax.d_i0, ax.i0.data(), ax.i0.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     JINC_CUDA(cudaMemcpyAsync(ax.d_n, ax.n.data(), ax.n.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     JINC_CUDA(cudaMemcpyAsync(ax.d_org, ax.org.data(), ax.org.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     JINC_CUDA(cudaMemcpyAsync(ax.d_rank, ax.rank.data(), ax.rank.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
@@ -502,8 +513,8 @@ void plan_fast_paths(jinc_table* t)
             build_cells_axis(t->h_start[1], t->h_rank[1], ax_a[1], ax_b[1], JINC_CELLS_NY, u.ax[1]) && u.ax[0].Q == u.ax[1].Q &&
             jinc_cells_instantiated(u.ax[0].Q, fs) &&
             cells_footprints_fit(u.ax[0], fs, JINC_CELLS_NX, 32, jinc_cells_footprint(u.ax[0].Q, fs, JINC_CELLS_NX, 32), false) &&
-            cells_footprints_fit(u.ax[1], fs, JINC_CELLS_NY, jinc_cells_warps(u.ax[1].Q),
-                                 jinc_cells_footprint(u.ax[1].Q, fs, JINC_CELLS_NY, jinc_cells_warps(u.ax[1].Q)), true)) {
+            cells_footprints_fit(u.ax[1], fs, JINC_CELLS_NY, jinc_cells_warps(u.ax[1].Q, fs),
+                                 jinc_cells_footprint(u.ax[1].Q, fs, JINC_CELLS_NY, jinc_cells_warps(u.ax[1].Q, fs)), true)) {
             u.Q = u.ax[0].Q;
             u.ok = true;
             t->fast_path = JINC_PATH_CELLS;
@@ -817,6 +828,7 @@ extern "C" void jinc_table_destroy(jinc_table* t)
     }
     for (CellsAxis& c : t->cells.ax) {
         cudaFree(c.d_cell);
+        cudaFree(c.d_i0);
         cudaFree(c.d_n);
         cudaFree(c.d_org);
         cudaFree(c.d_rank);

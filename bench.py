@@ -408,9 +408,20 @@ def make_filter(cfg, devices, slots=0, flags=0):
                        devices=list(devices), slots_per_device=slots, flags=flags)
 
 
-def verify_against_oracle(cfg, flt, planes_by_frame, dst_by_frame, shapes):
-    """Outside the timed region: rows of the kernel-only leg's OUTPUT (first and last frame of the batch: top, a tile
-    seam in the middle, bottom of every plane) are downloaded and compared with the CPU oracle within the parity bar."""
+def capture_output_rows(cfg, planes_by_frame, dst_by_frame, shapes):
+    """Right after the kernel-only leg: rows of its OUTPUT (first and last frame of the batch: top, a tile seam in the
+    middle, bottom of every plane) are downloaded; verify_against_oracle compares them once every timed leg is done."""
+    cap = []
+    for fi, (planes, dsts) in enumerate(zip(planes_by_frame, dst_by_frame)):
+        for i, pl in enumerate(planes):
+            H, W = shapes[i][1]
+            for (y0, y1) in ((0, 3), (H // 2 - 1, H // 2 + 2), (H - 3, H)):
+                cap.append((fi, i, y0, y1, pl, dsts[i][y0:y1, :W].cpu().numpy()))
+    return cap
+
+
+def verify_against_oracle(cfg, captured):
+    """Outside the timed regions: the captured rows of the kernel-only leg's output against the CPU oracle (parity bar)."""
     from oracle import cpu as oc
 
     fmt, kw = cfg["fmt"], cfg["kw"]
@@ -422,26 +433,22 @@ def verify_against_oracle(cfg, flt, planes_by_frame, dst_by_frame, shapes):
     tabs = [oc.Table(p, lut) for p in pp]
     peak = float(fmt.peak) if fmt.bits < 32 else 0.0
     worst, rows_checked = 0.0, 0
-    for fi, (planes, dsts) in enumerate(zip(planes_by_frame, dst_by_frame)):
-        for i, pl in enumerate(planes):
-            t = tabs[1] if (len(tabs) > 1 and i in (1, 2)) else tabs[0]
-            H, W = t.dst_h, t.dst_w
-            for (y0, y1) in ((0, 3), (H // 2 - 1, H // 2 + 2), (H - 3, H)):
-                ref = t.resize(pl, peak, rows=(y0, y1))[y0:y1]
-                got = dsts[i][y0:y1, :W].cpu().numpy()
-                if fmt.bits == 32:
-                    err = float((np.abs(got.astype(np.float64) - ref) / np.maximum(1.0, np.abs(ref))).max())
-                    ok = err <= 1e-5
-                else:
-                    err = float(np.abs(got.astype(np.int64) - ref.astype(np.int64)).max())
-                    ok = err <= 1
-                worst = max(worst, err)
-                rows_checked += y1 - y0
-                if not ok:
-                    raise SystemExit(f"bench.py: kernel-only output differs from the oracle (frame {fi} plane {i} rows {y0}-{y1}: {err})")
+    for fi, i, y0, y1, pl, got in captured:
+        t = tabs[1] if (len(tabs) > 1 and i in (1, 2)) else tabs[0]
+        ref = t.resize(pl, peak, rows=(y0, y1))[y0:y1]
+        if fmt.bits == 32:
+            err = float((np.abs(got.astype(np.float64) - ref) / np.maximum(1.0, np.abs(ref))).max())
+            ok = err <= 1e-5
+        else:
+            err = float(np.abs(got.astype(np.int64) - ref.astype(np.int64)).max())
+            ok = err <= 1
+        worst = max(worst, err)
+        rows_checked += y1 - y0
+        if not ok:
+            raise SystemExit(f"bench.py: kernel-only output differs from the oracle (frame {fi} plane {i} rows {y0}-{y1}: {err})")
     for t in tabs:
         t.close()
-    return {"ok": True, "against": "CPU oracle (oracle/jinc_oracle.c)", "frames_checked": len(planes_by_frame),
+    return {"ok": True, "against": "CPU oracle (oracle/jinc_oracle.c)", "frames_checked": len({c[0] for c in captured}),
             "rows_checked": rows_checked, "max_err": worst, "bar": "1e-5 relative" if fmt.bits == 32 else "1 LSB"}
 
 
@@ -596,8 +603,9 @@ def measure_config(D, args, cfg, config_id: int, steps: int, warmup: int, full: 
     dom_ms = [a.elapsed_time(b) for a, b in pairs]
     res = dict(F=F, fs_l=fs_l, fs_c=fs_c, infos=infos, ms_total=ms_total, dom_ms=dom_ms, gpu_launches=gpu_launches,
                construct_ms=sum(i.build_ms for i in infos), filter_create_ms=filter_create_s * 1e3, shapes=shapes)
+    captured = None
     if D.rank == 0 and args.parts == 3 and not args.no_verify:
-        res["verified"] = verify_against_oracle(cfg, flt, [planes_np[0], planes_np[F - 1]], [dev_dst[0], dev_dst[F - 1]], shapes)
+        captured = capture_output_rows(cfg, [planes_np[0], planes_np[F - 1]], [dev_dst[0], dev_dst[F - 1]], shapes)
 
     if full:
         # ---------------- pure-copy ceiling of the same buffers (no kernels)
@@ -640,6 +648,8 @@ def measure_config(D, args, cfg, config_id: int, steps: int, warmup: int, full: 
             res["plugin_construct_ms"], res["plugin_host_buffers"] = construct_s * 1e3, stats
         except Exception as ex:  # the other legs stand on their own
             res["plugin_error"] = str(ex)[:200]
+    if captured is not None:  # last: the other ranks wait at the next barrier, not inside a timed leg's warm-up
+        res["verified"] = verify_against_oracle(cfg, captured)
     return res
 
 

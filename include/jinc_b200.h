@@ -162,7 +162,7 @@ enum {
      * freed, while filters with this flag exist: a stale registration sends DMA to the buffer's former pages and makes
      * unrelated CUDA calls on the re-used address range fail.  The pipeline checks every transfer through its own
      * registrations (arrival sentinels in destination planes, probe words read back from source planes), drops a
-     * registration that fails and redoes that frame through the staged path; registrations idle for two seconds are
+     * registration that fails and redoes that frame through the staged path; registrations idle for five seconds are
      * dropped, and all of them when the last such filter is destroyed.  Memory the caller allocated page-locked is
      * always used directly, flag or not.  The plugin sets the flag unless JINCRESIZE_B200_HOSTREG=0. */
     JINC_FILTER_HOST_REGISTER = 1,
