@@ -46,6 +46,20 @@ struct CellsGeom {
 constexpr int CL_STRIP_SPT = 4;
 constexpr int CL_STRIP_MAX_PW = 64;
 
+// the NX x NY samples of one residue pair; PX > 0: the cell size is a compile-time constant (immediate store offsets)
+template <typename T, int NX, int NY, int PX>
+__device__ __forceinline__ void store_cells(T* __restrict__ o, long long rstep, int px_runtime, unsigned live, const float (&acc)[NY][NX],
+                                            float peak)
+{
+    const int step = PX > 0 ? PX : px_runtime;
+#pragma unroll
+    for (int j = 0; j < NY; ++j, o += rstep)
+#pragma unroll
+        for (int i = 0; i < NX; ++i)
+            if (live & (1u << (j * NX + i)))
+                o[i * step] = finish<T>(acc[j][i], peak);
+}
+
 template <typename T, int FS, int Q>
 __global__ void __launch_bounds__((CellsGeom<FS, Q>::THREADS), (CellsGeom<FS, Q>::THREADS == 128 && FS <= 9 ? 3 : 2)) resample_cells(const __grid_constant__ CellsArgs a)
 {
@@ -121,7 +135,13 @@ __global__ void __launch_bounds__((CellsGeom<FS, Q>::THREADS), (CellsGeom<FS, Q>
     // output addressing, once per thread: residue (py, px) of cell (cell_x + i, cell_y + j) is obase[py * dp + px + j * rstep + i * Px]
     T* __restrict__ const obase = dst + (long long)(a.y0 + Py * cell_y) * dp + (a.x0 + Px * cell_x);
     const long long rstep = (long long)Py * dp;
-    const bool full = ncx == G::NX && ncy == G::NY && cell_y >= a.cell_y_begin && cell_y + G::NY <= a.cell_y_end; // then ix0 = iy0 = 0
+    unsigned live = 0; // bit j * NX + i: cell (i, j) of the group belongs to this chunk (and to the row band)
+#pragma unroll
+    for (int j = 0; j < G::NY; ++j)
+#pragma unroll
+        for (int i = 0; i < G::NX; ++i)
+            if (i >= ix0 && i < ix0 + ncx && j >= iy0 && j < iy0 + ncy && cell_y + j >= a.cell_y_begin && cell_y + j < a.cell_y_end)
+                live |= 1u << (j * G::NX + i);
 
 #pragma unroll 1
     for (int py = 0; py < Py; ++py) {
@@ -194,25 +214,14 @@ __global__ void __launch_bounds__((CellsGeom<FS, Q>::THREADS), (CellsGeom<FS, Q>
                 }
             }
 
-            // ---- this residue pair's samples of the chunk: every Px-th column of every Py-th row
+            // ---- this residue pair's samples of the chunk: every Px-th column of every Py-th row.  One code path for
+            //      every lane (a warp holds whole and split groups side by side): a per-thread bit mask says which of
+            //      the 4 x 4 samples belong to the chunk, and the usual cell sizes get immediate store offsets.
             T* __restrict__ o = obase + (long long)py * dp + px;
-            if (full) { // the usual case: no per-sample tests
-#pragma unroll
-                for (int j = 0; j < G::NY; ++j, o += rstep)
-#pragma unroll
-                    for (int i = 0; i < G::NX; ++i)
-                        o[i * Px] = finish<T>(acc[j][i], a.fr.peak);
-            } else {
-#pragma unroll
-                for (int j = 0; j < G::NY; ++j, o += rstep) {
-                    const int cy = cell_y + j;
-                    if (j >= iy0 && j < iy0 + ncy && cy >= a.cell_y_begin && cy < a.cell_y_end) {
-#pragma unroll
-                        for (int i = 0; i < G::NX; ++i)
-                            if (i >= ix0 && i < ix0 + ncx)
-                                o[i * Px] = finish<T>(acc[j][i], a.fr.peak);
-                    }
-                }
+            switch (Px) {
+            case 3: store_cells<T, G::NX, G::NY, 3>(o, rstep, Px, live, acc, a.fr.peak); break;
+            case 4: store_cells<T, G::NX, G::NY, 4>(o, rstep, Px, live, acc, a.fr.peak); break;
+            default: store_cells<T, G::NX, G::NY, 0>(o, rstep, Px, live, acc, a.fr.peak); break;
             }
         }
     }
