@@ -98,6 +98,14 @@ SMALL_CASES = [
     # 4x upscale: exactly periodic (source step 0.25), sixteen unit-step passes
     ("up4x_tap3_420p8", ah.YUV420P8, 160, 90, 640, 360, dict(tap=3)),
     ("up4x_tap4_rgbp16", ah.Format("rgbp", 16), 120, 68, 480, 272, dict(tap=4)),
+    # more rational ratios of the chunked-cells kernel: 5:4 and 9:4 upscales and the 3:4 downscale (source step 4 per cell),
+    # 3x (step 1), 5:3 (step 3), taps 2 and 5 at 3:2
+    ("up5to4_tap3_420p8", ah.YUV420P8, 256, 144, 320, 180, dict(tap=3)),
+    ("up9to4_tap4_y16", ah.Format("y", 16), 128, 64, 288, 144, dict(tap=4)),
+    ("down3to4_tap3_444p10", ah.Format("444", 10), 320, 240, 240, 180, dict(tap=3)),
+    ("up3x_tap3_f32_y", ah.Format("y", 32), 120, 72, 360, 216, dict(tap=3)),
+    ("up5to3_tap4_rgbp8", ah.Format("rgbp", 8), 144, 96, 240, 160, dict(tap=4)),
+    ("up1p5_tap5_422p12", ah.Format("422", 12), 256, 120, 384, 180, dict(tap=5, cplace="mpeg1")),
     # general kernel with four planes on one table, and a steep irregular downscale whose source footprints do not fit
     # in shared memory (per-plane fallback of the general kernel)
     ("rgbap10_irregular_up", ah.Format("rgbap", 10), 200, 120, 290, 170, dict(tap=4)),
