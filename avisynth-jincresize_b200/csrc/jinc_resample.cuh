@@ -556,13 +556,104 @@ __device__ __forceinline__ void strip_samples_fused(const StripArgs& a, const Fr
             dst[(long long)m[k].y * dp + m[k].x] = finish<T>(acc[k], fsx.peak);
 }
 
+// SPT same-block samples whose windows OVERLAP: adjacent same-phase outputs of one row, window origins STEP apart
+// (the strips of the exact-2x geometry: outputs x, x+2, x+4, x+6 read columns sx, sx+1, sx+2, sx+3).  A window row of
+// FSC + (SPT-1)*STEP staged values is read once and feeds SPT x FSC FMAs; the weight row is read once as vectors.
+template <typename T, int FSC, int SPT, int STEP>
+__device__ __forceinline__ void strip_run_rows(const FrameSet& fsx, const StripMeta (&m)[SPT], int plane, const float* __restrict__ tile,
+                                               int fw, int sx_lo, int sy_lo)
+{
+    constexpr int FSP = (FSC + 3) & ~3, SEG = FSC + (SPT - 1) * STEP;
+    const float* __restrict__ s = tile + (m[0].sy - sy_lo) * fw + (m[0].sx - sx_lo);
+    const float4* __restrict__ w4 = reinterpret_cast<const float4*>(m[0].w);
+    float acc[SPT];
+#pragma unroll
+    for (int k = 0; k < SPT; ++k)
+        acc[k] = 0.f;
+#pragma unroll 1
+    for (int ly = 0; ly < FSC; ++ly, s += fw, w4 += FSP / 4) {
+        float seg[SEG], wr[FSP];
+#pragma unroll
+        for (int q = 0; q < FSP / 4; ++q) {
+            const float4 t = __ldg(w4 + q);
+            wr[4 * q] = t.x;
+            wr[4 * q + 1] = t.y;
+            wr[4 * q + 2] = t.z;
+            wr[4 * q + 3] = t.w;
+        }
+#pragma unroll
+        for (int i = 0; i < SEG; ++i)
+            seg[i] = s[i];
+#pragma unroll
+        for (int lx = 0; lx < FSC; ++lx)
+#pragma unroll
+            for (int k = 0; k < SPT; ++k)
+                acc[k] = fmaf(seg[lx + k * STEP], wr[lx], acc[k]);
+    }
+    const PlanePtrs& pp = frame_ptrs(fsx);
+    T* __restrict__ dst = static_cast<T*>(pp.dst[plane]) + (long long)m[0].y * pp.dst_pitch[plane];
+#pragma unroll
+    for (int k = 0; k < SPT; ++k)
+        dst[m[k].x] = finish<T>(acc[k], fsx.peak);
+}
+
+// The same for adjacent same-phase outputs of one COLUMN (window origins one row apart): a staged window row of FSC
+// values feeds up to SPT outputs, each with its own weight row; a sliding window of SPT weight rows lives in registers.
+template <typename T, int FSC, int SPT>
+__device__ __forceinline__ void strip_run_cols(const FrameSet& fsx, const StripMeta (&m)[SPT], int plane, const float* __restrict__ tile,
+                                               int fw, int sx_lo, int sy_lo)
+{
+    static_assert(SPT == 4, "the weight-row window is indexed modulo 4");
+    constexpr int FSP = (FSC + 3) & ~3;
+    const float* __restrict__ s = tile + (m[0].sy - sy_lo) * fw + (m[0].sx - sx_lo);
+    const float4* __restrict__ w4 = reinterpret_cast<const float4*>(m[0].w);
+    float acc[SPT], wwin[4][FSP];
+#pragma unroll
+    for (int k = 0; k < SPT; ++k)
+        acc[k] = 0.f;
+#pragma unroll
+    for (int r = 0; r < FSC + SPT - 1; ++r, s += fw) { // r: source row below the first output's window origin
+        float seg[FSC];
+#pragma unroll
+        for (int i = 0; i < FSC; ++i)
+            seg[i] = s[i];
+        if (r < FSC) {
+#pragma unroll
+            for (int q = 0; q < FSP / 4; ++q) {
+                const float4 t = __ldg(w4 + r * (FSP / 4) + q);
+                wwin[r & 3][4 * q] = t.x;
+                wwin[r & 3][4 * q + 1] = t.y;
+                wwin[r & 3][4 * q + 2] = t.z;
+                wwin[r & 3][4 * q + 3] = t.w;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < SPT; ++k) {
+            const int ly = r - k; // weight row of output k (a constant after unrolling)
+            if (ly >= 0 && ly < FSC) {
+#pragma unroll
+                for (int lx = 0; lx < FSC; ++lx)
+                    acc[k] = fmaf(seg[lx], wwin[ly & 3][lx], acc[k]);
+            }
+        }
+    }
+    const PlanePtrs& pp = frame_ptrs(fsx);
+    T* __restrict__ dst = static_cast<T*>(pp.dst[plane]);
+    const long long dp = pp.dst_pitch[plane];
+#pragma unroll
+    for (int k = 0; k < SPT; ++k)
+        dst[(long long)m[k].y * dp + m[k].x] = finish<T>(acc[k], fsx.peak);
+}
+
 // Strip block `sb` of the grid (planes are the slow dimension): one patch of PW x PH outputs, SPT per thread.  The
 // source rectangle the patch reads (window origins are monotonic along both axes) is staged into shared memory as
 // floats when it fits, so the global loads are coalesced, converted once and every window row is read from shared
 // memory; otherwise every sample reads global memory directly.  A thread's SPT samples lie in one output row (wide
 // strips) or one output column (narrow strips), a multiple of the phase period apart, so they normally share one weight
-// block and run fused.
-template <typename T, int FSC, int THREADS = STRIP_THREADS, int SPT = 1>
+// block and run fused.  PERIOD > 0 (the exact-2x kernel: 2) makes them ADJACENT same-phase outputs (x, x + PERIOD, ...),
+// whose window origins are STEP apart: their windows overlap, and strip_run_rows / strip_run_cols read every staged
+// value once for all of them.
+template <typename T, int FSC, int THREADS = STRIP_THREADS, int SPT = 1, int PERIOD = 0, int STEP = 0>
 __device__ __forceinline__ void strip_block(const StripArgs& a, const FrameSet& fsx, unsigned sb, float* __restrict__ tile)
 {
     static_assert((SPT & (SPT - 1)) == 0 && (THREADS & (THREADS - 1)) == 0, "powers of two");
@@ -582,14 +673,24 @@ __device__ __forceinline__ void strip_block(const StripArgs& a, const FrameSet& 
     const int fw = a.start_x[ox0 + nx - 1] + fs - sx_lo, fh = a.start_y[oy0 + ny - 1] + fs - sy_lo;
     StripMeta meta[SPT];
     unsigned live = 0;
+    const bool rows = a.row_mode[r] != 0;
     {
-        // sample k of thread t: row mode (x, y) = (tx + k * PW/SPT, ty), column mode (tx, ty + k * PH/SPT).  The live
-        // samples of a thread are a prefix (coordinates grow with k).  The axis tables are read once per distinct
+        // sample k of thread t: row mode (x, y) = (tx + k * dx, ty), column mode (tx, ty + k * dy), with dx = PW/SPT
+        // (dy = PH/SPT) -- or, with PERIOD, the thread's samples PERIOD apart inside a group of SPT * PERIOD outputs.  The
+        // live samples of a thread are a prefix (coordinates grow with k).  The axis tables are read once per distinct
         // coordinate: SPT + 1 positions instead of 2 SPT.
-        const bool rows = a.row_mode[r] != 0;
         const int txl = rows ? pwl - SPT_L2 : pwl; // log2 of the threads per patch row
-        const int tx = (int)threadIdx.x & ((1 << txl) - 1), ty = (int)threadIdx.x >> txl;
-        const int dx = rows ? 1 << txl : 0, dy = rows ? 0 : THREADS >> pwl;
+        int tx = (int)threadIdx.x & ((1 << txl) - 1), ty = (int)threadIdx.x >> txl;
+        int dx = rows ? 1 << txl : 0, dy = rows ? 0 : THREADS >> pwl;
+        if (PERIOD > 0) {
+            if (rows) {
+                tx = (tx / PERIOD) * (SPT * PERIOD) + tx % PERIOD;
+                dx = PERIOD;
+            } else {
+                ty = (ty / PERIOD) * (SPT * PERIOD) + ty % PERIOD;
+                dy = PERIOD;
+            }
+        }
         const int fsp = (fs + 3) & ~3;
         int sxv[SPT], rxv[SPT], syv[SPT], ryv[SPT];
 #pragma unroll
@@ -668,6 +769,23 @@ __device__ __forceinline__ void strip_block(const StripArgs& a, const FrameSet& 
                 meta[k] = meta[0];
             same = same && meta[k].w == meta[0].w;
             vec = vec && meta[k].wstride != 0 && (meta[k].wstride & 3) == 0 && meta[k].wstride == meta[0].wstride;
+        }
+        if (PERIOD > 0 && FSC > 0 && vec && same && live == (1u << SPT) - 1u) {
+            // adjacent same-phase samples with regularly advancing origins: overlapping windows, every value read once
+            bool run = true;
+#pragma unroll
+            for (int k = 1; k < SPT; ++k)
+                run = run && (rows ? (meta[k].sy == meta[0].sy && meta[k].sx == meta[0].sx + k * STEP)
+                                   : (meta[k].sx == meta[0].sx && meta[k].sy == meta[0].sy + k * STEP));
+            if (run && rows) {
+                strip_run_rows<T, (FSC > 0 ? FSC : 4), SPT, (STEP > 0 ? STEP : 1)>(fsx, meta, (int)plane, tile, fw, sx_lo, sy_lo);
+                return;
+            }
+            if (run && STEP == 1 && SPT == 4 && FSC <= 9) { // the weight-row window of larger windows does not fit the registers
+                strip_run_cols<T, (FSC > 0 && FSC <= 9 ? FSC : 4), 4>(fsx, reinterpret_cast<const StripMeta(&)[4]>(meta), (int)plane, tile, fw,
+                                                                      sx_lo, sy_lo);
+                return;
+            }
         }
         if (vec) {
             if (same)

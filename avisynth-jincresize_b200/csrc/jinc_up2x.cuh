@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(UP_THREADS, (FS >= 13 ? 4 : 6))
     unsigned role_id;
     if (block_role(blockIdx.x, (unsigned)a.strip_blocks, a.strip_shift, role_id)) {
         // ---------------- strip role
-        strip_block<T, FS, UP_THREADS, UP_STRIP_SPT>(a.st, a.fr, role_id, reinterpret_cast<float*>(smem_raw));
+        strip_block<T, FS, UP_THREADS, UP_STRIP_SPT, 2, 1>(a.st, a.fr, role_id, reinterpret_cast<float*>(smem_raw)); // samples two outputs apart: origins one apart
         return;
     }
 
