@@ -344,13 +344,13 @@ bool axis_periodic(const std::vector<int32_t>& start, const std::vector<int32_t>
     return false;
 }
 
-// Piecewise-periodic structure of one axis over the interior run [a,b): the smallest P (cell = P outputs) for which
+// Piecewise-periodic structure of one axis over the interior run [a,b): the smallest P <= 16 (cell = P outputs) for which
 // start[i+P] - start[i] is one constant Q almost everywhere, then chunks of up to N cells inside which every residue
 // keeps its rank and its origins advance by exactly Q per cell.  False when the axis has no such structure or the
 // chunks come out too short to be worth a thread each.
 bool build_cells_axis(const std::vector<int32_t>& start, const std::vector<int32_t>& rank, int a, int b, int N, CellsAxis& out)
 {
-    for (int P = 1; P <= 8; ++P) {
+    for (int P = 1; P <= 16; ++P) { // 9:4 (480p -> 1080p) has P = 9
         const int n = b - a - P;
         if (n < 8 * P)
             continue;

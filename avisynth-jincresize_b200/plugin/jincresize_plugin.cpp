@@ -22,7 +22,8 @@
 //     instead, and is cheap here because instances created with identical arguments share ONE GPU filter (tables,
 //     slots, streams) through a process-wide reference-counted cache.
 // Environment: JINCRESIZE_B200_DEVICES ("0,1,..." or "all"; default: device 0), JINCRESIZE_B200_SLOTS,
-// JINCRESIZE_B200_HOSTREG=0 (never page-lock the host's frame buffers), JINCRESIZE_B200_CHROMALOC, JINCRESIZE_B200_MTMODE.
+// JINCRESIZE_B200_HOSTREG=0 (never page-lock the host's frame buffers), JINCRESIZE_B200_BANDS=n (cut every frame into n row
+// bands over the filter's GPUs: latency of single large frames), JINCRESIZE_B200_CHROMALOC, JINCRESIZE_B200_MTMODE.
 #include <algorithm>
 #include <cctype>
 #include <cstdlib>
@@ -39,6 +40,7 @@ namespace {
 struct Instance {
     jinc_filter* filter = nullptr;
     std::string key; // entry of the shared-filter cache
+    int bands = 0;   // > 0: every frame is cut into this many row bands (JINCRESIZE_B200_BANDS)
     int n_planes = 0;
     bool rgb = false;
     bool writes_chromaloc = false;
@@ -112,7 +114,10 @@ AVS_VideoFrame* AVSC_CC get_frame(AVS_FilterInfo* fi, int n)
         fr.dst[i] = avs_get_write_ptr_p(dst, ids[i]);
         fr.dst_pitch[i] = avs_get_pitch_p(dst, ids[i]);
     }
-    if (jinc_filter_process(inst->filter, &fr) != JINC_OK) {
+    // whole frames by default (frames overlap each other across Prefetch threads); row bands overlap the transfers and
+    // kernels of ONE frame, and spread it over the filter's GPUs, which is what a host without Prefetch wants
+    const int rc = inst->bands > 0 ? jinc_filter_process_bands(inst->filter, &fr, inst->bands) : jinc_filter_process(inst->filter, &fr);
+    if (rc != JINC_OK) {
         // the text lives in the environment's string heap: concurrent failing callers never share storage
         const std::string msg = std::string("JincResize: ") + jinc_last_error();
         fi->error = avs_save_string(fi->env, msg.c_str(), -1);
@@ -301,6 +306,8 @@ AVS_Value AVSC_CC create_jincresize(AVS_ScriptEnvironment* env, AVS_Value args, 
     auto* inst = new Instance();
     inst->filter = filter;
     inst->key = key;
+    if (const char* b = getenv("JINCRESIZE_B200_BANDS"))
+        inst->bands = std::max(0, std::min(atoi(b), 256));
     inst->n_planes = p.n_planes;
     inst->rgb = avs_is_rgb(vi) != 0;
     inst->writes_chromaloc = subsampled_family;

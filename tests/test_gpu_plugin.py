@@ -150,6 +150,27 @@ def test_identical_instances_share_one_gpu_filter(envs, monkeypatch):
     assert capi.live_filters() == n0
 
 
+def test_plugin_row_bands_env(envs, monkeypatch):
+    """JINCRESIZE_B200_BANDS=n: get_frame cuts every frame into n row bands; frames are byte-identical to whole frames."""
+    from minihost import avs_host as ah
+
+    ours, _ = envs
+    fmt, w, h = ah.YUV420P8, 480, 270
+    frames = [make_planes(fmt, w, h, "noise", seed=s) for s in range(2)]
+    src = ours.source(fmt, w, h, frames)
+    whole = ours.invoke("Jinc36Resize", src, 960, 540, cplace="MPEG2")
+    monkeypatch.setenv("JINCRESIZE_B200_BANDS", "3")
+    banded = ours.invoke("Jinc36Resize", src, 960, 540, cplace="MPEG2")
+    monkeypatch.delenv("JINCRESIZE_B200_BANDS")
+    for n in range(2):
+        a, _ = whole.get_frame(n)
+        b, _ = banded.get_frame(n)
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+    for c in (whole, banded, src):
+        c.release()
+
+
 def test_prefetch_threads_share_one_instance(envs):
     """Frame-parallel get_frame from 6 host threads on ONE instance (MT_NICE_FILTER): every frame still correct."""
     from minihost import avs_host as ah
