@@ -130,6 +130,31 @@ struct CellsPlan {
     CellsAxis ax[2];
 };
 
+// Strip plan (whole-frame launches of a fast path; jinc_resize.cu builds it once per table, jinc_resample.cuh runs it).
+// The border strips are cut into the same patches as at launch time, but everything a strip block used to derive in its
+// prologue -- the patch's source footprint, every thread's samples, their window offsets, weight blocks and the way
+// they are accumulated -- is worked out once on the host, and the few distinct weight blocks of a patch are packed
+// next to each other so the block copies them into shared memory with its footprint.
+struct StripPlanPatch {
+    int32_t sx_lo, sy_lo, fw, fh; // source footprint of the patch
+    uint32_t magic;               // floor(e / fw) = umulhi(e, magic)
+    int32_t n_wb;                 // weight blocks staged in shared memory; < 0: patch not planned (prologue path)
+    uint32_t wdata_off;           // first float of the patch's packed weight blocks in StripPlan::d_wdata
+    uint32_t tile_floats;         // shared-memory offset of the staged blocks (footprint rounded up to 16 bytes)
+};
+enum { JINC_SK_NONE = 0, JINC_SK_RUN_ROWS, JINC_SK_RUN_COLS, JINC_SK_FUSED_SHARED, JINC_SK_FUSED_SEP, JINC_SK_PER_SAMPLE };
+struct StripPlan {
+    bool ok = false;
+    int threads = 0, spt = 0;
+    unsigned n_patches = 0;  // per plane; equals what set_strip_rects yields for the whole-frame rectangles
+    unsigned n_planned = 0;  // patches that run from the plan
+    StripPlanPatch* d_patches = nullptr;
+    // [patch][sample k][thread]: .x = x | y << 16, .y = offset of the window origin in the staged footprint,
+    // .z = float offset of the weight block among the staged ones, .w (sample 0) = kind | live mask << 8
+    uint4* d_threads = nullptr;
+    float* d_wdata = nullptr;
+};
+
 struct jinc_table {
     jinc_ctx* ctx = nullptr;
     jinc_table_params params{};
@@ -147,6 +172,8 @@ struct jinc_table {
     int32_t* d_border_block = nullptr; // [bgeom.total] slot -> class block (null: per-slot weights above)
     float* d_border_wb = nullptr;      // [n_border_blocks][fs][fsp], fsp = fs rounded up to 4 (16-byte rows, pad = 0)
     int n_border_blocks = 0;
+    std::vector<int32_t> h_border_block; // host copy of the slot -> class map (strip plan)
+    StripPlan strip_plan;
     // host mirrors of the small per-axis arrays (for planning and introspection)
     std::vector<int32_t> h_start[2], h_phase[2], h_rank[2], h_qint[2];
     std::vector<uint8_t> h_border[2];
@@ -167,6 +194,8 @@ void jinc_lut_build_host(double radius, double blur, double* lut);
 int jinc_table_build_device(jinc_table* t, const double* lut);
 
 // jinc_resize.cu
+int jinc_build_strip_plan(jinc_table* t); // after plan_fast_paths and the weight blocks; no plan is not an error
+void jinc_free_strip_plan(jinc_table* t);
 int jinc_launch_resize(jinc_ctx* ctx, const jinc_table* t, int sample_bytes, float peak, const void* d_src,
                        ptrdiff_t src_pitch, void* d_dst, ptrdiff_t dst_pitch, int y_begin, int y_end,
                        cudaStream_t stream, int* launches);

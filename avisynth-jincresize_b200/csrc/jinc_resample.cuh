@@ -35,6 +35,7 @@
 #include <algorithm>
 #include <cstring>
 #include <type_traits>
+#include <vector>
 
 #include "jinc_internal.h"
 #include "jinc_weights.cuh"
@@ -229,6 +230,11 @@ struct StripArgs {
     unsigned blocks_per_plane; // = patch_begin[4]; the grid holds this many strip blocks per plane
     unsigned blocks_per_plane_magic, patches_x_magic[4]; // div_magic of the two divisors above
     unsigned smem_floats;      // shared memory a strip block may use to stage its source footprint (0: none)
+    // whole-frame launches of a table with a strip plan (jinc_internal.h: StripPlan), else null: the patches above are
+    // then the plan's, and a strip block reads its descriptors instead of deriving them
+    const StripPlanPatch* plan_patches;
+    const uint4* plan_threads;
+    const float* plan_wdata;
 };
 
 struct FrameSet {
@@ -803,6 +809,378 @@ __device__ __forceinline__ void strip_block(const StripArgs& a, const FrameSet& 
             strip_sample_staged<T, FSC>(a, fsx, meta[k], (int)plane, tile, fw, sx_lo, sy_lo);
         else
             strip_sample<T, FSC>(a, fsx, meta[k].x, meta[k].y, (int)plane);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ planned strip blocks
+//
+// The same patches and the same thread-to-sample mapping as strip_block, but run from the table's StripPlan: the patch
+// descriptor gives the footprint, one 16-byte record per thread (and sample) gives the output coordinates, the window's
+// offset in the staged footprint, the weight block and how the thread's samples are accumulated.  The distinct weight
+// blocks of the patch (a handful: one per border row or column and phase) are copied into shared memory next to the
+// footprint, so the accumulation loops read nothing from global memory.  Every sample is accumulated in the same tap
+// order as in strip_block (row-major, one fused multiply-add per tap): both paths give identical bits.
+
+template <typename T, int FSC, int SPT, int STEP>
+__device__ __forceinline__ void plan_run_rows(const float* __restrict__ s, int fw, const float* __restrict__ w, T* __restrict__ o, int xstep,
+                                              float peak)
+{
+    constexpr int FSP = (FSC + 3) & ~3, SEG = FSC + (SPT - 1) * STEP;
+    float acc[SPT];
+#pragma unroll
+    for (int k = 0; k < SPT; ++k)
+        acc[k] = 0.f;
+#pragma unroll(FSC <= 9 ? FSC : 1)
+    for (int ly = 0; ly < FSC; ++ly) {
+        float seg[SEG], wr[FSP];
+#pragma unroll
+        for (int q = 0; q < FSP / 4; ++q) {
+            const float4 t = *reinterpret_cast<const float4*>(w + ly * FSP + 4 * q);
+            wr[4 * q] = t.x;
+            wr[4 * q + 1] = t.y;
+            wr[4 * q + 2] = t.z;
+            wr[4 * q + 3] = t.w;
+        }
+#pragma unroll
+        for (int i = 0; i < SEG; ++i)
+            seg[i] = s[ly * fw + i];
+#pragma unroll
+        for (int lx = 0; lx < FSC; ++lx)
+#pragma unroll
+            for (int k = 0; k < SPT; ++k)
+                acc[k] = fmaf(seg[lx + k * STEP], wr[lx], acc[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < SPT; ++k)
+        o[k * xstep] = finish<T>(acc[k], peak);
+}
+
+// adjacent same-phase outputs of one column, window origins one row apart: a staged row of FSC values feeds up to four
+// outputs, each with its own weight row (read from shared memory when it is needed)
+template <typename T, int FSC>
+__device__ __forceinline__ void plan_run_cols(const float* __restrict__ s, int fw, const float* __restrict__ w, T* __restrict__ o, long long ystep,
+                                              float peak)
+{
+    constexpr int FSP = (FSC + 3) & ~3, SPT = 4;
+    float acc[SPT];
+#pragma unroll
+    for (int k = 0; k < SPT; ++k)
+        acc[k] = 0.f;
+#pragma unroll
+    for (int r = 0; r < FSC + SPT - 1; ++r) {
+        float seg[FSC];
+#pragma unroll
+        for (int i = 0; i < FSC; ++i)
+            seg[i] = s[r * fw + i];
+#pragma unroll
+        for (int k = 0; k < SPT; ++k) {
+            const int ly = r - k; // weight row of output k (a constant after unrolling)
+            if (ly >= 0 && ly < FSC) {
+                float wr[FSP];
+#pragma unroll
+                for (int q = 0; q < FSP / 4; ++q) {
+                    const float4 t = *reinterpret_cast<const float4*>(w + ly * FSP + 4 * q);
+                    wr[4 * q] = t.x;
+                    wr[4 * q + 1] = t.y;
+                    wr[4 * q + 2] = t.z;
+                    wr[4 * q + 3] = t.w;
+                }
+#pragma unroll
+                for (int lx = 0; lx < FSC; ++lx)
+                    acc[k] = fmaf(seg[lx], wr[lx], acc[k]);
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < SPT; ++k)
+        o[k * ystep] = finish<T>(acc[k], peak);
+}
+
+// SPT samples with separate windows, interleaved; SHARED: one weight block for all of them
+template <typename T, int FSC, int SPT, bool SHARED>
+__device__ __forceinline__ void plan_fused(const uint4 (&r)[SPT], unsigned live, const float* __restrict__ tile, int fw,
+                                           const float* __restrict__ wsm, T* __restrict__ dst, long long dp, float peak)
+{
+    constexpr int FSP = (FSC + 3) & ~3, NW = SHARED ? 1 : SPT;
+    const float* __restrict__ s[SPT];
+    const float* __restrict__ w[NW];
+    float acc[SPT];
+#pragma unroll
+    for (int k = 0; k < SPT; ++k) {
+        s[k] = tile + (int)r[k].y;
+        acc[k] = 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < NW; ++k)
+        w[k] = wsm + r[k].z;
+#pragma unroll 1
+    for (int ly = 0; ly < FSC; ++ly) {
+#pragma unroll
+        for (int q = 0; q < FSP / 4; ++q) {
+            float4 t[NW];
+#pragma unroll
+            for (int k = 0; k < NW; ++k)
+                t[k] = *reinterpret_cast<const float4*>(w[k] + 4 * q);
+            const int lx = 4 * q;
+#pragma unroll
+            for (int k = 0; k < SPT; ++k) {
+                const float4& tk = t[SHARED ? 0 : k];
+                acc[k] = fmaf(s[k][lx], tk.x, acc[k]);
+                if (lx + 1 < FSC)
+                    acc[k] = fmaf(s[k][lx + 1], tk.y, acc[k]);
+                if (lx + 2 < FSC)
+                    acc[k] = fmaf(s[k][lx + 2], tk.z, acc[k]);
+                if (lx + 3 < FSC)
+                    acc[k] = fmaf(s[k][lx + 3], tk.w, acc[k]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < NW; ++k)
+            w[k] += FSP;
+#pragma unroll
+        for (int k = 0; k < SPT; ++k)
+            s[k] += fw;
+    }
+#pragma unroll
+    for (int k = 0; k < SPT; ++k)
+        if (live & (1u << k))
+            dst[(long long)(r[k].x >> 16) * dp + (r[k].x & 0xffffu)] = finish<T>(acc[k], peak);
+}
+
+// the prologue path as a real function: planned launches call it for the few patches the plan leaves out
+template <typename T, int FSC, int THREADS, int SPT, int PERIOD, int STEP>
+__device__ __noinline__ void strip_block_unplanned(const StripArgs& a, const FrameSet& fsx, unsigned sb, float* __restrict__ tile)
+{
+    strip_block<T, FSC, THREADS, SPT, PERIOD, STEP>(a, fsx, sb, tile);
+}
+
+template <typename T, int FSC, int THREADS, int SPT, int PERIOD, int STEP>
+__device__ __forceinline__ void strip_block_planned(const StripArgs& a, const FrameSet& fsx, unsigned sb, float* __restrict__ tile)
+{
+    static_assert(FSC > 0, "planned strips need a compile-time window size");
+    constexpr int FSP = (FSC + 3) & ~3, WB4 = FSC * FSP / 4;
+    const unsigned plane = div_by(sb, a.blocks_per_plane_magic);
+    const unsigned pid = sb - plane * a.blocks_per_plane;
+    const int4* __restrict__ pd = reinterpret_cast<const int4*>(a.plan_patches + pid);
+    const int4 pb = __ldg(pd + 1); // magic, n_wb, wdata_off, tile_floats
+    if (pb.y < 0) {
+        strip_block_unplanned<T, FSC, THREADS, SPT, PERIOD, STEP>(a, fsx, sb, tile);
+        return;
+    }
+    const int4 pa = __ldg(pd); // sx_lo, sy_lo, fw, fh
+    const uint4* __restrict__ recs = a.plan_threads + (size_t)pid * (unsigned)(SPT * THREADS) + threadIdx.x;
+    const uint4 r0 = __ldg(recs);
+    const PlanePtrs& pp = frame_ptrs(fsx);
+    const int fw = pa.z;
+    float* __restrict__ wsm = tile + pb.w;
+    {
+        // the patch's weight blocks (packed in plan order: a straight copy) and its source footprint, converted to float.
+        // The first round of both is loaded before anything is stored: one memory round trip for the usual patch.
+        const float4* __restrict__ wsrc = reinterpret_cast<const float4*>(a.plan_wdata + (unsigned)pb.z);
+        float4* __restrict__ wdst = reinterpret_cast<float4*>(wsm);
+        const int nw4 = pb.y * WB4;
+        const int pitch = (int)pp.src_pitch[plane];
+        const T* __restrict__ src = static_cast<const T*>(pp.src[plane]) + (long long)pa.y * pitch + pa.x;
+        const unsigned n = (unsigned)(fw * pa.w), magic = (unsigned)pb.x;
+        float4 wv[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+            wv[u] = __ldg(wsrc + min((int)threadIdx.x + u * THREADS, max(nw4 - 1, 0)));
+        for (unsigned e0 = threadIdx.x; e0 < n; e0 += 4 * THREADS) {
+            T v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { // all four loads are issued before the first conversion
+                const unsigned e = min(e0 + u * THREADS, n - 1);
+                const unsigned row = __umulhi(e, magic);
+                v[u] = __ldg(src + (int)(row * (unsigned)pitch + (e - row * (unsigned)fw)));
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (e0 + u * THREADS < n)
+                    tile[e0 + u * THREADS] = sample_to_float(v[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+            if ((int)threadIdx.x + u * THREADS < nw4)
+                wdst[threadIdx.x + u * THREADS] = wv[u];
+        for (int i = threadIdx.x + 2 * THREADS; i < nw4; i += THREADS)
+            wdst[i] = __ldg(wsrc + i);
+    }
+    __syncthreads();
+    const unsigned kind = r0.w & 0xffu, live = r0.w >> 8;
+    if (kind == JINC_SK_NONE)
+        return;
+    T* __restrict__ dst = static_cast<T*>(pp.dst[plane]);
+    const long long dp = pp.dst_pitch[plane];
+    if (PERIOD > 0 && kind == JINC_SK_RUN_ROWS) {
+        plan_run_rows<T, FSC, SPT, (STEP > 0 ? STEP : 1)>(tile + (int)r0.y, fw, wsm + r0.z, dst + (long long)(r0.x >> 16) * dp + (r0.x & 0xffffu),
+                                                           PERIOD, fsx.peak);
+        return;
+    }
+    if constexpr (PERIOD > 0 && STEP == 1 && SPT == 4 && FSC <= 9) {
+        if (kind == JINC_SK_RUN_COLS) {
+            plan_run_cols<T, FSC>(tile + (int)r0.y, fw, wsm + r0.z, dst + (long long)(r0.x >> 16) * dp + (r0.x & 0xffffu), (long long)PERIOD * dp,
+                                  fsx.peak);
+            return;
+        }
+    }
+    uint4 r[SPT];
+    r[0] = r0;
+#pragma unroll
+    for (int k = 1; k < SPT; ++k)
+        r[k] = __ldg(recs + k * THREADS);
+    if (kind == JINC_SK_FUSED_SHARED) {
+        plan_fused<T, FSC, SPT, true>(r, live, tile, fw, wsm, dst, dp, fsx.peak);
+    } else if (kind == JINC_SK_FUSED_SEP) {
+        plan_fused<T, FSC, SPT, false>(r, live, tile, fw, wsm, dst, dp, fsx.peak);
+    } else { // JINC_SK_PER_SAMPLE: no vector-readable block (per-pixel border weights): straight from global memory
+#pragma unroll 1
+        for (int k = 0; k < SPT; ++k)
+            if (live & (1u << k))
+                strip_sample<T, FSC>(a, fsx, (int)(r[k].x & 0xffffu), (int)(r[k].x >> 16), (int)plane);
+    }
+}
+
+// Host side of the plan: the thread-to-sample mapping and the choice of accumulation path of strip_block, evaluated for
+// every thread of every patch.  `a` holds the whole-frame rectangles (set_strip_rects).  Returns the patch descriptors,
+// the thread records and the (sel << 31 | block) list of the weight blocks to pack, in patch order.
+struct StripPlanHost {
+    std::vector<StripPlanPatch> patches;
+    std::vector<uint4> recs;
+    std::vector<uint32_t> wlist;
+    unsigned n_planned = 0;
+};
+
+inline void build_strip_plan_host(const jinc_table* t, const StripArgs& a, int THREADS, int SPT, int PERIOD, int STEP, StripPlanHost& out)
+{
+    const int fs = t->sc.fs, fsp = (fs + 3) & ~3, wbf = fs * fsp;
+    const std::vector<int32_t>&start_x = t->h_start[0], &start_y = t->h_start[1], &rank_x = t->h_rank[0], &rank_y = t->h_rank[1];
+    const bool have_classes = !t->h_border_block.empty();
+    const bool phase_padded = t->d_weights_p != nullptr;
+    const int phase_stride = phase_padded ? fsp : fs;
+    const int n_rank_x = t->ax[0].n_rank;
+    int spt_l2 = 0;
+    while ((1 << spt_l2) < SPT)
+        ++spt_l2;
+    const unsigned total = a.blocks_per_plane;
+    out.patches.assign(total, StripPlanPatch{});
+    out.recs.assign((size_t)total * SPT * THREADS, make_uint4(0, 0, 0, 0));
+    out.wlist.clear();
+    out.n_planned = 0;
+    struct Meta {
+        int x, y, sx, sy, wstride;
+        uint32_t wkey; // sel << 31 | block; only meaningful when wstride != 0
+    };
+    std::vector<Meta> meta((size_t)SPT);
+    std::vector<uint32_t> keys; // distinct weight blocks of the patch, in first-use order
+    for (unsigned pid = 0; pid < total; ++pid) {
+        const int r = (int)(pid >= a.patch_begin[1]) + (int)(pid >= a.patch_begin[2]) + (int)(pid >= a.patch_begin[3]);
+        const unsigned lp = pid - a.patch_begin[r];
+        const unsigned pyi = lp / a.patches_x[r], pxi = lp - pyi * a.patches_x[r];
+        const int pwl = a.pw_log2[r];
+        const int ox0 = a.rect[r].x0 + (int)(pxi << pwl), oy0 = a.rect[r].y0 + (int)pyi * ((THREADS * SPT) >> pwl);
+        const int nx = std::min(1 << pwl, a.rect[r].x1 - ox0), ny = std::min((THREADS * SPT) >> pwl, a.rect[r].y1 - oy0);
+        const int sx_lo = start_x[ox0], sy_lo = start_y[oy0];
+        const int fw = start_x[ox0 + nx - 1] + fs - sx_lo, fh = start_y[oy0 + ny - 1] + fs - sy_lo;
+        StripPlanPatch& pd = out.patches[pid];
+        pd.sx_lo = sx_lo;
+        pd.sy_lo = sy_lo;
+        pd.fw = fw;
+        pd.fh = fh;
+        pd.magic = 0xFFFFFFFFu / (unsigned)fw + 1u;
+        pd.n_wb = -1;
+        pd.wdata_off = 0;
+        pd.tile_floats = ((unsigned)(fw * fh) + 3u) & ~3u;
+        if ((long long)fw * fh > (long long)a.smem_floats)
+            continue; // the footprint is not staged: prologue path
+        const bool rows = a.row_mode[r] != 0;
+        const int txl = rows ? pwl - spt_l2 : pwl;
+        keys.clear();
+        uint4* prec = out.recs.data() + (size_t)pid * SPT * THREADS;
+        for (int tid = 0; tid < THREADS; ++tid) {
+            int tx = tid & ((1 << txl) - 1), ty = tid >> txl;
+            int dx = rows ? 1 << txl : 0, dy = rows ? 0 : THREADS >> pwl;
+            if (PERIOD > 0) {
+                if (rows) {
+                    tx = (tx / PERIOD) * (SPT * PERIOD) + tx % PERIOD;
+                    dx = PERIOD;
+                } else {
+                    ty = (ty / PERIOD) * (SPT * PERIOD) + ty % PERIOD;
+                    dy = PERIOD;
+                }
+            }
+            unsigned live = 0;
+            for (int k = 0; k < SPT; ++k) {
+                const int lx = tx + k * dx, ly = ty + k * dy;
+                if (lx >= nx || ly >= ny)
+                    continue;
+                live |= 1u << k;
+                Meta& m = meta[k];
+                m.x = ox0 + lx;
+                m.y = oy0 + ly;
+                m.sx = start_x[m.x];
+                m.sy = start_y[m.y];
+                const int rx = rank_x[m.x], ry = rank_y[m.y];
+                if (rx >= 0 && ry >= 0) {
+                    m.wkey = (uint32_t)(ry * n_rank_x + rx);
+                    m.wstride = phase_stride;
+                } else if (have_classes) {
+                    m.wkey = 0x80000000u | (uint32_t)t->h_border_block[(size_t)jinc_border_slot(t->bgeom, m.x, m.y)];
+                    m.wstride = fsp;
+                } else {
+                    m.wkey = 0;
+                    m.wstride = 0;
+                }
+            }
+            unsigned kind = JINC_SK_NONE;
+            if (live & 1u) { // live samples are a prefix
+                bool same = true, vec = true;
+                for (int k = 0; k < SPT; ++k) {
+                    if (!(live & (1u << k)))
+                        meta[k] = meta[0];
+                    same = same && meta[k].wstride == meta[0].wstride && (meta[k].wstride == 0 || meta[k].wkey == meta[0].wkey);
+                    vec = vec && meta[k].wstride != 0 && (meta[k].wstride & 3) == 0 && meta[k].wstride == meta[0].wstride;
+                }
+                kind = JINC_SK_PER_SAMPLE;
+                if (SPT > 1 && vec) {
+                    kind = same ? JINC_SK_FUSED_SHARED : JINC_SK_FUSED_SEP;
+                    if (PERIOD > 0 && same && live == (1u << SPT) - 1u) {
+                        bool run = true;
+                        for (int k = 1; k < SPT; ++k)
+                            run = run && (rows ? (meta[k].sy == meta[0].sy && meta[k].sx == meta[0].sx + k * STEP)
+                                               : (meta[k].sx == meta[0].sx && meta[k].sy == meta[0].sy + k * STEP));
+                        if (run && rows)
+                            kind = JINC_SK_RUN_ROWS;
+                        else if (run && STEP == 1 && SPT == 4 && fs <= 9)
+                            kind = JINC_SK_RUN_COLS;
+                    }
+                }
+                for (int k = 0; k < SPT; ++k) {
+                    const Meta& m = meta[k];
+                    uint32_t slot = 0;
+                    if (kind != JINC_SK_PER_SAMPLE) {
+                        size_t j = 0;
+                        while (j < keys.size() && keys[j] != m.wkey)
+                            ++j;
+                        if (j == keys.size())
+                            keys.push_back(m.wkey);
+                        slot = (uint32_t)j * (uint32_t)wbf;
+                    }
+                    prec[(size_t)k * THREADS + tid] = make_uint4((uint32_t)m.x | ((uint32_t)m.y << 16), (uint32_t)((m.sy - sy_lo) * fw + (m.sx - sx_lo)),
+                                                                 slot, k == 0 ? (kind | (live << 8)) : 0u);
+                }
+            }
+        }
+        if ((unsigned long long)pd.tile_floats + (unsigned long long)keys.size() * wbf > a.smem_floats) {
+            // the patch's weight blocks do not fit next to its footprint (corner patches of wide windows): prologue path
+            for (size_t i = 0; i < (size_t)SPT * THREADS; ++i)
+                prec[i] = make_uint4(0, 0, 0, 0);
+            continue;
+        }
+        pd.n_wb = (int32_t)keys.size();
+        pd.wdata_off = (uint32_t)(out.wlist.size() * (size_t)wbf);
+        out.wlist.insert(out.wlist.end(), keys.begin(), keys.end());
+        ++out.n_planned;
     }
 }
 

@@ -5,6 +5,8 @@
 // are described once, in jinc_resample.cuh; the kernel families live in jinc_up2x.cuh (exact 2x), jinc_down.cuh
 // (integer-ratio downscale and the exactly periodic 2:3 path) and jinc_cells.cuh (rational ratios with piecewise-periodic
 // phases), each instantiated once per sample type in its own translation unit so that the build runs in parallel.
+#include <cstdlib>
+
 #include "jinc_resample.cuh"
 
 using namespace jinc_rs;
@@ -296,6 +298,13 @@ int launch_typed(const jinc_table* t, const FrameSet& fr, int n_frames, int y_be
             a.st = sa;
             const long long strip_blocks =
                 set_strip_rects(a.st, rects, n_rects, UP_THREADS * UP_STRIP_SPT, UP_STRIP_MAX_PW, up2x_smem_bytes(t->sc.fs)) * fr.n_planes;
+            const StripPlan& sp = t->strip_plan;
+            if (sp.ok && n_rects == 4 && y_begin == 0 && y_end == t->sc.dst_h && a.st.blocks_per_plane == sp.n_patches) {
+                // whole frame: the strip blocks run from the table's plan (same patches, nothing derived per block)
+                a.st.plan_patches = sp.d_patches;
+                a.st.plan_threads = sp.d_threads;
+                a.st.plan_wdata = sp.d_wdata;
+            }
             a.src_w = t->sc.src_w;
             a.src_h = t->sc.src_h;
             a.x0 = u.x0;
@@ -482,6 +491,17 @@ int launch_typed(const jinc_table* t, const FrameSet& fr, int n_frames, int y_be
     return JINC_OK;
 }
 
+// packs the weight blocks a plan names (sel << 31 | block) next to each other: one thread block per weight block
+__global__ void __launch_bounds__(128) gather_blocks_kernel(float* __restrict__ out, const uint32_t* __restrict__ list, const float* __restrict__ phase_blocks,
+                                                            const float* __restrict__ border_blocks, int block_floats)
+{
+    const uint32_t e = list[blockIdx.x];
+    const float* __restrict__ src = ((e >> 31) ? border_blocks : phase_blocks) + (size_t)(e & 0x7fffffffu) * block_floats;
+    float* __restrict__ dst = out + (size_t)blockIdx.x * block_floats;
+    for (int i = threadIdx.x; i < block_floats; i += blockDim.x)
+        dst[i] = src[i];
+}
+
 int check_and_fill(PlanePtrs& pl, int sample_bytes, int n_planes, const void* const* d_src, const ptrdiff_t* src_pitch,
                    void* const* d_dst, const ptrdiff_t* dst_pitch)
 {
@@ -522,6 +542,70 @@ int dispatch(const jinc_table* t, int sample_bytes, const FrameSet& fr, int n_fr
 } // namespace
 
 size_t jinc_plane_ptrs_size() { return sizeof(PlanePtrs); }
+
+void jinc_free_strip_plan(jinc_table* t)
+{
+    StripPlan& sp = t->strip_plan;
+    cudaFree(sp.d_patches);
+    cudaFree(sp.d_threads);
+    cudaFree(sp.d_wdata);
+    sp = StripPlan{};
+}
+
+// Strip plan of the exact-2x tables (the BASELINE upscale configs): see StripPlan in jinc_internal.h.  Tables without a
+// plan (other kernel families, planes wider than the 16-bit coordinates of a record) keep the prologue path.
+int jinc_build_strip_plan(jinc_table* t)
+{
+    StripPlan& sp = t->strip_plan;
+    sp = StripPlan{};
+    const char* off = getenv("JINCRESIZE_B200_STRIP_PLAN");
+    if (off && off[0] == '0')
+        return JINC_OK;
+    if (t->fast_path != JINC_PATH_UP2X || !up2x_supported(t->sc.fs) || t->sc.dst_w > 65535 || t->sc.dst_h > 65535)
+        return JINC_OK;
+    const int fs = t->sc.fs, wbf = fs * ((fs + 3) & ~3);
+    const Up2xPlan& u = t->up2x;
+    const int W = t->sc.dst_w, H = t->sc.dst_h, fy0 = u.y0, fy1 = u.y0 + 2 * u.ncy;
+    const Rect rects[4] = {Rect{0, 0, W, fy0}, Rect{0, fy1, W, H}, Rect{0, fy0, t->ix0, fy1}, Rect{t->ix1, fy0, W, fy1}}; // as launch_typed
+    StripArgs sa;
+    fill_strip_args(t, sa);
+    if (set_strip_rects(sa, rects, 4, UP_THREADS * UP_STRIP_SPT, UP_STRIP_MAX_PW, up2x_smem_bytes(fs)) == 0)
+        return JINC_OK;
+    StripPlanHost h;
+    build_strip_plan_host(t, sa, UP_THREADS, UP_STRIP_SPT, 2, 1, h);
+    if (h.n_planned == 0)
+        return JINC_OK;
+    cudaStream_t st = t->ctx->stream;
+    JINC_CUDA(cudaSetDevice(t->ctx->device));
+    JINC_CUDA(cudaMalloc(reinterpret_cast<void**>(&sp.d_patches), h.patches.size() * sizeof(StripPlanPatch)));
+    JINC_CUDA(cudaMalloc(reinterpret_cast<void**>(&sp.d_threads), h.recs.size() * sizeof(uint4)));
+    JINC_CUDA(cudaMalloc(reinterpret_cast<void**>(&sp.d_wdata), (h.wlist.size() + 1) * wbf * sizeof(float)));
+    JINC_CUDA(cudaMemcpyAsync(sp.d_patches, h.patches.data(), h.patches.size() * sizeof(StripPlanPatch), cudaMemcpyHostToDevice, st));
+    JINC_CUDA(cudaMemcpyAsync(sp.d_threads, h.recs.data(), h.recs.size() * sizeof(uint4), cudaMemcpyHostToDevice, st));
+    if (!h.wlist.empty()) {
+        uint32_t* d_list = nullptr;
+        JINC_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_list), h.wlist.size() * sizeof(uint32_t)));
+        cudaError_t e = cudaMemcpyAsync(d_list, h.wlist.data(), h.wlist.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) {
+            gather_blocks_kernel<<<(unsigned)h.wlist.size(), 128, 0, st>>>(sp.d_wdata, d_list, t->d_weights_p ? t->d_weights_p : t->d_weights,
+                                                                           t->d_border_wb, wbf);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess)
+            e = cudaStreamSynchronize(st); // the host vectors and the list are temporaries
+        cudaFree(d_list);
+        if (e != cudaSuccess)
+            return jinc_fail(JINC_E_CUDA, "strip plan: %s", cudaGetErrorString(e));
+    } else {
+        JINC_CUDA(cudaStreamSynchronize(st));
+    }
+    sp.threads = UP_THREADS;
+    sp.spt = UP_STRIP_SPT;
+    sp.n_patches = (unsigned)h.patches.size();
+    sp.n_planned = h.n_planned;
+    sp.ok = true;
+    return JINC_OK;
+}
 
 int jinc_pack_plane_ptrs(void* out, int sample_bytes, int n_planes, const void* const* d_src, const ptrdiff_t* src_pitch,
                          void* const* d_dst, const ptrdiff_t* dst_pitch)

@@ -732,8 +732,9 @@ int jinc_table_build_device(jinc_table* t, const double* lut)
                 JINC_CUDA(cudaMemcpyAsync(t->d_border_block, block_of.data(), block_of.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
                 border_class_kernel<<<(unsigned)reps.size(), 128, 0, st>>>(ba, d_reps, t->d_border_wb);
                 JINC_CUDA(cudaGetLastError());
-                JINC_CUDA(cudaStreamSynchronize(st)); // reps / block_of are host temporaries
+                JINC_CUDA(cudaStreamSynchronize(st)); // reps is a host temporary
                 cudaFree(d_reps);
+                t->h_border_block = std::move(block_of);
             }
         }
     }
@@ -769,7 +770,7 @@ int jinc_table_build_device(jinc_table* t, const double* lut)
     }
     if (t->bgeom.total >= (1ll << 31))
         return jinc_fail(JINC_E_UNSUPPORTED, "jinc_table: %lld border pixels exceed the 32-bit slot index", t->bgeom.total);
-    return JINC_OK;
+    return jinc_build_strip_plan(t);
 }
 
 // ================================================================ C ABI: tables
@@ -840,6 +841,7 @@ extern "C" void jinc_table_destroy(jinc_table* t)
     cudaFree(t->d_border_w);
     cudaFree(t->d_border_block);
     cudaFree(t->d_border_wb);
+    jinc_free_strip_plan(t);
     delete t;
 }
 
