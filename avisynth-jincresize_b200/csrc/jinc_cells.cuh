@@ -43,8 +43,6 @@ struct CellsGeom {
     static constexpr size_t SMEM = (size_t)FH * ROW * sizeof(float);
 };
 
-constexpr int CL_STRIP_SPT = 4;
-constexpr int CL_STRIP_MAX_PW = 64;
 
 // the NX x NY samples of one residue pair; PX > 0: the cell size is a compile-time constant (immediate store offsets)
 template <typename T, int NX, int NY, int PX>
@@ -69,7 +67,10 @@ __global__ void __launch_bounds__((CellsGeom<FS, Q>::THREADS), (CellsGeom<FS, Q>
 
     unsigned role_id;
     if (block_role(blockIdx.x, (unsigned)a.strip_blocks, a.strip_shift, role_id)) {
-        strip_block<T, FS, G::THREADS, CL_STRIP_SPT>(a.st, a.fr, role_id, tile);
+        if (a.st.plan_patches)
+            strip_block_planned<T, FS, G::THREADS, CL_STRIP_SPT, Q>(a.st, a.fr, role_id, tile);
+        else
+            strip_block_unplanned<T, FS, G::THREADS, CL_STRIP_SPT, 0, 0>(a.st, a.fr, role_id, tile);
         return;
     }
     const int plane = (int)div_by(role_id, a.tiles_per_plane_magic);
@@ -235,8 +236,10 @@ int launch_cells_cfg(const jinc_table* t, CellsArgs& a, int n_frames, cudaStream
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
     if (e != cudaSuccess)
         return jinc_fail(JINC_E_CUDA, "cudaFuncSetAttribute(cells smem %zu): %s", G::SMEM, cudaGetErrorString(e));
-    const long long strip_blocks =
+    long long strip_blocks =
         n_rects > 0 ? set_strip_rects(a.st, rects, n_rects, G::THREADS * CL_STRIP_SPT, CL_STRIP_MAX_PW, G::SMEM) * a.fr.n_planes : 0;
+    if (n_rects > 0 && a.want_strip_plan && attach_strip_plan(t, a.st, G::THREADS, CL_STRIP_SPT))
+        strip_blocks = (long long)a.st.blocks_per_plane * a.fr.n_planes;
     a.tiles_x = (a.n_cx + 31) / 32;
     a.tiles_per_plane = a.tiles_x * ((a.cyk_end - a.cyk_begin + G::WARPS - 1) / G::WARPS);
     a.tiles_x_magic = div_magic((unsigned)a.tiles_x);

@@ -131,23 +131,23 @@ struct CellsPlan {
 };
 
 // Strip plan (whole-frame launches of a fast path; jinc_resize.cu builds it once per table, jinc_resample.cuh runs it).
-// The border strips are cut into the same patches as at launch time, but everything a strip block used to derive in its
-// prologue -- the patch's source footprint, every thread's samples, their window offsets, weight blocks and the way
-// they are accumulated -- is worked out once on the host, and the few distinct weight blocks of a patch are packed
-// next to each other so the block copies them into shared memory with its footprint.
+// Everything a strip block otherwise derives in its prologue -- the patches of the border strips, a patch's source
+// footprint, every thread's samples, their window offsets, weight blocks and the way they are accumulated -- is worked
+// out once on the host, and the few distinct weight blocks of a patch are packed next to each other so the block
+// copies them into shared memory with its footprint.
 struct StripPlanPatch {
     int32_t sx_lo, sy_lo, fw, fh; // source footprint of the patch
     uint32_t magic;               // floor(e / fw) = umulhi(e, magic)
-    int32_t n_wb;                 // weight blocks staged in shared memory; < 0: patch not planned (prologue path)
+    int32_t n_wb;                 // weight blocks staged in shared memory; < 0: too many, read from the packed copy
     uint32_t wdata_off;           // first float of the patch's packed weight blocks in StripPlan::d_wdata
     uint32_t tile_floats;         // shared-memory offset of the staged blocks (footprint rounded up to 16 bytes)
 };
 enum { JINC_SK_NONE = 0, JINC_SK_RUN_ROWS, JINC_SK_RUN_COLS, JINC_SK_FUSED_SHARED, JINC_SK_FUSED_SEP, JINC_SK_PER_SAMPLE };
 struct StripPlan {
     bool ok = false;
-    int threads = 0, spt = 0;
-    unsigned n_patches = 0;  // per plane; equals what set_strip_rects yields for the whole-frame rectangles
-    unsigned n_planned = 0;  // patches that run from the plan
+    int threads = 0, spt = 0, px = 0, py = 0;
+    unsigned n_patches = 0;  // strip blocks per plane
+    unsigned n_staged = 0;   // patches whose weight blocks are staged in shared memory
     StripPlanPatch* d_patches = nullptr;
     // [patch][sample k][thread]: .x = x | y << 16, .y = offset of the window origin in the staged footprint,
     // .z = float offset of the weight block among the staged ones, .w (sample 0) = kind | live mask << 8

@@ -235,6 +235,7 @@ struct StripArgs {
     const StripPlanPatch* plan_patches;
     const uint4* plan_threads;
     const float* plan_wdata;
+    int plan_px, plan_py; // phase period of the outputs: distance of a planned thread's samples
 };
 
 struct FrameSet {
@@ -814,14 +815,41 @@ __device__ __forceinline__ void strip_block(const StripArgs& a, const FrameSet& 
 
 // ------------------------------------------------------------------------------------------ planned strip blocks
 //
-// The same patches and the same thread-to-sample mapping as strip_block, but run from the table's StripPlan: the patch
-// descriptor gives the footprint, one 16-byte record per thread (and sample) gives the output coordinates, the window's
-// offset in the staged footprint, the weight block and how the thread's samples are accumulated.  The distinct weight
-// blocks of the patch (a handful: one per border row or column and phase) are copied into shared memory next to the
-// footprint, so the accumulation loops read nothing from global memory.  Every sample is accumulated in the same tap
-// order as in strip_block (row-major, one fused multiply-add per tap): both paths give identical bits.
+// Whole-frame launches of a table with a StripPlan (jinc_internal.h) run their strip blocks from it.  The plan cuts the
+// border strips into its own patches and gives every thread up to SPT samples of ONE border row (wide strips) or column
+// (tall strips) that are a phase period apart -- adjacent outputs of the same phase, so they normally share one weight
+// block and their windows overlap.  A patch descriptor holds the source footprint, one 16-byte record per thread and
+// sample holds the output coordinates, the window's offset in the staged footprint, the weight block and how the
+// thread's samples are accumulated.  The distinct weight blocks of a patch (a handful: one per border row or column and
+// phase) are packed next to each other by the table build and copied into shared memory with the footprint, so the
+// accumulation loops read nothing from global memory (patches with too many blocks for that -- corners of wide windows --
+// read the packed copy).  Every sample is accumulated in the same tap order as in strip_block (row-major, one fused
+// multiply-add per tap): both paths give identical bits.
 
-template <typename T, int FSC, int SPT, int STEP>
+template <bool WS>
+__device__ __forceinline__ float4 plan_w4(const float* __restrict__ w)
+{
+    if (WS)
+        return *reinterpret_cast<const float4*>(w); // shared memory
+    return __ldg(reinterpret_cast<const float4*>(w));
+}
+
+template <bool WS, int FSP>
+__device__ __forceinline__ void plan_weight_row(const float* __restrict__ w, float (&wr)[FSP])
+{
+#pragma unroll
+    for (int q = 0; q < FSP / 4; ++q) {
+        const float4 t = plan_w4<WS>(w + 4 * q);
+        wr[4 * q] = t.x;
+        wr[4 * q + 1] = t.y;
+        wr[4 * q + 2] = t.z;
+        wr[4 * q + 3] = t.w;
+    }
+}
+
+// SPT same-block samples of one row whose window origins are STEP apart: a window row of FSC + (SPT-1)*STEP staged
+// values is read once and feeds SPT x FSC FMAs
+template <typename T, int FSC, int SPT, int STEP, bool WS>
 __device__ __forceinline__ void plan_run_rows(const float* __restrict__ s, int fw, const float* __restrict__ w, T* __restrict__ o, int xstep,
                                               float peak)
 {
@@ -833,14 +861,7 @@ __device__ __forceinline__ void plan_run_rows(const float* __restrict__ s, int f
 #pragma unroll(FSC <= 9 ? FSC : 1)
     for (int ly = 0; ly < FSC; ++ly) {
         float seg[SEG], wr[FSP];
-#pragma unroll
-        for (int q = 0; q < FSP / 4; ++q) {
-            const float4 t = *reinterpret_cast<const float4*>(w + ly * FSP + 4 * q);
-            wr[4 * q] = t.x;
-            wr[4 * q + 1] = t.y;
-            wr[4 * q + 2] = t.z;
-            wr[4 * q + 3] = t.w;
-        }
+        plan_weight_row<WS, FSP>(w + ly * FSP, wr);
 #pragma unroll
         for (int i = 0; i < SEG; ++i)
             seg[i] = s[ly * fw + i];
@@ -855,36 +876,29 @@ __device__ __forceinline__ void plan_run_rows(const float* __restrict__ s, int f
         o[k * xstep] = finish<T>(acc[k], peak);
 }
 
-// adjacent same-phase outputs of one column, window origins one row apart: a staged row of FSC values feeds up to four
-// outputs, each with its own weight row (read from shared memory when it is needed)
-template <typename T, int FSC>
+// the same down one column (window origins STEP rows apart): a staged row of FSC values feeds up to SPT outputs, each
+// with its own weight row
+template <typename T, int FSC, int SPT, int STEP, bool WS>
 __device__ __forceinline__ void plan_run_cols(const float* __restrict__ s, int fw, const float* __restrict__ w, T* __restrict__ o, long long ystep,
                                               float peak)
 {
-    constexpr int FSP = (FSC + 3) & ~3, SPT = 4;
+    constexpr int FSP = (FSC + 3) & ~3;
     float acc[SPT];
 #pragma unroll
     for (int k = 0; k < SPT; ++k)
         acc[k] = 0.f;
 #pragma unroll
-    for (int r = 0; r < FSC + SPT - 1; ++r) {
+    for (int r = 0; r < FSC + (SPT - 1) * STEP; ++r) {
         float seg[FSC];
 #pragma unroll
         for (int i = 0; i < FSC; ++i)
             seg[i] = s[r * fw + i];
 #pragma unroll
         for (int k = 0; k < SPT; ++k) {
-            const int ly = r - k; // weight row of output k (a constant after unrolling)
+            const int ly = r - k * STEP; // weight row of output k (a constant after unrolling)
             if (ly >= 0 && ly < FSC) {
                 float wr[FSP];
-#pragma unroll
-                for (int q = 0; q < FSP / 4; ++q) {
-                    const float4 t = *reinterpret_cast<const float4*>(w + ly * FSP + 4 * q);
-                    wr[4 * q] = t.x;
-                    wr[4 * q + 1] = t.y;
-                    wr[4 * q + 2] = t.z;
-                    wr[4 * q + 3] = t.w;
-                }
+                plan_weight_row<WS, FSP>(w + ly * FSP, wr);
 #pragma unroll
                 for (int lx = 0; lx < FSC; ++lx)
                     acc[k] = fmaf(seg[lx], wr[lx], acc[k]);
@@ -897,9 +911,9 @@ __device__ __forceinline__ void plan_run_cols(const float* __restrict__ s, int f
 }
 
 // SPT samples with separate windows, interleaved; SHARED: one weight block for all of them
-template <typename T, int FSC, int SPT, bool SHARED>
+template <typename T, int FSC, int SPT, bool SHARED, bool WS>
 __device__ __forceinline__ void plan_fused(const uint4 (&r)[SPT], unsigned live, const float* __restrict__ tile, int fw,
-                                           const float* __restrict__ wsm, T* __restrict__ dst, long long dp, float peak)
+                                           const float* __restrict__ wbase, T* __restrict__ dst, long long dp, float peak)
 {
     constexpr int FSP = (FSC + 3) & ~3, NW = SHARED ? 1 : SPT;
     const float* __restrict__ s[SPT];
@@ -912,7 +926,7 @@ __device__ __forceinline__ void plan_fused(const uint4 (&r)[SPT], unsigned live,
     }
 #pragma unroll
     for (int k = 0; k < NW; ++k)
-        w[k] = wsm + r[k].z;
+        w[k] = wbase + r[k].z;
 #pragma unroll 1
     for (int ly = 0; ly < FSC; ++ly) {
 #pragma unroll
@@ -920,7 +934,7 @@ __device__ __forceinline__ void plan_fused(const uint4 (&r)[SPT], unsigned live,
             float4 t[NW];
 #pragma unroll
             for (int k = 0; k < NW; ++k)
-                t[k] = *reinterpret_cast<const float4*>(w[k] + 4 * q);
+                t[k] = plan_w4<WS>(w[k] + 4 * q);
             const int lx = 4 * q;
 #pragma unroll
             for (int k = 0; k < SPT; ++k) {
@@ -947,14 +961,51 @@ __device__ __forceinline__ void plan_fused(const uint4 (&r)[SPT], unsigned live,
             dst[(long long)(r[k].x >> 16) * dp + (r[k].x & 0xffffu)] = finish<T>(acc[k], peak);
 }
 
-// the prologue path as a real function: planned launches call it for the few patches the plan leaves out
+// the prologue path as a real function (row-band launches and tables without a plan)
 template <typename T, int FSC, int THREADS, int SPT, int PERIOD, int STEP>
 __device__ __noinline__ void strip_block_unplanned(const StripArgs& a, const FrameSet& fsx, unsigned sb, float* __restrict__ tile)
 {
     strip_block<T, FSC, THREADS, SPT, PERIOD, STEP>(a, fsx, sb, tile);
 }
 
-template <typename T, int FSC, int THREADS, int SPT, int PERIOD, int STEP>
+template <typename T, int FSC, int THREADS, int SPT, int STEP, bool WS>
+__device__ __forceinline__ void plan_accumulate(const StripArgs& a, const FrameSet& fsx, unsigned plane, const uint4& r0, const uint4* __restrict__ recs,
+                                                const float* __restrict__ tile, int fw, const float* __restrict__ wbase)
+{
+    const unsigned kind = r0.w & 0xffu, live = r0.w >> 8;
+    const PlanePtrs& pp = frame_ptrs(fsx);
+    T* __restrict__ dst = static_cast<T*>(pp.dst[plane]);
+    const long long dp = pp.dst_pitch[plane];
+    if (kind == JINC_SK_RUN_ROWS) {
+        plan_run_rows<T, FSC, SPT, STEP, WS>(tile + (int)r0.y, fw, wbase + r0.z, dst + (long long)(r0.x >> 16) * dp + (r0.x & 0xffffu), a.plan_px,
+                                             fsx.peak);
+        return;
+    }
+    if constexpr (FSC <= 9) {
+        if (kind == JINC_SK_RUN_COLS) {
+            plan_run_cols<T, FSC, SPT, STEP, WS>(tile + (int)r0.y, fw, wbase + r0.z, dst + (long long)(r0.x >> 16) * dp + (r0.x & 0xffffu),
+                                                 (long long)a.plan_py * dp, fsx.peak);
+            return;
+        }
+    }
+    uint4 r[SPT];
+    r[0] = r0;
+#pragma unroll
+    for (int k = 1; k < SPT; ++k)
+        r[k] = __ldg(recs + k * THREADS);
+    if (kind == JINC_SK_FUSED_SHARED) {
+        plan_fused<T, FSC, SPT, true, WS>(r, live, tile, fw, wbase, dst, dp, fsx.peak);
+    } else if (kind == JINC_SK_FUSED_SEP) {
+        plan_fused<T, FSC, SPT, false, WS>(r, live, tile, fw, wbase, dst, dp, fsx.peak);
+    } else { // JINC_SK_PER_SAMPLE: no vector-readable block (per-pixel border weights): straight from global memory
+#pragma unroll 1
+        for (int k = 0; k < SPT; ++k)
+            if (live & (1u << k))
+                strip_sample<T, FSC>(a, fsx, (int)(r[k].x & 0xffffu), (int)(r[k].x >> 16), (int)plane);
+    }
+}
+
+template <typename T, int FSC, int THREADS, int SPT, int STEP>
 __device__ __forceinline__ void strip_block_planned(const StripArgs& a, const FrameSet& fsx, unsigned sb, float* __restrict__ tile)
 {
     static_assert(FSC > 0, "planned strips need a compile-time window size");
@@ -962,23 +1013,21 @@ __device__ __forceinline__ void strip_block_planned(const StripArgs& a, const Fr
     const unsigned plane = div_by(sb, a.blocks_per_plane_magic);
     const unsigned pid = sb - plane * a.blocks_per_plane;
     const int4* __restrict__ pd = reinterpret_cast<const int4*>(a.plan_patches + pid);
+    const int4 pa = __ldg(pd);     // sx_lo, sy_lo, fw, fh
     const int4 pb = __ldg(pd + 1); // magic, n_wb, wdata_off, tile_floats
-    if (pb.y < 0) {
-        strip_block_unplanned<T, FSC, THREADS, SPT, PERIOD, STEP>(a, fsx, sb, tile);
-        return;
-    }
-    const int4 pa = __ldg(pd); // sx_lo, sy_lo, fw, fh
     const uint4* __restrict__ recs = a.plan_threads + (size_t)pid * (unsigned)(SPT * THREADS) + threadIdx.x;
     const uint4 r0 = __ldg(recs);
     const PlanePtrs& pp = frame_ptrs(fsx);
     const int fw = pa.z;
+    const bool ws = pb.y >= 0; // the patch's weight blocks are staged
     float* __restrict__ wsm = tile + pb.w;
+    const float* __restrict__ wglobal = a.plan_wdata + (unsigned)pb.z;
     {
         // the patch's weight blocks (packed in plan order: a straight copy) and its source footprint, converted to float.
         // The first round of both is loaded before anything is stored: one memory round trip for the usual patch.
-        const float4* __restrict__ wsrc = reinterpret_cast<const float4*>(a.plan_wdata + (unsigned)pb.z);
+        const float4* __restrict__ wsrc = reinterpret_cast<const float4*>(wglobal);
         float4* __restrict__ wdst = reinterpret_cast<float4*>(wsm);
-        const int nw4 = pb.y * WB4;
+        const int nw4 = max(pb.y, 0) * WB4;
         const int pitch = (int)pp.src_pitch[plane];
         const T* __restrict__ src = static_cast<const T*>(pp.src[plane]) + (long long)pa.y * pitch + pa.x;
         const unsigned n = (unsigned)(fw * pa.w), magic = (unsigned)pb.x;
@@ -1007,181 +1056,205 @@ __device__ __forceinline__ void strip_block_planned(const StripArgs& a, const Fr
             wdst[i] = __ldg(wsrc + i);
     }
     __syncthreads();
-    const unsigned kind = r0.w & 0xffu, live = r0.w >> 8;
-    if (kind == JINC_SK_NONE)
+    if ((r0.w & 0xffu) == JINC_SK_NONE)
         return;
-    T* __restrict__ dst = static_cast<T*>(pp.dst[plane]);
-    const long long dp = pp.dst_pitch[plane];
-    if (PERIOD > 0 && kind == JINC_SK_RUN_ROWS) {
-        plan_run_rows<T, FSC, SPT, (STEP > 0 ? STEP : 1)>(tile + (int)r0.y, fw, wsm + r0.z, dst + (long long)(r0.x >> 16) * dp + (r0.x & 0xffffu),
-                                                           PERIOD, fsx.peak);
-        return;
-    }
-    if constexpr (PERIOD > 0 && STEP == 1 && SPT == 4 && FSC <= 9) {
-        if (kind == JINC_SK_RUN_COLS) {
-            plan_run_cols<T, FSC>(tile + (int)r0.y, fw, wsm + r0.z, dst + (long long)(r0.x >> 16) * dp + (r0.x & 0xffffu), (long long)PERIOD * dp,
-                                  fsx.peak);
-            return;
-        }
-    }
-    uint4 r[SPT];
-    r[0] = r0;
-#pragma unroll
-    for (int k = 1; k < SPT; ++k)
-        r[k] = __ldg(recs + k * THREADS);
-    if (kind == JINC_SK_FUSED_SHARED) {
-        plan_fused<T, FSC, SPT, true>(r, live, tile, fw, wsm, dst, dp, fsx.peak);
-    } else if (kind == JINC_SK_FUSED_SEP) {
-        plan_fused<T, FSC, SPT, false>(r, live, tile, fw, wsm, dst, dp, fsx.peak);
-    } else { // JINC_SK_PER_SAMPLE: no vector-readable block (per-pixel border weights): straight from global memory
-#pragma unroll 1
-        for (int k = 0; k < SPT; ++k)
-            if (live & (1u << k))
-                strip_sample<T, FSC>(a, fsx, (int)(r[k].x & 0xffffu), (int)(r[k].x >> 16), (int)plane);
-    }
+    if (ws)
+        plan_accumulate<T, FSC, THREADS, SPT, STEP, true>(a, fsx, plane, r0, recs, tile, fw, wsm);
+    else
+        plan_accumulate<T, FSC, THREADS, SPT, STEP, false>(a, fsx, plane, r0, recs, tile, fw, wglobal);
 }
 
-// Host side of the plan: the thread-to-sample mapping and the choice of accumulation path of strip_block, evaluated for
-// every thread of every patch.  `a` holds the whole-frame rectangles (set_strip_rects).  Returns the patch descriptors,
-// the thread records and the (sel << 31 | block) list of the weight blocks to pack, in patch order.
+// Host side of the plan.  The strips (up to four rectangles) are cut into patches: 64 outputs wide in the wide strips,
+// 8 in the tall ones, as tall as the block has threads for.  In a wide strip a thread takes up to SPT outputs of one row
+// that are px apart (one residue class of the row), in a tall strip up to SPT outputs of one column that are py apart;
+// how they are accumulated is decided here, by the rules of strip_block.
+struct StripPlanParams {
+    int threads, spt;
+    int px, py;   // phase period of the outputs along x and y
+    int step;     // distance of the window origins of same-phase neighbours (both axes)
+    unsigned smem_floats;
+};
+
 struct StripPlanHost {
     std::vector<StripPlanPatch> patches;
     std::vector<uint4> recs;
-    std::vector<uint32_t> wlist;
-    unsigned n_planned = 0;
+    std::vector<uint32_t> wlist; // sel << 31 | block, in packing order
+    unsigned n_staged = 0;       // patches whose weight blocks fit in shared memory
+    bool ok = false;
 };
 
-inline void build_strip_plan_host(const jinc_table* t, const StripArgs& a, int THREADS, int SPT, int PERIOD, int STEP, StripPlanHost& out)
+inline void build_strip_plan_host(const jinc_table* t, const Rect* rects, int n_rects, const StripPlanParams& pp, StripPlanHost& out)
 {
     const int fs = t->sc.fs, fsp = (fs + 3) & ~3, wbf = fs * fsp;
+    const int THREADS = pp.threads, SPT = pp.spt;
     const std::vector<int32_t>&start_x = t->h_start[0], &start_y = t->h_start[1], &rank_x = t->h_rank[0], &rank_y = t->h_rank[1];
     const bool have_classes = !t->h_border_block.empty();
-    const bool phase_padded = t->d_weights_p != nullptr;
-    const int phase_stride = phase_padded ? fsp : fs;
+    const int phase_stride = t->d_weights_p ? fsp : fs;
     const int n_rank_x = t->ax[0].n_rank;
-    int spt_l2 = 0;
-    while ((1 << spt_l2) < SPT)
-        ++spt_l2;
-    const unsigned total = a.blocks_per_plane;
-    out.patches.assign(total, StripPlanPatch{});
-    out.recs.assign((size_t)total * SPT * THREADS, make_uint4(0, 0, 0, 0));
-    out.wlist.clear();
-    out.n_planned = 0;
+    out = StripPlanHost{};
     struct Meta {
         int x, y, sx, sy, wstride;
         uint32_t wkey; // sel << 31 | block; only meaningful when wstride != 0
     };
+    struct Item {
+        int x[8], y[8], n;
+    };
     std::vector<Meta> meta((size_t)SPT);
+    std::vector<Item> items;
     std::vector<uint32_t> keys; // distinct weight blocks of the patch, in first-use order
-    for (unsigned pid = 0; pid < total; ++pid) {
-        const int r = (int)(pid >= a.patch_begin[1]) + (int)(pid >= a.patch_begin[2]) + (int)(pid >= a.patch_begin[3]);
-        const unsigned lp = pid - a.patch_begin[r];
-        const unsigned pyi = lp / a.patches_x[r], pxi = lp - pyi * a.patches_x[r];
-        const int pwl = a.pw_log2[r];
-        const int ox0 = a.rect[r].x0 + (int)(pxi << pwl), oy0 = a.rect[r].y0 + (int)pyi * ((THREADS * SPT) >> pwl);
-        const int nx = std::min(1 << pwl, a.rect[r].x1 - ox0), ny = std::min((THREADS * SPT) >> pwl, a.rect[r].y1 - oy0);
-        const int sx_lo = start_x[ox0], sy_lo = start_y[oy0];
-        const int fw = start_x[ox0 + nx - 1] + fs - sx_lo, fh = start_y[oy0 + ny - 1] + fs - sy_lo;
-        StripPlanPatch& pd = out.patches[pid];
-        pd.sx_lo = sx_lo;
-        pd.sy_lo = sy_lo;
-        pd.fw = fw;
-        pd.fh = fh;
-        pd.magic = 0xFFFFFFFFu / (unsigned)fw + 1u;
-        pd.n_wb = -1;
-        pd.wdata_off = 0;
-        pd.tile_floats = ((unsigned)(fw * fh) + 3u) & ~3u;
-        if ((long long)fw * fh > (long long)a.smem_floats)
-            continue; // the footprint is not staged: prologue path
-        const bool rows = a.row_mode[r] != 0;
-        const int txl = rows ? pwl - spt_l2 : pwl;
-        keys.clear();
-        uint4* prec = out.recs.data() + (size_t)pid * SPT * THREADS;
-        for (int tid = 0; tid < THREADS; ++tid) {
-            int tx = tid & ((1 << txl) - 1), ty = tid >> txl;
-            int dx = rows ? 1 << txl : 0, dy = rows ? 0 : THREADS >> pwl;
-            if (PERIOD > 0) {
-                if (rows) {
-                    tx = (tx / PERIOD) * (SPT * PERIOD) + tx % PERIOD;
-                    dx = PERIOD;
-                } else {
-                    ty = (ty / PERIOD) * (SPT * PERIOD) + ty % PERIOD;
-                    dy = PERIOD;
-                }
-            }
-            unsigned live = 0;
-            for (int k = 0; k < SPT; ++k) {
-                const int lx = tx + k * dx, ly = ty + k * dy;
-                if (lx >= nx || ly >= ny)
-                    continue;
-                live |= 1u << k;
-                Meta& m = meta[k];
-                m.x = ox0 + lx;
-                m.y = oy0 + ly;
-                m.sx = start_x[m.x];
-                m.sy = start_y[m.y];
-                const int rx = rank_x[m.x], ry = rank_y[m.y];
-                if (rx >= 0 && ry >= 0) {
-                    m.wkey = (uint32_t)(ry * n_rank_x + rx);
-                    m.wstride = phase_stride;
-                } else if (have_classes) {
-                    m.wkey = 0x80000000u | (uint32_t)t->h_border_block[(size_t)jinc_border_slot(t->bgeom, m.x, m.y)];
-                    m.wstride = fsp;
-                } else {
-                    m.wkey = 0;
-                    m.wstride = 0;
-                }
-            }
-            unsigned kind = JINC_SK_NONE;
-            if (live & 1u) { // live samples are a prefix
-                bool same = true, vec = true;
-                for (int k = 0; k < SPT; ++k) {
-                    if (!(live & (1u << k)))
-                        meta[k] = meta[0];
-                    same = same && meta[k].wstride == meta[0].wstride && (meta[k].wstride == 0 || meta[k].wkey == meta[0].wkey);
-                    vec = vec && meta[k].wstride != 0 && (meta[k].wstride & 3) == 0 && meta[k].wstride == meta[0].wstride;
-                }
-                kind = JINC_SK_PER_SAMPLE;
-                if (SPT > 1 && vec) {
-                    kind = same ? JINC_SK_FUSED_SHARED : JINC_SK_FUSED_SEP;
-                    if (PERIOD > 0 && same && live == (1u << SPT) - 1u) {
-                        bool run = true;
-                        for (int k = 1; k < SPT; ++k)
-                            run = run && (rows ? (meta[k].sy == meta[0].sy && meta[k].sx == meta[0].sx + k * STEP)
-                                               : (meta[k].sx == meta[0].sx && meta[k].sy == meta[0].sy + k * STEP));
-                        if (run && rows)
-                            kind = JINC_SK_RUN_ROWS;
-                        else if (run && STEP == 1 && SPT == 4 && fs <= 9)
-                            kind = JINC_SK_RUN_COLS;
-                    }
-                }
-                for (int k = 0; k < SPT; ++k) {
-                    const Meta& m = meta[k];
-                    uint32_t slot = 0;
-                    if (kind != JINC_SK_PER_SAMPLE) {
-                        size_t j = 0;
-                        while (j < keys.size() && keys[j] != m.wkey)
-                            ++j;
-                        if (j == keys.size())
-                            keys.push_back(m.wkey);
-                        slot = (uint32_t)j * (uint32_t)wbf;
-                    }
-                    prec[(size_t)k * THREADS + tid] = make_uint4((uint32_t)m.x | ((uint32_t)m.y << 16), (uint32_t)((m.sy - sy_lo) * fw + (m.sx - sx_lo)),
-                                                                 slot, k == 0 ? (kind | (live << 8)) : 0u);
-                }
-            }
-        }
-        if ((unsigned long long)pd.tile_floats + (unsigned long long)keys.size() * wbf > a.smem_floats) {
-            // the patch's weight blocks do not fit next to its footprint (corner patches of wide windows): prologue path
-            for (size_t i = 0; i < (size_t)SPT * THREADS; ++i)
-                prec[i] = make_uint4(0, 0, 0, 0);
+    if (SPT > 8)
+        return;
+    for (int ri = 0; ri < n_rects; ++ri) {
+        const Rect rc = rects[ri];
+        const int w = rc.x1 - rc.x0, h = rc.y1 - rc.y0;
+        if (w <= 0 || h <= 0)
             continue;
+        const bool rows = w >= h; // top/bottom strips are wide, left/right strips are tall
+        const int pw = rows ? 64 : 8;
+        for (int ox0 = rc.x0; ox0 < rc.x1; ox0 += pw) {
+            const int nx = std::min(pw, rc.x1 - ox0);
+            // patch height: as many rows as the block has threads for
+            int ph;
+            if (rows) {
+                int per_row = 0;
+                for (int p = 0; p < pp.px; ++p) {
+                    int cnt = 0;
+                    for (int x = ox0; x < ox0 + nx; ++x)
+                        cnt += (x % pp.px) == p;
+                    per_row += (cnt + SPT - 1) / SPT;
+                }
+                ph = std::max(1, THREADS / std::max(per_row, 1));
+                if (per_row > THREADS)
+                    return; // cannot happen for 64-wide patches
+            } else {
+                const int m = THREADS / (nx * pp.py); // groups of SPT * py rows
+                if (m < 1)
+                    return;
+                ph = m * SPT * pp.py;
+            }
+            for (int oy0 = rc.y0; oy0 < rc.y1; oy0 += ph) {
+                const int ny = std::min(ph, rc.y1 - oy0);
+                const int sx_lo = start_x[ox0], sy_lo = start_y[oy0];
+                const int fw = start_x[ox0 + nx - 1] + fs - sx_lo, fh = start_y[oy0 + ny - 1] + fs - sy_lo;
+                if ((long long)fw * fh > (long long)pp.smem_floats)
+                    return; // footprints of the planned kernel families always fit; otherwise no plan at all
+                // the work items of the patch
+                items.clear();
+                if (rows) {
+                    for (int y = oy0; y < oy0 + ny; ++y)
+                        for (int p = 0; p < pp.px; ++p) {
+                            Item it{};
+                            for (int x = ox0; x < ox0 + nx; ++x) {
+                                if (x % pp.px != p)
+                                    continue;
+                                it.x[it.n] = x;
+                                it.y[it.n] = y;
+                                if (++it.n == SPT) {
+                                    items.push_back(it);
+                                    it.n = 0;
+                                }
+                            }
+                            if (it.n)
+                                items.push_back(it);
+                        }
+                } else {
+                    for (int x = ox0; x < ox0 + nx; ++x)
+                        for (int p = 0; p < pp.py; ++p) {
+                            Item it{};
+                            for (int y = oy0; y < oy0 + ny; ++y) {
+                                if (y % pp.py != p)
+                                    continue;
+                                it.x[it.n] = x;
+                                it.y[it.n] = y;
+                                if (++it.n == SPT) {
+                                    items.push_back(it);
+                                    it.n = 0;
+                                }
+                            }
+                            if (it.n)
+                                items.push_back(it);
+                        }
+                }
+                if ((int)items.size() > THREADS)
+                    return;
+                StripPlanPatch pd{};
+                pd.sx_lo = sx_lo;
+                pd.sy_lo = sy_lo;
+                pd.fw = fw;
+                pd.fh = fh;
+                pd.magic = 0xFFFFFFFFu / (unsigned)fw + 1u;
+                pd.tile_floats = ((unsigned)(fw * fh) + 3u) & ~3u;
+                const size_t rec0 = out.recs.size();
+                out.recs.resize(rec0 + (size_t)SPT * THREADS, make_uint4(0, 0, 0, 0));
+                uint4* prec = out.recs.data() + rec0;
+                keys.clear();
+                for (size_t tid = 0; tid < items.size(); ++tid) {
+                    const Item& it = items[tid];
+                    const unsigned live = (1u << it.n) - 1u;
+                    for (int k = 0; k < it.n; ++k) {
+                        Meta& m = meta[k];
+                        m.x = it.x[k];
+                        m.y = it.y[k];
+                        m.sx = start_x[m.x];
+                        m.sy = start_y[m.y];
+                        const int rx = rank_x[m.x], ry = rank_y[m.y];
+                        if (rx >= 0 && ry >= 0) {
+                            m.wkey = (uint32_t)(ry * n_rank_x + rx);
+                            m.wstride = phase_stride;
+                        } else if (have_classes) {
+                            m.wkey = 0x80000000u | (uint32_t)t->h_border_block[(size_t)jinc_border_slot(t->bgeom, m.x, m.y)];
+                            m.wstride = fsp;
+                        } else {
+                            m.wkey = 0;
+                            m.wstride = 0;
+                        }
+                    }
+                    bool same = true, vec = true;
+                    for (int k = 0; k < SPT; ++k) {
+                        if (k >= it.n)
+                            meta[k] = meta[0]; // computed, not stored
+                        same = same && meta[k].wstride == meta[0].wstride && (meta[k].wstride == 0 || meta[k].wkey == meta[0].wkey);
+                        vec = vec && meta[k].wstride != 0 && (meta[k].wstride & 3) == 0 && meta[k].wstride == meta[0].wstride;
+                    }
+                    unsigned kind = JINC_SK_PER_SAMPLE;
+                    if (vec) {
+                        kind = same ? JINC_SK_FUSED_SHARED : JINC_SK_FUSED_SEP;
+                        if (same && it.n == SPT) {
+                            bool run = true;
+                            for (int k = 1; k < SPT; ++k)
+                                run = run && (rows ? (meta[k].sy == meta[0].sy && meta[k].sx == meta[0].sx + k * pp.step)
+                                                   : (meta[k].sx == meta[0].sx && meta[k].sy == meta[0].sy + k * pp.step));
+                            if (run && rows)
+                                kind = JINC_SK_RUN_ROWS;
+                            else if (run && fs <= 9)
+                                kind = JINC_SK_RUN_COLS;
+                        }
+                    }
+                    for (int k = 0; k < SPT; ++k) {
+                        const Meta& m = meta[k];
+                        uint32_t slot = 0;
+                        if (kind != JINC_SK_PER_SAMPLE) {
+                            size_t j = 0;
+                            while (j < keys.size() && keys[j] != m.wkey)
+                                ++j;
+                            if (j == keys.size())
+                                keys.push_back(m.wkey);
+                            slot = (uint32_t)j * (uint32_t)wbf;
+                        }
+                        prec[(size_t)k * THREADS + tid] = make_uint4((uint32_t)m.x | ((uint32_t)m.y << 16),
+                                                                     (uint32_t)((m.sy - sy_lo) * fw + (m.sx - sx_lo)), slot, k == 0 ? (kind | (live << 8)) : 0u);
+                    }
+                }
+                const bool staged = (unsigned long long)pd.tile_floats + (unsigned long long)keys.size() * wbf <= pp.smem_floats;
+                pd.n_wb = staged ? (int32_t)keys.size() : -1;
+                pd.wdata_off = (uint32_t)(out.wlist.size() * (size_t)wbf);
+                out.wlist.insert(out.wlist.end(), keys.begin(), keys.end());
+                out.n_staged += staged ? 1u : 0u;
+                out.patches.push_back(pd);
+            }
         }
-        pd.n_wb = (int32_t)keys.size();
-        pd.wdata_off = (uint32_t)(out.wlist.size() * (size_t)wbf);
-        out.wlist.insert(out.wlist.end(), keys.begin(), keys.end());
-        ++out.n_planned;
     }
+    out.ok = !out.patches.empty();
 }
 
 // Role of block b in a merged grid of interior tile blocks and `strips` strip blocks: strip block k sits at grid
@@ -1422,6 +1495,9 @@ int launch_down(const jinc_table* t, DownArgs& a, int q, const int* wblocks, boo
 
 // ------------------------------------------------------------------------------------------ chunked-cells kernel (jinc_cells.cuh)
 
+constexpr int CL_STRIP_SPT = 4;    // strip role of the cells kernel: outputs per thread, widest patch
+constexpr int CL_STRIP_MAX_PW = 64;
+
 struct CellsArgs {
     FrameSet fr;
     StripArgs st;
@@ -1444,7 +1520,11 @@ struct CellsArgs {
     int src_w, src_h;
     int tiles_x, tiles_per_plane, interior_blocks, strip_blocks, strip_shift;
     unsigned tiles_x_magic, tiles_per_plane_magic;
+    bool want_strip_plan; // host only: a whole-frame launch, the strips may run from the table's plan
 };
+
+// whole-frame launches: the strip blocks of a table with a plan run from it (jinc_resize.cu)
+bool attach_strip_plan(const jinc_table* t, StripArgs& st, int threads, int spt);
 
 // defined in jinc_cells.cuh, instantiated in jinc_cells_<type>_q<Q>.cu (one source step Q per translation unit)
 template <typename T, int Q>

@@ -296,15 +296,10 @@ int launch_typed(const jinc_table* t, const FrameSet& fr, int n_frames, int y_be
             memset(&a, 0, sizeof(a));
             a.fr = fr;
             a.st = sa;
-            const long long strip_blocks =
+            long long strip_blocks =
                 set_strip_rects(a.st, rects, n_rects, UP_THREADS * UP_STRIP_SPT, UP_STRIP_MAX_PW, up2x_smem_bytes(t->sc.fs)) * fr.n_planes;
-            const StripPlan& sp = t->strip_plan;
-            if (sp.ok && n_rects == 4 && y_begin == 0 && y_end == t->sc.dst_h && a.st.blocks_per_plane == sp.n_patches) {
-                // whole frame: the strip blocks run from the table's plan (same patches, nothing derived per block)
-                a.st.plan_patches = sp.d_patches;
-                a.st.plan_threads = sp.d_threads;
-                a.st.plan_wdata = sp.d_wdata;
-            }
+            if (n_rects == 4 && y_begin == 0 && y_end == t->sc.dst_h && attach_strip_plan(t, a.st, UP_THREADS, UP_STRIP_SPT))
+                strip_blocks = (long long)a.st.blocks_per_plane * fr.n_planes; // whole frame: the strip blocks run from the table's plan
             a.src_w = t->sc.src_w;
             a.src_h = t->sc.src_h;
             a.x0 = u.x0;
@@ -377,6 +372,7 @@ int launch_typed(const jinc_table* t, const FrameSet& fr, int n_frames, int y_be
             a.src_w = t->sc.src_w;
             a.src_h = t->sc.src_h;
             a.interior_blocks = (parts & JINC_PART_INTERIOR) ? 1 : 0; // resolved to the tile count by the launcher
+            a.want_strip_plan = n_rects == 4 && y_begin == 0 && y_end == t->sc.dst_h;
             const int rc = launch_cells<T>(t, a, n_frames, st, rects, n_rects);
             if (rc != 1) {
                 if (rc == 0)
@@ -552,8 +548,24 @@ void jinc_free_strip_plan(jinc_table* t)
     sp = StripPlan{};
 }
 
-// Strip plan of the exact-2x tables (the BASELINE upscale configs): see StripPlan in jinc_internal.h.  Tables without a
-// plan (other kernel families, planes wider than the 16-bit coordinates of a record) keep the prologue path.
+// whole-frame launches: the strip blocks of a table with a plan run from it (its own patches)
+bool jinc_rs::attach_strip_plan(const jinc_table* t, StripArgs& st, int threads, int spt)
+{
+    const StripPlan& sp = t->strip_plan;
+    if (!sp.ok || sp.threads != threads || sp.spt != spt)
+        return false;
+    st.plan_patches = sp.d_patches;
+    st.plan_threads = sp.d_threads;
+    st.plan_wdata = sp.d_wdata;
+    st.plan_px = sp.px;
+    st.plan_py = sp.py;
+    st.blocks_per_plane = sp.n_patches;
+    st.blocks_per_plane_magic = div_magic(sp.n_patches);
+    return true;
+}
+
+// Strip plan of the exact-2x and chunked-cells tables (the upscale ratios): see StripPlan in jinc_internal.h.  Tables
+// without a plan (other kernel families, planes wider than the 16-bit coordinates of a record) keep the prologue path.
 int jinc_build_strip_plan(jinc_table* t)
 {
     StripPlan& sp = t->strip_plan;
@@ -561,19 +573,26 @@ int jinc_build_strip_plan(jinc_table* t)
     const char* off = getenv("JINCRESIZE_B200_STRIP_PLAN");
     if (off && off[0] == '0')
         return JINC_OK;
-    if (t->fast_path != JINC_PATH_UP2X || !up2x_supported(t->sc.fs) || t->sc.dst_w > 65535 || t->sc.dst_h > 65535)
+    if (t->sc.dst_w > 65535 || t->sc.dst_h > 65535)
         return JINC_OK;
     const int fs = t->sc.fs, wbf = fs * ((fs + 3) & ~3);
-    const Up2xPlan& u = t->up2x;
-    const int W = t->sc.dst_w, H = t->sc.dst_h, fy0 = u.y0, fy1 = u.y0 + 2 * u.ncy;
-    const Rect rects[4] = {Rect{0, 0, W, fy0}, Rect{0, fy1, W, H}, Rect{0, fy0, t->ix0, fy1}, Rect{t->ix1, fy0, W, fy1}}; // as launch_typed
-    StripArgs sa;
-    fill_strip_args(t, sa);
-    if (set_strip_rects(sa, rects, 4, UP_THREADS * UP_STRIP_SPT, UP_STRIP_MAX_PW, up2x_smem_bytes(fs)) == 0)
+    StripPlanParams pp{};
+    if (t->fast_path == JINC_PATH_UP2X && up2x_supported(fs)) {
+        pp = StripPlanParams{UP_THREADS, UP_STRIP_SPT, 2, 2, 1, (unsigned)(up2x_smem_bytes(fs) / sizeof(float))};
+    } else if (t->fast_path == JINC_PATH_CELLS && t->cells.ok && jinc_cells_instantiated(t->cells.Q, fs)) {
+        const int q = t->cells.Q, warps = jinc_cells_warps(q, fs);
+        const int d = q * JINC_CELLS_NX, fwc = jinc_cells_footprint(q, fs, JINC_CELLS_NX, 32), fhc = jinc_cells_footprint(q, fs, JINC_CELLS_NY, warps);
+        const size_t smem = (size_t)fhc * (size_t)(d * ((fwc + d - 1) / d)) * sizeof(float); // CellsGeom<FS, Q>::SMEM
+        pp = StripPlanParams{32 * warps, CL_STRIP_SPT, t->cells.ax[0].P, t->cells.ax[1].P, q, (unsigned)(smem / sizeof(float))};
+    } else {
         return JINC_OK;
+    }
+    const int W = t->sc.dst_w, H = t->sc.dst_h;
+    // the whole-frame strips around the interior, as launch_typed cuts them
+    const Rect rects[4] = {Rect{0, 0, W, t->iy0}, Rect{0, t->iy1, W, H}, Rect{0, t->iy0, t->ix0, t->iy1}, Rect{t->ix1, t->iy0, W, t->iy1}};
     StripPlanHost h;
-    build_strip_plan_host(t, sa, UP_THREADS, UP_STRIP_SPT, 2, 1, h);
-    if (h.n_planned == 0)
+    build_strip_plan_host(t, rects, 4, pp, h);
+    if (!h.ok)
         return JINC_OK;
     cudaStream_t st = t->ctx->stream;
     JINC_CUDA(cudaSetDevice(t->ctx->device));
@@ -599,10 +618,12 @@ int jinc_build_strip_plan(jinc_table* t)
     } else {
         JINC_CUDA(cudaStreamSynchronize(st));
     }
-    sp.threads = UP_THREADS;
-    sp.spt = UP_STRIP_SPT;
+    sp.threads = pp.threads;
+    sp.spt = pp.spt;
+    sp.px = pp.px;
+    sp.py = pp.py;
     sp.n_patches = (unsigned)h.patches.size();
-    sp.n_planned = h.n_planned;
+    sp.n_staged = h.n_staged;
     sp.ok = true;
     return JINC_OK;
 }

@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(UP_THREADS, (FS >= 13 ? 4 : 6))
         // ---------------- strip role
         // samples two outputs apart, origins one apart; whole-frame launches run from the table's strip plan
         if (a.st.plan_patches)
-            strip_block_planned<T, FS, UP_THREADS, UP_STRIP_SPT, 2, 1>(a.st, a.fr, role_id, reinterpret_cast<float*>(smem_raw));
+            strip_block_planned<T, FS, UP_THREADS, UP_STRIP_SPT, 1>(a.st, a.fr, role_id, reinterpret_cast<float*>(smem_raw));
         else
             strip_block_unplanned<T, FS, UP_THREADS, UP_STRIP_SPT, 2, 1>(a.st, a.fr, role_id, reinterpret_cast<float*>(smem_raw));
         return;
