@@ -93,7 +93,10 @@ __global__ void __launch_bounds__((DownGeom<T, FS, Q, NX, NY>::THREADS), 2)
     const DownWeights<FS, Q>& W = WN.pass[pz];
     unsigned role_id;
     if (block_role(blockIdx.x, pz == 0 ? (unsigned)a.strip_blocks : 0u, a.strip_shift, role_id)) {
-        strip_block<T, FS, G::THREADS, DN_STRIP_SPT>(a.st, a.fr, role_id, reinterpret_cast<float*>(smem_raw));
+        if (NPASS == 1 && a.st.plan_patches) // whole-frame launch of an integer-ratio table: the strips run from its plan
+            strip_block_planned<T, FS, G::THREADS, DN_STRIP_SPT, Q>(a.st, a.fr, role_id, reinterpret_cast<float*>(smem_raw));
+        else
+            strip_block<T, FS, G::THREADS, DN_STRIP_SPT>(a.st, a.fr, role_id, reinterpret_cast<float*>(smem_raw));
         return;
     }
     if (role_id >= (unsigned)a.interior_blocks)
@@ -213,12 +216,14 @@ __global__ void __launch_bounds__((DownGeom<T, FS, Q, NX, NY>::THREADS), 2)
 }
 
 template <typename T, int FS, int Q, int NX, int NY, int CVT, int NPASS>
-int launch_down_cfg(DownArgs& a, const DownWeightsN<FS, Q, NPASS>& w, long long strip_blocks_of, int n_frames, cudaStream_t st,
+int launch_down_cfg(const jinc_table* t, DownArgs& a, const DownWeightsN<FS, Q, NPASS>& w, long long strip_blocks_of, int n_frames, cudaStream_t st,
                     const Rect* rects, int n_rects)
 {
     using G = DownGeom<T, FS, Q, NX, NY>;
-    const long long strip_blocks =
+    long long strip_blocks =
         strip_blocks_of ? set_strip_rects(a.st, rects, n_rects, G::THREADS * DN_STRIP_SPT, DN_STRIP_MAX_PW, G::SMEM) * a.fr.n_planes : 0;
+    if (strip_blocks_of && NPASS == 1 && a.want_strip_plan && attach_strip_plan(t, a.st, G::THREADS, DN_STRIP_SPT))
+        strip_blocks = (long long)a.st.blocks_per_plane * a.fr.n_planes;
     a.tiles_x = (a.x1 - a.x0 + DN_TW - 1) / DN_TW;
     a.tiles_per_plane = a.tiles_x * ((a.y1 - a.y0 + G::TH - 1) / G::TH);
     a.tiles_x_magic = div_magic((unsigned)a.tiles_x);
@@ -281,16 +286,16 @@ int launch_down_fs(const jinc_table* t, DownArgs& a, const int* wblocks, bool wa
         }
     }
     if constexpr (sizeof(T) == 4) {
-        return launch_down_cfg<T, FS, Q, DN_NX, DN_NY, DN_CVT_FLOAT, NPASS>(a, w, want_strips, n_frames, st, rects, n_rects);
+        return launch_down_cfg<T, FS, Q, DN_NX, DN_NY, DN_CVT_FLOAT, NPASS>(t, a, w, want_strips, n_frames, st, rects, n_rects);
     } else {
         if (bits <= 15) {
             // f = 0.5 + (x << pre_shift) / 65536  =>  sum(w f) = 0.5 sum(w) + sum(w x) * 2^(pre_shift - 16)
             a.pre_shift = 15 - bits;
             a.out_scale = (float)(1 << (16 - a.pre_shift));
-            return launch_down_cfg<T, FS, Q, DN_NX, DN_NY, DN_CVT_PRMT, NPASS>(a, w, want_strips, n_frames, st, rects, n_rects);
+            return launch_down_cfg<T, FS, Q, DN_NX, DN_NY, DN_CVT_PRMT, NPASS>(t, a, w, want_strips, n_frames, st, rects, n_rects);
         }
         if constexpr (sizeof(T) == 2)
-            return launch_down_cfg<T, FS, Q, DN_NX, DN_NY, DN_CVT_I2F, NPASS>(a, w, want_strips, n_frames, st, rects, n_rects);
+            return launch_down_cfg<T, FS, Q, DN_NX, DN_NY, DN_CVT_I2F, NPASS>(t, a, w, want_strips, n_frames, st, rects, n_rects);
         return 1;
     }
 }

@@ -141,6 +141,10 @@ struct StripPlanPatch {
     int32_t n_wb;                 // weight blocks staged in shared memory; < 0: too many, read from the packed copy
     uint32_t wdata_off;           // first float of the patch's packed weight blocks in StripPlan::d_wdata
     uint32_t tile_floats;         // shared-memory offset of the staged blocks (footprint rounded up to 16 bytes)
+    int32_t row_stride;           // floats per staged footprint row (fw, or step * sub when de-interleaved)
+    int32_t sub;                  // de-interleaved rows: column c sits at (c % step) * sub + c / step
+    int32_t deint;                // 1: the footprint is staged de-interleaved by the window step (patches of row runs only)
+    int32_t pad_;
 };
 enum { JINC_SK_NONE = 0, JINC_SK_RUN_ROWS, JINC_SK_RUN_COLS, JINC_SK_FUSED_SHARED, JINC_SK_FUSED_SEP, JINC_SK_PER_SAMPLE };
 struct StripPlan {

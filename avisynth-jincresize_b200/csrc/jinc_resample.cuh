@@ -238,6 +238,9 @@ struct StripArgs {
     int plan_px, plan_py; // phase period of the outputs: distance of a planned thread's samples
 };
 
+// whole-frame launches: the strip blocks of a table with a plan run from it (jinc_resize.cu)
+bool attach_strip_plan(const jinc_table* t, StripArgs& st, int threads, int spt);
+
 struct FrameSet {
     PlanePtrs one;           // used when frames == nullptr
     const PlanePtrs* frames; // device array [grid.y] for batched launches
@@ -826,12 +829,29 @@ __device__ __forceinline__ void strip_block(const StripArgs& a, const FrameSet& 
 // read the packed copy).  Every sample is accumulated in the same tap order as in strip_block (row-major, one fused
 // multiply-add per tap): both paths give identical bits.
 
+// De-interleaved footprint of a patch of row runs: the lanes of a warp are spt * step columns apart, so column c sits at
+// (c % (spt * step)) * sub + c / (spt * step): the same element of consecutive lanes in consecutive words.  `sub` covers
+// the widest patch (64 outputs) and is odd, which puts the two patch rows of a warp on different banks.
+__host__ __device__ constexpr int plan_deint_sub(int step, int spt, int fs)
+{
+    return ((64 * step + fs + step + spt * step - 1) / (spt * step)) | 1;
+}
+
 template <bool WS>
 __device__ __forceinline__ float4 plan_w4(const float* __restrict__ w)
 {
     if (WS)
         return *reinterpret_cast<const float4*>(w); // shared memory
     return __ldg(reinterpret_cast<const float4*>(w));
+}
+
+// weight block of a record of a patch whose blocks are not staged: straight from the table (sel << 31 | block)
+template <int FSC>
+__device__ __forceinline__ const float* plan_block(const StripArgs& a, uint32_t z)
+{
+    constexpr int WBF = FSC * ((FSC + 3) & ~3);
+    const float* __restrict__ base = (z >> 31) ? a.border_wb : (a.weights_p ? a.weights_p : a.weights);
+    return base + (size_t)(z & 0x7fffffffu) * WBF;
 }
 
 template <bool WS, int FSP>
@@ -848,28 +868,61 @@ __device__ __forceinline__ void plan_weight_row(const float* __restrict__ w, flo
 }
 
 // SPT same-block samples of one row whose window origins are STEP apart: a window row of FSC + (SPT-1)*STEP staged
-// values is read once and feeds SPT x FSC FMAs
-template <typename T, int FSC, int SPT, int STEP, bool WS>
-__device__ __forceinline__ void plan_run_rows(const float* __restrict__ s, int fw, const float* __restrict__ w, T* __restrict__ o, int xstep,
-                                              float peak)
+// values is read once and feeds SPT x FSC FMAs.  DEINT: the footprint is staged de-interleaved (plan_deint_sub) and the
+// thread's window starts on a multiple of SPT * STEP: every shared-memory offset is an immediate.
+template <typename T, int FSC, int SPT, int STEP, bool WS, bool DEINT>
+__device__ __forceinline__ void plan_run_rows(const float* __restrict__ s, int rs, const float* __restrict__ w, T* __restrict__ o, int xstep, float peak)
 {
-    constexpr int FSP = (FSC + 3) & ~3, SEG = FSC + (SPT - 1) * STEP;
+    constexpr int FSP = (FSC + 3) & ~3, SEG = FSC + (SPT - 1) * STEP, D = SPT * STEP, SUBC = plan_deint_sub(STEP, SPT, FSC);
     float acc[SPT];
 #pragma unroll
     for (int k = 0; k < SPT; ++k)
         acc[k] = 0.f;
+    if constexpr (FSC > 9 && !WS) {
+        // wide windows, weights from global memory: the next weight row is in flight while this one is applied
+        float4 wn[FSP / 4];
+#pragma unroll
+        for (int q = 0; q < FSP / 4; ++q)
+            wn[q] = plan_w4<false>(w + 4 * q);
+#pragma unroll 1
+        for (int ly = 0; ly < FSC; ++ly) {
+            float seg[SEG], wr[FSP];
+#pragma unroll
+            for (int q = 0; q < FSP / 4; ++q) {
+                wr[4 * q] = wn[q].x;
+                wr[4 * q + 1] = wn[q].y;
+                wr[4 * q + 2] = wn[q].z;
+                wr[4 * q + 3] = wn[q].w;
+            }
+            const float* __restrict__ wnext = w + min(ly + 1, FSC - 1) * FSP;
+#pragma unroll
+            for (int q = 0; q < FSP / 4; ++q)
+                wn[q] = plan_w4<false>(wnext + 4 * q);
+            const float* __restrict__ srow = s + ly * (DEINT ? D * SUBC : rs);
+#pragma unroll
+            for (int i = 0; i < SEG; ++i)
+                seg[i] = DEINT ? srow[(i % D) * SUBC + i / D] : srow[i];
+#pragma unroll
+            for (int lx = 0; lx < FSC; ++lx)
+#pragma unroll
+                for (int k = 0; k < SPT; ++k)
+                    acc[k] = fmaf(seg[lx + k * STEP], wr[lx], acc[k]);
+        }
+    } else {
 #pragma unroll(FSC <= 9 ? FSC : 1)
-    for (int ly = 0; ly < FSC; ++ly) {
-        float seg[SEG], wr[FSP];
-        plan_weight_row<WS, FSP>(w + ly * FSP, wr);
+        for (int ly = 0; ly < FSC; ++ly) {
+            float seg[SEG], wr[FSP];
+            plan_weight_row<WS, FSP>(w + ly * FSP, wr);
+            const float* __restrict__ srow = s + ly * (DEINT ? D * SUBC : rs);
 #pragma unroll
-        for (int i = 0; i < SEG; ++i)
-            seg[i] = s[ly * fw + i];
+            for (int i = 0; i < SEG; ++i)
+                seg[i] = DEINT ? srow[(i % D) * SUBC + i / D] : srow[i];
 #pragma unroll
-        for (int lx = 0; lx < FSC; ++lx)
+            for (int lx = 0; lx < FSC; ++lx)
 #pragma unroll
-            for (int k = 0; k < SPT; ++k)
-                acc[k] = fmaf(seg[lx + k * STEP], wr[lx], acc[k]);
+                for (int k = 0; k < SPT; ++k)
+                    acc[k] = fmaf(seg[lx + k * STEP], wr[lx], acc[k]);
+        }
     }
 #pragma unroll
     for (int k = 0; k < SPT; ++k)
@@ -887,21 +940,51 @@ __device__ __forceinline__ void plan_run_cols(const float* __restrict__ s, int f
 #pragma unroll
     for (int k = 0; k < SPT; ++k)
         acc[k] = 0.f;
+    if constexpr (FSC <= 9) {
 #pragma unroll
-    for (int r = 0; r < FSC + (SPT - 1) * STEP; ++r) {
-        float seg[FSC];
+        for (int r = 0; r < FSC + (SPT - 1) * STEP; ++r) {
+            float seg[FSC];
 #pragma unroll
-        for (int i = 0; i < FSC; ++i)
-            seg[i] = s[r * fw + i];
+            for (int i = 0; i < FSC; ++i)
+                seg[i] = s[r * fw + i];
 #pragma unroll
-        for (int k = 0; k < SPT; ++k) {
-            const int ly = r - k * STEP; // weight row of output k (a constant after unrolling)
-            if (ly >= 0 && ly < FSC) {
-                float wr[FSP];
-                plan_weight_row<WS, FSP>(w + ly * FSP, wr);
+            for (int k = 0; k < SPT; ++k) {
+                const int ly = r - k * STEP; // weight row of output k (a constant after unrolling)
+                if (ly >= 0 && ly < FSC) {
+                    float wr[FSP];
+                    plan_weight_row<WS, FSP>(w + ly * FSP, wr);
 #pragma unroll
-                for (int lx = 0; lx < FSC; ++lx)
-                    acc[k] = fmaf(seg[lx], wr[lx], acc[k]);
+                    for (int lx = 0; lx < FSC; ++lx)
+                        acc[k] = fmaf(seg[lx], wr[lx], acc[k]);
+                }
+            }
+        }
+    } else {
+        // wide windows: the row loop stays rolled, which outputs a source row feeds is tested at run time (the same for
+        // every thread)
+#pragma unroll 1
+        for (int r = 0; r < FSC + (SPT - 1) * STEP; ++r) {
+            float seg[FSC];
+#pragma unroll
+            for (int i = 0; i < FSC; ++i)
+                seg[i] = s[r * fw + i];
+#pragma unroll
+            for (int k = 0; k < SPT; ++k) {
+                const int ly = r - k * STEP;
+                if (ly >= 0 && ly < FSC) {
+                    const float* __restrict__ wrow = w + ly * FSP;
+#pragma unroll
+                    for (int q = 0; q < FSP / 4; ++q) {
+                        const float4 t = plan_w4<WS>(wrow + 4 * q);
+                        acc[k] = fmaf(seg[4 * q], t.x, acc[k]);
+                        if (4 * q + 1 < FSC)
+                            acc[k] = fmaf(seg[4 * q + 1], t.y, acc[k]);
+                        if (4 * q + 2 < FSC)
+                            acc[k] = fmaf(seg[4 * q + 2], t.z, acc[k]);
+                        if (4 * q + 3 < FSC)
+                            acc[k] = fmaf(seg[4 * q + 3], t.w, acc[k]);
+                    }
+                }
             }
         }
     }
@@ -912,7 +995,7 @@ __device__ __forceinline__ void plan_run_cols(const float* __restrict__ s, int f
 
 // SPT samples with separate windows, interleaved; SHARED: one weight block for all of them
 template <typename T, int FSC, int SPT, bool SHARED, bool WS>
-__device__ __forceinline__ void plan_fused(const uint4 (&r)[SPT], unsigned live, const float* __restrict__ tile, int fw,
+__device__ __forceinline__ void plan_fused(const StripArgs& a, const uint4 (&r)[SPT], unsigned live, const float* __restrict__ tile, int fw,
                                            const float* __restrict__ wbase, T* __restrict__ dst, long long dp, float peak)
 {
     constexpr int FSP = (FSC + 3) & ~3, NW = SHARED ? 1 : SPT;
@@ -926,34 +1009,70 @@ __device__ __forceinline__ void plan_fused(const uint4 (&r)[SPT], unsigned live,
     }
 #pragma unroll
     for (int k = 0; k < NW; ++k)
-        w[k] = wbase + r[k].z;
-#pragma unroll 1
-    for (int ly = 0; ly < FSC; ++ly) {
+        w[k] = WS ? wbase + r[k].z : plan_block<FSC>(a, r[k].z);
+    if constexpr (SHARED && FSC > 9 && !WS) {
+        // wide windows, one block read from global memory: the next weight row is in flight while this one is applied
+        float4 wn[FSP / 4];
 #pragma unroll
-        for (int q = 0; q < FSP / 4; ++q) {
-            float4 t[NW];
+        for (int q = 0; q < FSP / 4; ++q)
+            wn[q] = plan_w4<false>(w[0] + 4 * q);
+#pragma unroll 1
+        for (int ly = 0; ly < FSC; ++ly) {
+            float4 wc[FSP / 4];
+#pragma unroll
+            for (int q = 0; q < FSP / 4; ++q)
+                wc[q] = wn[q];
+            const float* __restrict__ wnext = w[0] + min(ly + 1, FSC - 1) * FSP;
+#pragma unroll
+            for (int q = 0; q < FSP / 4; ++q)
+                wn[q] = plan_w4<false>(wnext + 4 * q);
+#pragma unroll
+            for (int q = 0; q < FSP / 4; ++q) {
+                const int lx = 4 * q;
+#pragma unroll
+                for (int k = 0; k < SPT; ++k) {
+                    acc[k] = fmaf(s[k][lx], wc[q].x, acc[k]);
+                    if (lx + 1 < FSC)
+                        acc[k] = fmaf(s[k][lx + 1], wc[q].y, acc[k]);
+                    if (lx + 2 < FSC)
+                        acc[k] = fmaf(s[k][lx + 2], wc[q].z, acc[k]);
+                    if (lx + 3 < FSC)
+                        acc[k] = fmaf(s[k][lx + 3], wc[q].w, acc[k]);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < SPT; ++k)
+                s[k] += fw;
+        }
+    } else {
+#pragma unroll 1
+        for (int ly = 0; ly < FSC; ++ly) {
+#pragma unroll
+            for (int q = 0; q < FSP / 4; ++q) {
+                float4 t[NW];
+#pragma unroll
+                for (int k = 0; k < NW; ++k)
+                    t[k] = plan_w4<WS>(w[k] + 4 * q);
+                const int lx = 4 * q;
+#pragma unroll
+                for (int k = 0; k < SPT; ++k) {
+                    const float4& tk = t[SHARED ? 0 : k];
+                    acc[k] = fmaf(s[k][lx], tk.x, acc[k]);
+                    if (lx + 1 < FSC)
+                        acc[k] = fmaf(s[k][lx + 1], tk.y, acc[k]);
+                    if (lx + 2 < FSC)
+                        acc[k] = fmaf(s[k][lx + 2], tk.z, acc[k]);
+                    if (lx + 3 < FSC)
+                        acc[k] = fmaf(s[k][lx + 3], tk.w, acc[k]);
+                }
+            }
 #pragma unroll
             for (int k = 0; k < NW; ++k)
-                t[k] = plan_w4<WS>(w[k] + 4 * q);
-            const int lx = 4 * q;
+                w[k] += FSP;
 #pragma unroll
-            for (int k = 0; k < SPT; ++k) {
-                const float4& tk = t[SHARED ? 0 : k];
-                acc[k] = fmaf(s[k][lx], tk.x, acc[k]);
-                if (lx + 1 < FSC)
-                    acc[k] = fmaf(s[k][lx + 1], tk.y, acc[k]);
-                if (lx + 2 < FSC)
-                    acc[k] = fmaf(s[k][lx + 2], tk.z, acc[k]);
-                if (lx + 3 < FSC)
-                    acc[k] = fmaf(s[k][lx + 3], tk.w, acc[k]);
-            }
+            for (int k = 0; k < SPT; ++k)
+                s[k] += fw;
         }
-#pragma unroll
-        for (int k = 0; k < NW; ++k)
-            w[k] += FSP;
-#pragma unroll
-        for (int k = 0; k < SPT; ++k)
-            s[k] += fw;
     }
 #pragma unroll
     for (int k = 0; k < SPT; ++k)
@@ -970,23 +1089,25 @@ __device__ __noinline__ void strip_block_unplanned(const StripArgs& a, const Fra
 
 template <typename T, int FSC, int THREADS, int SPT, int STEP, bool WS>
 __device__ __forceinline__ void plan_accumulate(const StripArgs& a, const FrameSet& fsx, unsigned plane, const uint4& r0, const uint4* __restrict__ recs,
-                                                const float* __restrict__ tile, int fw, const float* __restrict__ wbase)
+                                                const float* __restrict__ tile, int rs, bool deint, const float* __restrict__ wbase)
 {
     const unsigned kind = r0.w & 0xffu, live = r0.w >> 8;
     const PlanePtrs& pp = frame_ptrs(fsx);
     T* __restrict__ dst = static_cast<T*>(pp.dst[plane]);
     const long long dp = pp.dst_pitch[plane];
+    const float* __restrict__ w0 = WS ? wbase + r0.z : plan_block<FSC>(a, r0.z); // sample 0's weight block
     if (kind == JINC_SK_RUN_ROWS) {
-        plan_run_rows<T, FSC, SPT, STEP, WS>(tile + (int)r0.y, fw, wbase + r0.z, dst + (long long)(r0.x >> 16) * dp + (r0.x & 0xffffu), a.plan_px,
-                                             fsx.peak);
+        T* __restrict__ o = dst + (long long)(r0.x >> 16) * dp + (r0.x & 0xffffu);
+        if (STEP > 1 && deint)
+            plan_run_rows<T, FSC, SPT, STEP, WS, (STEP > 1)>(tile + (int)r0.y, rs, w0, o, a.plan_px, fsx.peak);
+        else
+            plan_run_rows<T, FSC, SPT, STEP, WS, false>(tile + (int)r0.y, rs, w0, o, a.plan_px, fsx.peak);
         return;
     }
-    if constexpr (FSC <= 9) {
-        if (kind == JINC_SK_RUN_COLS) {
-            plan_run_cols<T, FSC, SPT, STEP, WS>(tile + (int)r0.y, fw, wbase + r0.z, dst + (long long)(r0.x >> 16) * dp + (r0.x & 0xffffu),
-                                                 (long long)a.plan_py * dp, fsx.peak);
-            return;
-        }
+    if (kind == JINC_SK_RUN_COLS) {
+        plan_run_cols<T, FSC, SPT, STEP, WS>(tile + (int)r0.y, rs, w0, dst + (long long)(r0.x >> 16) * dp + (r0.x & 0xffffu),
+                                             (long long)a.plan_py * dp, fsx.peak);
+        return;
     }
     uint4 r[SPT];
     r[0] = r0;
@@ -994,9 +1115,9 @@ __device__ __forceinline__ void plan_accumulate(const StripArgs& a, const FrameS
     for (int k = 1; k < SPT; ++k)
         r[k] = __ldg(recs + k * THREADS);
     if (kind == JINC_SK_FUSED_SHARED) {
-        plan_fused<T, FSC, SPT, true, WS>(r, live, tile, fw, wbase, dst, dp, fsx.peak);
+        plan_fused<T, FSC, SPT, true, WS>(a, r, live, tile, rs, wbase, dst, dp, fsx.peak);
     } else if (kind == JINC_SK_FUSED_SEP) {
-        plan_fused<T, FSC, SPT, false, WS>(r, live, tile, fw, wbase, dst, dp, fsx.peak);
+        plan_fused<T, FSC, SPT, false, WS>(a, r, live, tile, rs, wbase, dst, dp, fsx.peak);
     } else { // JINC_SK_PER_SAMPLE: no vector-readable block (per-pixel border weights): straight from global memory
 #pragma unroll 1
         for (int k = 0; k < SPT; ++k)
@@ -1009,16 +1130,20 @@ template <typename T, int FSC, int THREADS, int SPT, int STEP>
 __device__ __forceinline__ void strip_block_planned(const StripArgs& a, const FrameSet& fsx, unsigned sb, float* __restrict__ tile)
 {
     static_assert(FSC > 0, "planned strips need a compile-time window size");
+    static_assert(sizeof(StripPlanPatch) == 48, "three 16-byte loads");
     constexpr int FSP = (FSC + 3) & ~3, WB4 = FSC * FSP / 4;
     const unsigned plane = div_by(sb, a.blocks_per_plane_magic);
     const unsigned pid = sb - plane * a.blocks_per_plane;
     const int4* __restrict__ pd = reinterpret_cast<const int4*>(a.plan_patches + pid);
     const int4 pa = __ldg(pd);     // sx_lo, sy_lo, fw, fh
     const int4 pb = __ldg(pd + 1); // magic, n_wb, wdata_off, tile_floats
+    const int4 pc = __ldg(pd + 2); // row_stride, sub, deint
     const uint4* __restrict__ recs = a.plan_threads + (size_t)pid * (unsigned)(SPT * THREADS) + threadIdx.x;
     const uint4 r0 = __ldg(recs);
     const PlanePtrs& pp = frame_ptrs(fsx);
-    const int fw = pa.z;
+    constexpr int D = SPT * STEP, SUBC = plan_deint_sub(STEP, SPT, FSC);
+    const int fw = pa.z, rs = pc.x;
+    const bool deint = STEP > 1 && pc.z != 0; // then rs == D * SUBC
     const bool ws = pb.y >= 0; // the patch's weight blocks are staged
     float* __restrict__ wsm = tile + pb.w;
     const float* __restrict__ wglobal = a.plan_wdata + (unsigned)pb.z;
@@ -1037,16 +1162,18 @@ __device__ __forceinline__ void strip_block_planned(const StripArgs& a, const Fr
             wv[u] = __ldg(wsrc + min((int)threadIdx.x + u * THREADS, max(nw4 - 1, 0)));
         for (unsigned e0 = threadIdx.x; e0 < n; e0 += 4 * THREADS) {
             T v[4];
+            unsigned at[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) { // all four loads are issued before the first conversion
                 const unsigned e = min(e0 + u * THREADS, n - 1);
-                const unsigned row = __umulhi(e, magic);
-                v[u] = __ldg(src + (int)(row * (unsigned)pitch + (e - row * (unsigned)fw)));
+                const unsigned row = __umulhi(e, magic), col = e - row * (unsigned)fw;
+                v[u] = __ldg(src + (int)(row * (unsigned)pitch + col));
+                at[u] = deint ? row * (unsigned)(D * SUBC) + (col % (unsigned)D) * (unsigned)SUBC + col / (unsigned)D : e;
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u)
                 if (e0 + u * THREADS < n)
-                    tile[e0 + u * THREADS] = sample_to_float(v[u]);
+                    tile[at[u]] = sample_to_float(v[u]);
         }
 #pragma unroll
         for (int u = 0; u < 2; ++u)
@@ -1059,202 +1186,9 @@ __device__ __forceinline__ void strip_block_planned(const StripArgs& a, const Fr
     if ((r0.w & 0xffu) == JINC_SK_NONE)
         return;
     if (ws)
-        plan_accumulate<T, FSC, THREADS, SPT, STEP, true>(a, fsx, plane, r0, recs, tile, fw, wsm);
+        plan_accumulate<T, FSC, THREADS, SPT, STEP, true>(a, fsx, plane, r0, recs, tile, rs, deint, wsm);
     else
-        plan_accumulate<T, FSC, THREADS, SPT, STEP, false>(a, fsx, plane, r0, recs, tile, fw, wglobal);
-}
-
-// Host side of the plan.  The strips (up to four rectangles) are cut into patches: 64 outputs wide in the wide strips,
-// 8 in the tall ones, as tall as the block has threads for.  In a wide strip a thread takes up to SPT outputs of one row
-// that are px apart (one residue class of the row), in a tall strip up to SPT outputs of one column that are py apart;
-// how they are accumulated is decided here, by the rules of strip_block.
-struct StripPlanParams {
-    int threads, spt;
-    int px, py;   // phase period of the outputs along x and y
-    int step;     // distance of the window origins of same-phase neighbours (both axes)
-    unsigned smem_floats;
-};
-
-struct StripPlanHost {
-    std::vector<StripPlanPatch> patches;
-    std::vector<uint4> recs;
-    std::vector<uint32_t> wlist; // sel << 31 | block, in packing order
-    unsigned n_staged = 0;       // patches whose weight blocks fit in shared memory
-    bool ok = false;
-};
-
-inline void build_strip_plan_host(const jinc_table* t, const Rect* rects, int n_rects, const StripPlanParams& pp, StripPlanHost& out)
-{
-    const int fs = t->sc.fs, fsp = (fs + 3) & ~3, wbf = fs * fsp;
-    const int THREADS = pp.threads, SPT = pp.spt;
-    const std::vector<int32_t>&start_x = t->h_start[0], &start_y = t->h_start[1], &rank_x = t->h_rank[0], &rank_y = t->h_rank[1];
-    const bool have_classes = !t->h_border_block.empty();
-    const int phase_stride = t->d_weights_p ? fsp : fs;
-    const int n_rank_x = t->ax[0].n_rank;
-    out = StripPlanHost{};
-    struct Meta {
-        int x, y, sx, sy, wstride;
-        uint32_t wkey; // sel << 31 | block; only meaningful when wstride != 0
-    };
-    struct Item {
-        int x[8], y[8], n;
-    };
-    std::vector<Meta> meta((size_t)SPT);
-    std::vector<Item> items;
-    std::vector<uint32_t> keys; // distinct weight blocks of the patch, in first-use order
-    if (SPT > 8)
-        return;
-    for (int ri = 0; ri < n_rects; ++ri) {
-        const Rect rc = rects[ri];
-        const int w = rc.x1 - rc.x0, h = rc.y1 - rc.y0;
-        if (w <= 0 || h <= 0)
-            continue;
-        const bool rows = w >= h; // top/bottom strips are wide, left/right strips are tall
-        const int pw = rows ? 64 : 8;
-        for (int ox0 = rc.x0; ox0 < rc.x1; ox0 += pw) {
-            const int nx = std::min(pw, rc.x1 - ox0);
-            // patch height: as many rows as the block has threads for
-            int ph;
-            if (rows) {
-                int per_row = 0;
-                for (int p = 0; p < pp.px; ++p) {
-                    int cnt = 0;
-                    for (int x = ox0; x < ox0 + nx; ++x)
-                        cnt += (x % pp.px) == p;
-                    per_row += (cnt + SPT - 1) / SPT;
-                }
-                ph = std::max(1, THREADS / std::max(per_row, 1));
-                if (per_row > THREADS)
-                    return; // cannot happen for 64-wide patches
-            } else {
-                const int m = THREADS / (nx * pp.py); // groups of SPT * py rows
-                if (m < 1)
-                    return;
-                ph = m * SPT * pp.py;
-            }
-            for (int oy0 = rc.y0; oy0 < rc.y1; oy0 += ph) {
-                const int ny = std::min(ph, rc.y1 - oy0);
-                const int sx_lo = start_x[ox0], sy_lo = start_y[oy0];
-                const int fw = start_x[ox0 + nx - 1] + fs - sx_lo, fh = start_y[oy0 + ny - 1] + fs - sy_lo;
-                if ((long long)fw * fh > (long long)pp.smem_floats)
-                    return; // footprints of the planned kernel families always fit; otherwise no plan at all
-                // the work items of the patch
-                items.clear();
-                if (rows) {
-                    for (int y = oy0; y < oy0 + ny; ++y)
-                        for (int p = 0; p < pp.px; ++p) {
-                            Item it{};
-                            for (int x = ox0; x < ox0 + nx; ++x) {
-                                if (x % pp.px != p)
-                                    continue;
-                                it.x[it.n] = x;
-                                it.y[it.n] = y;
-                                if (++it.n == SPT) {
-                                    items.push_back(it);
-                                    it.n = 0;
-                                }
-                            }
-                            if (it.n)
-                                items.push_back(it);
-                        }
-                } else {
-                    for (int x = ox0; x < ox0 + nx; ++x)
-                        for (int p = 0; p < pp.py; ++p) {
-                            Item it{};
-                            for (int y = oy0; y < oy0 + ny; ++y) {
-                                if (y % pp.py != p)
-                                    continue;
-                                it.x[it.n] = x;
-                                it.y[it.n] = y;
-                                if (++it.n == SPT) {
-                                    items.push_back(it);
-                                    it.n = 0;
-                                }
-                            }
-                            if (it.n)
-                                items.push_back(it);
-                        }
-                }
-                if ((int)items.size() > THREADS)
-                    return;
-                StripPlanPatch pd{};
-                pd.sx_lo = sx_lo;
-                pd.sy_lo = sy_lo;
-                pd.fw = fw;
-                pd.fh = fh;
-                pd.magic = 0xFFFFFFFFu / (unsigned)fw + 1u;
-                pd.tile_floats = ((unsigned)(fw * fh) + 3u) & ~3u;
-                const size_t rec0 = out.recs.size();
-                out.recs.resize(rec0 + (size_t)SPT * THREADS, make_uint4(0, 0, 0, 0));
-                uint4* prec = out.recs.data() + rec0;
-                keys.clear();
-                for (size_t tid = 0; tid < items.size(); ++tid) {
-                    const Item& it = items[tid];
-                    const unsigned live = (1u << it.n) - 1u;
-                    for (int k = 0; k < it.n; ++k) {
-                        Meta& m = meta[k];
-                        m.x = it.x[k];
-                        m.y = it.y[k];
-                        m.sx = start_x[m.x];
-                        m.sy = start_y[m.y];
-                        const int rx = rank_x[m.x], ry = rank_y[m.y];
-                        if (rx >= 0 && ry >= 0) {
-                            m.wkey = (uint32_t)(ry * n_rank_x + rx);
-                            m.wstride = phase_stride;
-                        } else if (have_classes) {
-                            m.wkey = 0x80000000u | (uint32_t)t->h_border_block[(size_t)jinc_border_slot(t->bgeom, m.x, m.y)];
-                            m.wstride = fsp;
-                        } else {
-                            m.wkey = 0;
-                            m.wstride = 0;
-                        }
-                    }
-                    bool same = true, vec = true;
-                    for (int k = 0; k < SPT; ++k) {
-                        if (k >= it.n)
-                            meta[k] = meta[0]; // computed, not stored
-                        same = same && meta[k].wstride == meta[0].wstride && (meta[k].wstride == 0 || meta[k].wkey == meta[0].wkey);
-                        vec = vec && meta[k].wstride != 0 && (meta[k].wstride & 3) == 0 && meta[k].wstride == meta[0].wstride;
-                    }
-                    unsigned kind = JINC_SK_PER_SAMPLE;
-                    if (vec) {
-                        kind = same ? JINC_SK_FUSED_SHARED : JINC_SK_FUSED_SEP;
-                        if (same && it.n == SPT) {
-                            bool run = true;
-                            for (int k = 1; k < SPT; ++k)
-                                run = run && (rows ? (meta[k].sy == meta[0].sy && meta[k].sx == meta[0].sx + k * pp.step)
-                                                   : (meta[k].sx == meta[0].sx && meta[k].sy == meta[0].sy + k * pp.step));
-                            if (run && rows)
-                                kind = JINC_SK_RUN_ROWS;
-                            else if (run && fs <= 9)
-                                kind = JINC_SK_RUN_COLS;
-                        }
-                    }
-                    for (int k = 0; k < SPT; ++k) {
-                        const Meta& m = meta[k];
-                        uint32_t slot = 0;
-                        if (kind != JINC_SK_PER_SAMPLE) {
-                            size_t j = 0;
-                            while (j < keys.size() && keys[j] != m.wkey)
-                                ++j;
-                            if (j == keys.size())
-                                keys.push_back(m.wkey);
-                            slot = (uint32_t)j * (uint32_t)wbf;
-                        }
-                        prec[(size_t)k * THREADS + tid] = make_uint4((uint32_t)m.x | ((uint32_t)m.y << 16),
-                                                                     (uint32_t)((m.sy - sy_lo) * fw + (m.sx - sx_lo)), slot, k == 0 ? (kind | (live << 8)) : 0u);
-                    }
-                }
-                const bool staged = (unsigned long long)pd.tile_floats + (unsigned long long)keys.size() * wbf <= pp.smem_floats;
-                pd.n_wb = staged ? (int32_t)keys.size() : -1;
-                pd.wdata_off = (uint32_t)(out.wlist.size() * (size_t)wbf);
-                out.wlist.insert(out.wlist.end(), keys.begin(), keys.end());
-                out.n_staged += staged ? 1u : 0u;
-                out.patches.push_back(pd);
-            }
-        }
-    }
-    out.ok = !out.patches.empty();
+        plan_accumulate<T, FSC, THREADS, SPT, STEP, false>(a, fsx, plane, r0, recs, tile, rs, deint, nullptr);
 }
 
 // Role of block b in a merged grid of interior tile blocks and `strips` strip blocks: strip block k sits at grid
@@ -1482,6 +1416,7 @@ struct DownArgs {
     unsigned tiles_x_magic, tiles_per_plane_magic; // div_magic of the two tile divisors
     int pre_shift;       // PRMT conversion: samples are staged as x << pre_shift
     float out_scale;     // PRMT conversion: power-of-two rescale of the de-biased sum
+    bool want_strip_plan; // host only: a whole-frame launch, the strips may run from the table's plan
 };
 
 // ---- launch entry points, one explicit instantiation per sample type (jinc_up2x_*.cu, jinc_down_*.cu)
@@ -1522,9 +1457,6 @@ struct CellsArgs {
     unsigned tiles_x_magic, tiles_per_plane_magic;
     bool want_strip_plan; // host only: a whole-frame launch, the strips may run from the table's plan
 };
-
-// whole-frame launches: the strip blocks of a table with a plan run from it (jinc_resize.cu)
-bool attach_strip_plan(const jinc_table* t, StripArgs& st, int threads, int spt);
 
 // defined in jinc_cells.cuh, instantiated in jinc_cells_<type>_q<Q>.cu (one source step Q per translation unit)
 template <typename T, int Q>

@@ -455,6 +455,7 @@ int launch_typed(const jinc_table* t, const FrameSet& fr, int n_frames, int y_be
             a.pass[0].out_x0 = a.x0;
             a.pass[0].out_y0 = a.y0;
             a.interior_blocks = (parts & JINC_PART_INTERIOR) ? 1 : 0; // resolved to the tile count by the launcher
+            a.want_strip_plan = n_rects == 4 && y_begin == 0 && y_end == t->sc.dst_h;
             const int rc = launch_down<T>(t, a, d.qx, &d.wblock, n_rects > 0, n_frames, st, rects, n_rects);
             if (rc != 1) {
                 if (rc == 0)
@@ -548,6 +549,263 @@ void jinc_free_strip_plan(jinc_table* t)
     sp = StripPlan{};
 }
 
+// Host side of the plan.  The strips (up to four rectangles) are cut into patches: 64 outputs wide in the wide strips,
+// 8 in the tall ones, as tall as the block has threads for.  In a wide strip a thread takes up to SPT outputs of one row
+// that are px apart (one residue class of the row), in a tall strip up to SPT outputs of one column that are py apart;
+// how they are accumulated is decided here, by the rules of strip_block.
+struct StripPlanParams {
+    int threads, spt;
+    int px, py;   // phase period of the outputs along x and y
+    int step;     // distance of the window origins of same-phase neighbours (both axes)
+    unsigned smem_floats;
+};
+
+struct StripPlanHost {
+    std::vector<StripPlanPatch> patches;
+    std::vector<uint4> recs;
+    std::vector<uint32_t> wlist; // sel << 31 | block, in packing order
+    unsigned n_staged = 0;       // patches whose weight blocks fit in shared memory
+    bool ok = false;
+};
+
+inline void build_strip_plan_host(const jinc_table* t, const Rect* rects, int n_rects, const StripPlanParams& pp, StripPlanHost& out)
+{
+    const int fs = t->sc.fs, fsp = (fs + 3) & ~3, wbf = fs * fsp;
+    const int THREADS = pp.threads, SPT = pp.spt;
+    const std::vector<int32_t>&start_x = t->h_start[0], &start_y = t->h_start[1], &rank_x = t->h_rank[0], &rank_y = t->h_rank[1];
+    const bool have_classes = !t->h_border_block.empty();
+    const int phase_stride = t->d_weights_p ? fsp : fs;
+    const int n_rank_x = t->ax[0].n_rank;
+    out = StripPlanHost{};
+    struct Meta {
+        int x, y, sx, sy, wstride;
+        uint32_t wkey; // sel << 31 | block; only meaningful when wstride != 0
+    };
+    struct Item {
+        int x[8], y[8], n;
+    };
+    std::vector<Meta> meta((size_t)SPT);
+    std::vector<Item> items;
+    std::vector<uint32_t> keys; // distinct weight blocks of the patch, in first-use order
+    if (SPT > 8)
+        return;
+    if (!have_classes && t->bgeom.total > 0)
+        return; // per-pixel border weights (ratios whose positions are not exactly periodic): the prologue path reads them coalesced
+    for (int ri = 0; ri < n_rects; ++ri) {
+        const Rect rc = rects[ri];
+        const int w = rc.x1 - rc.x0, h = rc.y1 - rc.y0;
+        if (w <= 0 || h <= 0)
+            continue;
+        const bool rows = w >= h; // top/bottom strips are wide, left/right strips are tall
+        const int pw = rows ? 64 : 8;
+        for (int ox0 = rc.x0; ox0 < rc.x1; ox0 += pw) {
+            const int nx = std::min(pw, rc.x1 - ox0);
+            // patch height: as many rows as the block has threads for
+            int ph;
+            if (rows) {
+                int per_row = 0;
+                for (int p = 0; p < pp.px; ++p) {
+                    int cnt = 0;
+                    for (int x = ox0; x < ox0 + nx; ++x)
+                        cnt += (x % pp.px) == p;
+                    per_row += (cnt + SPT - 1) / SPT;
+                }
+                ph = std::max(1, THREADS / std::max(per_row, 1));
+                if (per_row > THREADS)
+                    return; // cannot happen for 64-wide patches
+            } else {
+                const int m = THREADS / (nx * pp.py); // groups of SPT * py rows
+                if (m < 1)
+                    return;
+                ph = m * SPT * pp.py;
+            }
+            for (int oy0 = rc.y0; oy0 < rc.y1; oy0 += ph) {
+                const int ny = std::min(ph, rc.y1 - oy0);
+                const int sx_lo = start_x[ox0], sy_lo = start_y[oy0];
+                const int fw = start_x[ox0 + nx - 1] + fs - sx_lo, fh = start_y[oy0 + ny - 1] + fs - sy_lo;
+                if ((long long)fw * fh > (long long)pp.smem_floats)
+                    return; // footprints of the planned kernel families always fit; otherwise no plan at all
+                // the work items of the patch
+                items.clear();
+                if (rows) {
+                    for (int y = oy0; y < oy0 + ny; ++y)
+                        for (int p = 0; p < pp.px; ++p) {
+                            Item it{};
+                            for (int x = ox0; x < ox0 + nx; ++x) {
+                                if (x % pp.px != p)
+                                    continue;
+                                it.x[it.n] = x;
+                                it.y[it.n] = y;
+                                if (++it.n == SPT) {
+                                    items.push_back(it);
+                                    it.n = 0;
+                                }
+                            }
+                            if (it.n)
+                                items.push_back(it);
+                        }
+                } else if (fs > 9) {
+                    // wide windows never run down a column (see below): a thread's samples need not be neighbours, so
+                    // neighbouring lanes take neighbouring rows (window rows `step` apart: different banks) and a thread's
+                    // samples lie a quarter of the patch apart -- the prologue path's mapping
+                    const int tyn = std::max(1, THREADS / nx), dy = (ny + SPT - 1) / SPT;
+                    for (int ty = 0; ty < std::min(tyn, dy); ++ty)
+                        for (int x = ox0; x < ox0 + nx; ++x) {
+                            Item it{};
+                            for (int k = 0; k < SPT; ++k) {
+                                const int y = oy0 + ty + k * dy;
+                                if (y < oy0 + ny) {
+                                    it.x[it.n] = x;
+                                    it.y[it.n] = y;
+                                    ++it.n;
+                                }
+                            }
+                            if (it.n)
+                                items.push_back(it);
+                        }
+                } else {
+                    // groups of one residue class down a column; neighbouring lanes take neighbouring columns (their windows
+                    // start in the same source rows: no bank conflicts between them)
+                    for (int g = 0;; ++g) {
+                        bool any = false;
+                        for (int p = 0; p < pp.py; ++p)
+                            for (int x = ox0; x < ox0 + nx; ++x) {
+                                Item it{};
+                                int seen = 0;
+                                for (int y = oy0; y < oy0 + ny; ++y) {
+                                    if (y % pp.py != p)
+                                        continue;
+                                    if (seen / SPT == g) {
+                                        it.x[it.n] = x;
+                                        it.y[it.n] = y;
+                                        ++it.n;
+                                    }
+                                    ++seen;
+                                }
+                                if (it.n) {
+                                    items.push_back(it);
+                                    any = true;
+                                }
+                            }
+                        if (!any)
+                            break;
+                    }
+                }
+                if ((int)items.size() > THREADS)
+                    return;
+                StripPlanPatch pd{};
+                pd.sx_lo = sx_lo;
+                pd.sy_lo = sy_lo;
+                pd.fw = fw;
+                pd.fh = fh;
+                pd.magic = 0xFFFFFFFFu / (unsigned)fw + 1u;
+                pd.row_stride = fw;
+                pd.sub = 0;
+                pd.deint = 0;
+                const size_t rec0 = out.recs.size();
+                out.recs.resize(rec0 + (size_t)SPT * THREADS, make_uint4(0, 0, 0, 0));
+                uint4* prec = out.recs.data() + rec0;
+                keys.clear();
+                for (size_t tid = 0; tid < items.size(); ++tid) {
+                    const Item& it = items[tid];
+                    const unsigned live = (1u << it.n) - 1u;
+                    for (int k = 0; k < it.n; ++k) {
+                        Meta& m = meta[k];
+                        m.x = it.x[k];
+                        m.y = it.y[k];
+                        m.sx = start_x[m.x];
+                        m.sy = start_y[m.y];
+                        const int rx = rank_x[m.x], ry = rank_y[m.y];
+                        if (rx >= 0 && ry >= 0) {
+                            m.wkey = (uint32_t)(ry * n_rank_x + rx);
+                            m.wstride = phase_stride;
+                        } else if (have_classes) {
+                            m.wkey = 0x80000000u | (uint32_t)t->h_border_block[(size_t)jinc_border_slot(t->bgeom, m.x, m.y)];
+                            m.wstride = fsp;
+                        } else {
+                            m.wkey = 0;
+                            m.wstride = 0;
+                        }
+                    }
+                    bool same = true, vec = true;
+                    for (int k = 0; k < SPT; ++k) {
+                        if (k >= it.n)
+                            meta[k] = meta[0]; // computed, not stored
+                        same = same && meta[k].wstride == meta[0].wstride && (meta[k].wstride == 0 || meta[k].wkey == meta[0].wkey);
+                        vec = vec && meta[k].wstride != 0 && (meta[k].wstride & 3) == 0 && meta[k].wstride == meta[0].wstride;
+                    }
+                    unsigned kind = JINC_SK_PER_SAMPLE;
+                    if (vec) {
+                        kind = same ? JINC_SK_FUSED_SHARED : JINC_SK_FUSED_SEP;
+                        if (same && it.n == SPT) {
+                            bool run = true;
+                            for (int k = 1; k < SPT; ++k)
+                                run = run && (rows ? (meta[k].sy == meta[0].sy && meta[k].sx == meta[0].sx + k * pp.step)
+                                                   : (meta[k].sx == meta[0].sx && meta[k].sy == meta[0].sy + k * pp.step));
+                            if (run && rows)
+                                kind = JINC_SK_RUN_ROWS;
+                            else if (run && fs <= 9) // wide windows down a column: one weight row for four source rows reads less
+                                kind = JINC_SK_RUN_COLS;
+                        }
+                    }
+                    for (int k = 0; k < SPT; ++k) {
+                        const Meta& m = meta[k];
+                        uint32_t slot = 0;
+                        if (kind != JINC_SK_PER_SAMPLE) {
+                            size_t j = 0;
+                            while (j < keys.size() && keys[j] != m.wkey)
+                                ++j;
+                            if (j == keys.size())
+                                keys.push_back(m.wkey);
+                            slot = (uint32_t)j * (uint32_t)wbf;
+                        }
+                        prec[(size_t)k * THREADS + tid] = make_uint4((uint32_t)m.x | ((uint32_t)m.y << 16),
+                                                                     (uint32_t)((m.sy - sy_lo) * fw + (m.sx - sx_lo)), slot, k == 0 ? (kind | (live << 8)) : 0u);
+                    }
+                }
+                // a patch of row runs whose windows all start on a multiple of spt * step is staged de-interleaved
+                if (pp.step > 1 && !items.empty()) {
+                    const int d = SPT * pp.step, sub = plan_deint_sub(pp.step, SPT, fs), rs = d * sub;
+                    bool pure = fw <= rs;
+                    for (size_t tid = 0; tid < items.size() && pure; ++tid) {
+                        const uint4& r0 = prec[tid];
+                        pure = (r0.w & 0xffu) == JINC_SK_RUN_ROWS && ((int)r0.y % fw) % d == 0;
+                    }
+                    if (pure && (long long)rs * fh <= (long long)pp.smem_floats) {
+                        pd.deint = 1;
+                        pd.sub = sub;
+                        pd.row_stride = rs;
+                        for (size_t tid = 0; tid < items.size(); ++tid) {
+                            uint4& r0 = prec[tid];
+                            const int row = (int)r0.y / fw, col = (int)r0.y % fw;
+                            r0.y = (uint32_t)(row * rs + col / d);
+                        }
+                    }
+                }
+                pd.tile_floats = ((unsigned)(pd.row_stride * fh) + 3u) & ~3u;
+                const bool staged = (unsigned long long)pd.tile_floats + (unsigned long long)keys.size() * wbf <= pp.smem_floats;
+                pd.n_wb = staged ? (int32_t)keys.size() : -1;
+                pd.wdata_off = (uint32_t)(out.wlist.size() * (size_t)wbf);
+                if (staged) {
+                    out.wlist.insert(out.wlist.end(), keys.begin(), keys.end());
+                } else {
+                    // too many blocks for shared memory: the records name the table's own blocks (shared by every patch, so
+                    // they stay in the caches) instead of slots of a packed copy
+                    for (int k = 0; k < SPT; ++k)
+                        for (size_t tid = 0; tid < items.size(); ++tid) {
+                            uint4& rk = prec[(size_t)k * THREADS + tid];
+                            if ((prec[tid].w & 0xffu) != JINC_SK_PER_SAMPLE)
+                                rk.z = keys[rk.z / (uint32_t)wbf];
+                        }
+                }
+                out.n_staged += staged ? 1u : 0u;
+                out.patches.push_back(pd);
+            }
+        }
+    }
+    out.ok = !out.patches.empty();
+}
+
 // whole-frame launches: the strip blocks of a table with a plan run from it (its own patches)
 bool jinc_rs::attach_strip_plan(const jinc_table* t, StripArgs& st, int threads, int spt)
 {
@@ -584,6 +842,14 @@ int jinc_build_strip_plan(jinc_table* t)
         const int d = q * JINC_CELLS_NX, fwc = jinc_cells_footprint(q, fs, JINC_CELLS_NX, 32), fhc = jinc_cells_footprint(q, fs, JINC_CELLS_NY, warps);
         const size_t smem = (size_t)fhc * (size_t)(d * ((fwc + d - 1) / d)) * sizeof(float); // CellsGeom<FS, Q>::SMEM
         pp = StripPlanParams{32 * warps, CL_STRIP_SPT, t->cells.ax[0].P, t->cells.ax[1].P, q, (unsigned)(smem / sizeof(float))};
+    } else if (t->fast_path == JINC_PATH_DOWN_INT && down_supported(t)) {
+        // DownGeom<T, FS, Q, 8, 2> of the integer sample types (128 threads per block; float planes run 64-thread blocks and
+        // keep the prologue path): a lower bound of its shared memory (the row padding left out)
+        const int q = t->down.qx;
+        const int nkw1 = (q & 1) ? (fs + 2) / 2 : ((fs + 1) & ~1) / 2;
+        const int nrowp = (q * (DN_TH - 1) + 2 * nkw1 + 1) / 2, mt = (fs + q - 1) / q, d = q * 8;
+        const int ncol = q * (DN_TW - 1) + q * (mt - 1) + q, sub = (ncol + d - 1) / d;
+        pp = StripPlanParams{128, DN_STRIP_SPT, 1, 1, q, (unsigned)((size_t)nrowp * d * sub)};
     } else {
         return JINC_OK;
     }
