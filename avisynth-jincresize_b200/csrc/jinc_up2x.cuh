@@ -3,11 +3,51 @@
 #ifndef JINC_UP2X_CUH
 #define JINC_UP2X_CUH
 
+#include <cstdlib>
+
 #include "jinc_resample.cuh"
 
 namespace jinc_rs {
 
 constexpr int UP_UNROLL_MAX_FS = 9; // windows up to this size get a fully unrolled row loop
+
+// ---- bulk-copy (TMA engine) staging of float tiles: raw rows land in shared memory asynchronously, one cp.async.bulk per
+//      tile row, all completing on one mbarrier; the pair layout is then made from shared memory instead of from
+//      registers filled by LDG.  Opt-in (JINCRESIZE_B200_TMA=1): measured against the register path in DESIGN.md 4.1.
+template <int FS>
+struct UpTma {
+    using G = UpGeom<FS>;
+    static constexpr int RAWC = (G::NC + 4 + 3) & ~3;  // floats per landed row: the tile's columns from an aligned start
+    static constexpr int ROWS = G::NR + 1;             // raw rows (pair row r needs rows r and r + 1)
+    static constexpr size_t LANDING = (size_t)ROWS * RAWC * sizeof(float);
+    static constexpr size_t SMEM = G::SMEM + LANDING + 16; // + the mbarrier
+};
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+                 "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
 
 // One pair row of the tile applied to the thread's 16 accumulators: phase row 0 uses weight row rr, phase row 1 uses
 // weight row rr - OY1.
@@ -45,7 +85,7 @@ __device__ __forceinline__ void up_row(const float2* __restrict__ trow, int rr, 
     }
 }
 
-template <typename T, int FS, int OX1, int OY1>
+template <typename T, int FS, int OX1, int OY1, bool TMA = false>
 __global__ void __launch_bounds__(UP_THREADS, (FS >= 13 ? 4 : 6))
     resample_up2x(const __grid_constant__ UpArgs a, const __grid_constant__ UpWeights<FS> W)
 {
@@ -82,6 +122,31 @@ __global__ void __launch_bounds__(UP_THREADS, (FS >= 13 ? 4 : 6))
     //      memory round trip per tile).  When the plane base and pitch allow it the groups are aligned vector loads
     //      (4 samples per LDG); the tile columns then start d = tsx & 3 samples into the first group.
     const bool vec_ok = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)(sp * (long long)sizeof(T))) & (4 * sizeof(T) - 1)) == 0;
+    if constexpr (TMA) {
+        static_assert(sizeof(T) == 4, "bulk-copy staging lands float rows");
+        // One cp.async.bulk per raw tile row (a contiguous, 16-byte aligned segment of the plane row: vec_ok is required by the
+        // launcher), issued by the lanes of warp 0, all completing on one mbarrier.  The segment is cut at the end of the
+        // plane row; what lies beyond only feeds discarded cells.
+        using TM = UpTma<FS>;
+        const uint32_t bar = smem_addr(smem_raw + G::SMEM + TM::LANDING);
+        const int x_al = tsx & ~3;
+        const int len = min(TM::RAWC, (int)sp - x_al) & ~3; // floats per row copy
+        if (threadIdx.x == 0)
+            mbar_init(bar, 1);
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            if (threadIdx.x == 0)
+                mbar_expect_tx(bar, (uint32_t)(TM::ROWS * len * (int)sizeof(float)));
+            for (int r = threadIdx.x; r < TM::ROWS; r += 32) {
+                const T* row = src + (long long)min(max(tsy + r, 0), a.src_h - 1) * sp + x_al;
+                bulk_g2s(smem_addr(smem_raw + G::SMEM + (size_t)r * TM::RAWC * sizeof(float)), row, (uint32_t)(len * (int)sizeof(float)), bar);
+            }
+        }
+        unsigned spins = 0;
+        while (!mbar_try_wait(bar, 0))
+            if (++spins > (1u << 24))
+                __trap(); // a transfer that never completes must not hang the device
+    }
     if (vec_ok) {
         using V = typename Vec4Of<T>::type;
         constexpr int GRP = G::SUB + 1;                 // groups per row (one more: the row starts inside a group)
@@ -93,10 +158,18 @@ __global__ void __launch_bounds__(UP_THREADS, (FS >= 13 ? 4 : 6))
             const int g = min(max((tsx >> 2) + q, 0), (a.src_w - 1) >> 2); // groups outside the plane only feed discarded cells
             const int r0 = seg * ROWS;
             V raw[ROWS + 1];
+            if constexpr (TMA) {
+                // the rows were landed by the bulk-copy engine (below): group q of landed row r0 + j
+                const V* __restrict__ landed = reinterpret_cast<const V*>(smem_raw + G::SMEM);
 #pragma unroll
-            for (int j = 0; j <= ROWS; ++j) {
-                const T* row = src + (long long)min(max(tsy + r0 + j, 0), a.src_h - 1) * sp;
-                raw[j] = __ldg(reinterpret_cast<const V*>(row) + g);
+                for (int j = 0; j <= ROWS; ++j)
+                    raw[j] = landed[min(r0 + j, UpTma<FS>::ROWS - 1) * (UpTma<FS>::RAWC / 4) + q];
+            } else {
+#pragma unroll
+                for (int j = 0; j <= ROWS; ++j) {
+                    const T* row = src + (long long)min(max(tsy + r0 + j, 0), a.src_h - 1) * sp;
+                    raw[j] = __ldg(reinterpret_cast<const V*>(row) + g);
+                }
             }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -222,13 +295,31 @@ int launch_up2x_fs(const jinc_table* t, UpArgs& a, long long strip_blocks, int n
         }
     auto kern = u.ox1 ? (u.oy1 ? resample_up2x<T, FS, 1, 1> : resample_up2x<T, FS, 1, 0>)
                       : (u.oy1 ? resample_up2x<T, FS, 0, 1> : resample_up2x<T, FS, 0, 0>);
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
+    size_t smem = G::SMEM;
+    if constexpr (sizeof(T) == 4) {
+        static const bool want_tma = [] {
+            const char* e = getenv("JINCRESIZE_B200_TMA");
+            return e && e[0] == '1';
+        }();
+        // bulk-copy staging needs 16-byte aligned plane rows in every frame; batched launches (device-side plane records)
+        // are the caller's promise, single frames are checked here
+        bool aligned = true;
+        if (!a.fr.frames)
+            for (int i = 0; i < a.fr.n_planes; ++i)
+                aligned = aligned && ((reinterpret_cast<uintptr_t>(a.fr.one.src[i]) | (uintptr_t)(a.fr.one.src_pitch[i] * 4)) & 15) == 0;
+        if (want_tma && aligned) {
+            kern = u.ox1 ? (u.oy1 ? resample_up2x<T, FS, 1, 1, true> : resample_up2x<T, FS, 1, 0, true>)
+                         : (u.oy1 ? resample_up2x<T, FS, 0, 1, true> : resample_up2x<T, FS, 0, 0, true>);
+            smem = UpTma<FS>::SMEM;
+        }
+    }
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess)
-        return jinc_fail(JINC_E_CUDA, "cudaFuncSetAttribute(up2x smem %zu): %s", G::SMEM, cudaGetErrorString(e));
+        return jinc_fail(JINC_E_CUDA, "cudaFuncSetAttribute(up2x smem %zu): %s", smem, cudaGetErrorString(e));
     a.strip_blocks = (int)strip_blocks;
     a.strip_shift = strip_role_shift(a.interior_blocks, strip_blocks);
     dim3 grid((unsigned)(a.interior_blocks + strip_blocks), n_frames, 1);
-    kern<<<grid, UP_THREADS, G::SMEM, st>>>(a, w);
+    kern<<<grid, UP_THREADS, smem, st>>>(a, w);
     e = cudaGetLastError();
     if (e != cudaSuccess)
         return jinc_fail(JINC_E_CUDA, "resample_up2x launch failed: %s", cudaGetErrorString(e));
