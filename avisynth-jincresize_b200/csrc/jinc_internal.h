@@ -196,6 +196,8 @@ void jinc_lut_build_host(double radius, double blur, double* lut);
 
 // jinc_table.cu
 int jinc_table_build_device(jinc_table* t, const double* lut);
+cudaError_t jinc_gather_blocks(float* out, const uint32_t* list, unsigned n, const float* phase_blocks, const float* border_blocks,
+                               int block_floats, cudaStream_t st);
 
 // jinc_resize.cu
 int jinc_build_strip_plan(jinc_table* t); // after plan_fast_paths and the weight blocks; no plan is not an error

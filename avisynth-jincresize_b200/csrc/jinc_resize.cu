@@ -5,6 +5,8 @@
 // are described once, in jinc_resample.cuh; the kernel families live in jinc_up2x.cuh (exact 2x), jinc_down.cuh
 // (integer-ratio downscale and the exactly periodic 2:3 path) and jinc_cells.cuh (rational ratios with piecewise-periodic
 // phases), each instantiated once per sample type in its own translation unit so that the build runs in parallel.
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 
 #include "jinc_resample.cuh"
@@ -488,17 +490,6 @@ int launch_typed(const jinc_table* t, const FrameSet& fr, int n_frames, int y_be
     return JINC_OK;
 }
 
-// packs the weight blocks a plan names (sel << 31 | block) next to each other: one thread block per weight block
-__global__ void __launch_bounds__(128) gather_blocks_kernel(float* __restrict__ out, const uint32_t* __restrict__ list, const float* __restrict__ phase_blocks,
-                                                            const float* __restrict__ border_blocks, int block_floats)
-{
-    const uint32_t e = list[blockIdx.x];
-    const float* __restrict__ src = ((e >> 31) ? border_blocks : phase_blocks) + (size_t)(e & 0x7fffffffu) * block_floats;
-    float* __restrict__ dst = out + (size_t)blockIdx.x * block_floats;
-    for (int i = threadIdx.x; i < block_floats; i += blockDim.x)
-        dst[i] = src[i];
-}
-
 int check_and_fill(PlanePtrs& pl, int sample_bytes, int n_planes, const void* const* d_src, const ptrdiff_t* src_pitch,
                    void* const* d_dst, const ptrdiff_t* dst_pitch)
 {
@@ -577,6 +568,7 @@ inline void build_strip_plan_host(const jinc_table* t, const Rect* rects, int n_
     const int phase_stride = t->d_weights_p ? fsp : fs;
     const int n_rank_x = t->ax[0].n_rank;
     out = StripPlanHost{};
+    out.recs.reserve((size_t)SPT * THREADS * 256);
     struct Meta {
         int x, y, sx, sy, wstride;
         uint32_t wkey; // sel << 31 | block; only meaningful when wstride != 0
@@ -706,6 +698,7 @@ inline void build_strip_plan_host(const jinc_table* t, const Rect* rects, int n_
                 out.recs.resize(rec0 + (size_t)SPT * THREADS, make_uint4(0, 0, 0, 0));
                 uint4* prec = out.recs.data() + rec0;
                 keys.clear();
+                size_t last_key = 0;
                 for (size_t tid = 0; tid < items.size(); ++tid) {
                     const Item& it = items[tid];
                     const unsigned live = (1u << it.n) - 1u;
@@ -752,9 +745,10 @@ inline void build_strip_plan_host(const jinc_table* t, const Rect* rects, int n_
                         const Meta& m = meta[k];
                         uint32_t slot = 0;
                         if (kind != JINC_SK_PER_SAMPLE) {
-                            size_t j = 0;
+                            size_t j = last_key < keys.size() && keys[last_key] == m.wkey ? last_key : 0; // neighbours share blocks
                             while (j < keys.size() && keys[j] != m.wkey)
                                 ++j;
+                            last_key = j;
                             if (j == keys.size())
                                 keys.push_back(m.wkey);
                             slot = (uint32_t)j * (uint32_t)wbf;
@@ -857,9 +851,11 @@ int jinc_build_strip_plan(jinc_table* t)
     // the whole-frame strips around the interior, as launch_typed cuts them
     const Rect rects[4] = {Rect{0, 0, W, t->iy0}, Rect{0, t->iy1, W, H}, Rect{0, t->iy0, t->ix0, t->iy1}, Rect{t->ix1, t->iy0, W, t->iy1}};
     StripPlanHost h;
+    const auto t_begin = std::chrono::steady_clock::now();
     build_strip_plan_host(t, rects, 4, pp, h);
     if (!h.ok)
         return JINC_OK;
+    const auto t_host = std::chrono::steady_clock::now();
     cudaStream_t st = t->ctx->stream;
     JINC_CUDA(cudaSetDevice(t->ctx->device));
     JINC_CUDA(cudaMalloc(reinterpret_cast<void**>(&sp.d_patches), h.patches.size() * sizeof(StripPlanPatch)));
@@ -872,9 +868,8 @@ int jinc_build_strip_plan(jinc_table* t)
         JINC_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_list), h.wlist.size() * sizeof(uint32_t)));
         cudaError_t e = cudaMemcpyAsync(d_list, h.wlist.data(), h.wlist.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st);
         if (e == cudaSuccess) {
-            gather_blocks_kernel<<<(unsigned)h.wlist.size(), 128, 0, st>>>(sp.d_wdata, d_list, t->d_weights_p ? t->d_weights_p : t->d_weights,
-                                                                           t->d_border_wb, wbf);
-            e = cudaGetLastError();
+            e = jinc_gather_blocks(sp.d_wdata, d_list, (unsigned)h.wlist.size(), t->d_weights_p ? t->d_weights_p : t->d_weights, t->d_border_wb,
+                                   wbf, st);
         }
         if (e == cudaSuccess)
             e = cudaStreamSynchronize(st); // the host vectors and the list are temporaries
@@ -883,6 +878,12 @@ int jinc_build_strip_plan(jinc_table* t)
             return jinc_fail(JINC_E_CUDA, "strip plan: %s", cudaGetErrorString(e));
     } else {
         JINC_CUDA(cudaStreamSynchronize(st));
+    }
+    if (const char* e = getenv("JINCRESIZE_B200_PLAN_TIMING"); e && e[0] == '1') {
+        const auto t_end = std::chrono::steady_clock::now();
+        fprintf(stderr, "strip plan %dx%d: %zu patches (%u staged), %zu packed blocks; host %.2f ms, upload %.2f ms\n", W, H, h.patches.size(),
+                h.n_staged, h.wlist.size(), std::chrono::duration<double, std::milli>(t_host - t_begin).count(),
+                std::chrono::duration<double, std::milli>(t_end - t_host).count());
     }
     sp.threads = pp.threads;
     sp.spt = pp.spt;
@@ -978,6 +979,13 @@ extern "C" int jinc_resize_plane_device(jinc_ctx* ctx, const jinc_table* t, int 
     JINC_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
     return jinc_launch_resize(ctx, t, sample_bytes, peak, d_src, src_pitch, d_dst, dst_pitch, 0, t->sc.dst_h, st, nullptr);
+}
+
+extern "C" int jinc_table_strip_plan(const jinc_table* t, int* staged)
+{
+    if (staged)
+        *staged = t && t->strip_plan.ok ? (int)t->strip_plan.n_staged : 0;
+    return t && t->strip_plan.ok ? (int)t->strip_plan.n_patches : 0;
 }
 
 extern "C" int jinc_table_launches_per_plane(const jinc_table* t)

@@ -250,6 +250,19 @@ __global__ void __launch_bounds__(128) border_class_kernel(BorderSumArgs a, cons
     }
 }
 
+// packs the weight blocks a strip plan names (sel << 31 | block) next to each other: one thread block per weight block.
+// Lives here, not next to the planner in jinc_resize.cu: that module (the general kernels) is large and would be loaded
+// just for this launch, 20 ms on the first table of a process.
+__global__ void __launch_bounds__(128) gather_blocks_kernel(float* __restrict__ out, const uint32_t* __restrict__ list, const float* __restrict__ phase_blocks,
+                                                            const float* __restrict__ border_blocks, int block_floats)
+{
+    const uint32_t e = list[blockIdx.x];
+    const float* __restrict__ src = ((e >> 31) ? border_blocks : phase_blocks) + (size_t)(e & 0x7fffffffu) * block_floats;
+    float* __restrict__ dst = out + (size_t)blockIdx.x * block_floats;
+    for (int i = threadIdx.x; i < block_floats; i += blockDim.x)
+        dst[i] = src[i];
+}
+
 template <typename T>
 int dev_alloc(T** p, size_t count)
 {
@@ -771,6 +784,13 @@ int jinc_table_build_device(jinc_table* t, const double* lut)
     if (t->bgeom.total >= (1ll << 31))
         return jinc_fail(JINC_E_UNSUPPORTED, "jinc_table: %lld border pixels exceed the 32-bit slot index", t->bgeom.total);
     return jinc_build_strip_plan(t);
+}
+
+cudaError_t jinc_gather_blocks(float* out, const uint32_t* list, unsigned n, const float* phase_blocks, const float* border_blocks,
+                               int block_floats, cudaStream_t st)
+{
+    gather_blocks_kernel<<<n, 128, 0, st>>>(out, list, phase_blocks, border_blocks, block_floats);
+    return cudaGetLastError();
 }
 
 // ================================================================ C ABI: tables

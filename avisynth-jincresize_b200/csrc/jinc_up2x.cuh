@@ -279,7 +279,10 @@ __global__ void __launch_bounds__(UP_THREADS, (FS >= 13 ? 4 : 6))
     }
 }
 
-template <typename T, int FS>
+// float planes staged by the bulk-copy engine: instantiated in its own translation unit (jinc_up2x_f32_bulk.cu)
+int launch_up2x_bulkcopy(const jinc_table* t, UpArgs& a, long long strip_blocks, int n_frames, cudaStream_t st);
+
+template <typename T, int FS, bool TMA>
 int launch_up2x_fs(const jinc_table* t, UpArgs& a, long long strip_blocks, int n_frames, cudaStream_t st)
 {
     using G = UpGeom<FS>;
@@ -293,26 +296,11 @@ int launch_up2x_fs(const jinc_table* t, UpArgs& a, long long strip_blocks, int n
                 for (int lx = 0; lx < FS; ++lx)
                     w.w[py][px][ly][lx] = blk[ly * FS + lx];
         }
-    auto kern = u.ox1 ? (u.oy1 ? resample_up2x<T, FS, 1, 1> : resample_up2x<T, FS, 1, 0>)
-                      : (u.oy1 ? resample_up2x<T, FS, 0, 1> : resample_up2x<T, FS, 0, 0>);
+    auto kern = u.ox1 ? (u.oy1 ? resample_up2x<T, FS, 1, 1, TMA> : resample_up2x<T, FS, 1, 0, TMA>)
+                      : (u.oy1 ? resample_up2x<T, FS, 0, 1, TMA> : resample_up2x<T, FS, 0, 0, TMA>);
     size_t smem = G::SMEM;
-    if constexpr (sizeof(T) == 4) {
-        static const bool want_tma = [] {
-            const char* e = getenv("JINCRESIZE_B200_TMA");
-            return e && e[0] == '1';
-        }();
-        // bulk-copy staging needs 16-byte aligned plane rows in every frame; batched launches (device-side plane records)
-        // are the caller's promise, single frames are checked here
-        bool aligned = true;
-        if (!a.fr.frames)
-            for (int i = 0; i < a.fr.n_planes; ++i)
-                aligned = aligned && ((reinterpret_cast<uintptr_t>(a.fr.one.src[i]) | (uintptr_t)(a.fr.one.src_pitch[i] * 4)) & 15) == 0;
-        if (want_tma && aligned) {
-            kern = u.ox1 ? (u.oy1 ? resample_up2x<T, FS, 1, 1, true> : resample_up2x<T, FS, 1, 0, true>)
-                         : (u.oy1 ? resample_up2x<T, FS, 0, 1, true> : resample_up2x<T, FS, 0, 0, true>);
-            smem = UpTma<FS>::SMEM;
-        }
-    }
+    if constexpr (TMA)
+        smem = UpTma<FS>::SMEM;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess)
         return jinc_fail(JINC_E_CUDA, "cudaFuncSetAttribute(up2x smem %zu): %s", smem, cudaGetErrorString(e));
@@ -326,18 +314,37 @@ int launch_up2x_fs(const jinc_table* t, UpArgs& a, long long strip_blocks, int n
     return JINC_OK;
 }
 
+template <typename T, bool TMA>
+int launch_up2x_any(const jinc_table* t, UpArgs& a, long long strip_blocks, int n_frames, cudaStream_t st)
+{
+    switch (t->sc.fs) {
+    case 7: return launch_up2x_fs<T, 7, TMA>(t, a, strip_blocks, n_frames, st);   // tap 3  (Jinc36Resize)
+    case 9: return launch_up2x_fs<T, 9, TMA>(t, a, strip_blocks, n_frames, st);   // tap 4  (Jinc64Resize)
+    case 11: return launch_up2x_fs<T, 11, TMA>(t, a, strip_blocks, n_frames, st); // tap 5
+    case 13: return launch_up2x_fs<T, 13, TMA>(t, a, strip_blocks, n_frames, st); // tap 6  (Jinc144Resize)
+    case 15: return launch_up2x_fs<T, 15, TMA>(t, a, strip_blocks, n_frames, st); // tap 7
+    case 17: return launch_up2x_fs<T, 17, TMA>(t, a, strip_blocks, n_frames, st); // tap 8  (Jinc256Resize)
+    default: return 1;
+    }
+}
+
 template <typename T>
 int launch_up2x(const jinc_table* t, UpArgs& a, long long strip_blocks, int n_frames, cudaStream_t st)
 {
-    switch (t->sc.fs) {
-    case 7: return launch_up2x_fs<T, 7>(t, a, strip_blocks, n_frames, st);   // tap 3  (Jinc36Resize)
-    case 9: return launch_up2x_fs<T, 9>(t, a, strip_blocks, n_frames, st);   // tap 4  (Jinc64Resize)
-    case 11: return launch_up2x_fs<T, 11>(t, a, strip_blocks, n_frames, st); // tap 5
-    case 13: return launch_up2x_fs<T, 13>(t, a, strip_blocks, n_frames, st); // tap 6  (Jinc144Resize)
-    case 15: return launch_up2x_fs<T, 15>(t, a, strip_blocks, n_frames, st); // tap 7
-    case 17: return launch_up2x_fs<T, 17>(t, a, strip_blocks, n_frames, st); // tap 8  (Jinc256Resize)
-    default: return 1;
+    if constexpr (sizeof(T) == 4) {
+        const char* tma_env = getenv("JINCRESIZE_B200_TMA");
+        if (tma_env && tma_env[0] == '1' && up2x_supported(t->sc.fs)) {
+            // bulk-copy staging needs 16-byte aligned plane rows in every frame; batched launches (device-side plane
+            // records) are the caller's promise, single frames are checked here
+            bool aligned = true;
+            if (!a.fr.frames)
+                for (int i = 0; i < a.fr.n_planes; ++i)
+                    aligned = aligned && ((reinterpret_cast<uintptr_t>(a.fr.one.src[i]) | (uintptr_t)(a.fr.one.src_pitch[i] * 4)) & 15) == 0;
+            if (aligned)
+                return launch_up2x_bulkcopy(t, a, strip_blocks, n_frames, st);
+        }
     }
+    return launch_up2x_any<T, false>(t, a, strip_blocks, n_frames, st);
 }
 
 } // namespace jinc_rs

@@ -58,7 +58,8 @@ EXPORTS = [
     "jinc_abi_version", "jinc_last_error", "jinc_device_count", "jinc_radius_for_tap", "jinc_eval_sqr",
     "jinc_lut_build", "jinc_ctx_create", "jinc_ctx_destroy", "jinc_ctx_device", "jinc_table_create",
     "jinc_table_destroy", "jinc_table_get_info", "jinc_table_axis", "jinc_table_pixel_weights",
-    "jinc_table_pixel_block", "jinc_resize_plane_device", "jinc_table_launches_per_plane", "jinc_filter_create",
+    "jinc_table_pixel_block", "jinc_resize_plane_device", "jinc_table_launches_per_plane", "jinc_table_strip_plan",
+    "jinc_filter_create",
     "jinc_filter_destroy", "jinc_filter_table", "jinc_filter_num_tables", "jinc_filter_num_devices",
     "jinc_filter_process", "jinc_filter_submit", "jinc_filter_wait", "jinc_filter_process_split",
     "jinc_filter_kernel_launches", "jinc_filter_process_device", "jinc_filter_process_device_batch",
@@ -96,6 +97,7 @@ def lib():
         L.jinc_resize_plane_device.restype = ci
         L.jinc_resize_plane_device.argtypes = [vp, vp, ci, C.c_float, vp, C.c_ssize_t, vp, C.c_ssize_t, vp]
         L.jinc_table_launches_per_plane.restype, L.jinc_table_launches_per_plane.argtypes = ci, [vp]
+        L.jinc_table_strip_plan.restype, L.jinc_table_strip_plan.argtypes = ci, [vp, C.POINTER(ci)]
         L.jinc_filter_create.restype, L.jinc_filter_create.argtypes = ci, [C.POINTER(FilterParams), C.POINTER(vp)]
         L.jinc_filter_destroy.restype, L.jinc_filter_destroy.argtypes = None, [vp]
         L.jinc_filter_table.restype, L.jinc_filter_table.argtypes = vp, [vp, ci]
@@ -230,6 +232,13 @@ class TableView:
     @property
     def launches_per_plane(self) -> int:
         return lib().jinc_table_launches_per_plane(self.handle)
+
+    @property
+    def strip_plan(self) -> tuple:
+        """(strip patches per plane, patches with their weight blocks in shared memory); (0, 0) without a plan"""
+        staged = C.c_int(0)
+        n = lib().jinc_table_strip_plan(self.handle, C.byref(staged))
+        return n, staged.value
 
 
 class Table(TableView):

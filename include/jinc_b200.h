@@ -130,6 +130,12 @@ JINC_API int jinc_resize_plane_device(jinc_ctx* ctx, const jinc_table* t, int sa
                                       void* stream);
 /* number of kernel launches the call above issues for this table (fast-path interior + border strips) */
 JINC_API int jinc_table_launches_per_plane(const jinc_table* t);
+/* Introspection of the table's strip plan (no reference counterpart: the reference keeps one weight block per border
+ * pixel, src/JincResize.cpp:443-518, and has no notion of patches).  Whole-frame launches of the exact-2x, chunked-cells
+ * and integer-ratio kernels run their border strips from descriptors worked out once per table; returns the number of
+ * strip patches per plane (0: no plan, the strips derive everything per block) and, through `staged` when it is not
+ * NULL, how many of them keep their weight blocks in shared memory.                                  */
+JINC_API int jinc_table_strip_plan(const jinc_table* t, int* staged);
 
 /* ---------------------------------------------------------------- filter instance + frame pipeline
  * Replaces: the geometry part of Create_JincResize (src/JincResize.cpp:762-866), JincResize_GetFrame's

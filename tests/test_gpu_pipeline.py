@@ -441,3 +441,60 @@ def test_two_gpu_frame_round_robin(capi):
         for g, r in zip(o, ref):
             assert_plane_close(g, r, False, "round robin")
     flt.close()
+
+
+PLAN_CASES = ["c1_yv12_2x_tap3", "c2_420p8_2x_tap3_mpeg2", "c3_444p16_2x_tap4_crop", "c4_rgbps_2x_tap8", "up2x_tap6_420p8",
+              "yuva420_14bit_2x", "up4to3_tap3_420p8", "up4x_tap3_420p8", "c5_420p10_quarter_tap6_blur", "half_tap3_yv12",
+              "quarter_tap4_422p12", "third_tap3_y8"]
+
+
+@pytest.mark.parametrize("name", PLAN_CASES)
+def test_strip_plan_equals_prologue_path(capi, name, monkeypatch):
+    """Whole-frame launches run their border strips from the table's strip plan (jinc_table_strip_plan: patches, thread
+    records and packed weight blocks worked out once per table); with JINCRESIZE_B200_STRIP_PLAN=0 a table has no plan and
+    every strip block derives its work in its prologue.  Both accumulate every sample in the same tap order: the frames
+    must be BYTE-identical (and both within the bar of the oracle, checked by the other tests)."""
+    _, fmt, w, h, tw, th, kw = CASES[name]
+    planes = make_planes(fmt, w, h, "noise", seed=11)
+    monkeypatch.setenv("JINCRESIZE_B200_STRIP_PLAN", "0")
+    plain = make_filter(fmt, w, h, tw, th, **kw)
+    assert all(plain.table(i).strip_plan == (0, 0) for i in range(plain.num_tables))
+    want = plain.process(planes)
+    plain.close()
+    monkeypatch.delenv("JINCRESIZE_B200_STRIP_PLAN")
+    flt = make_filter(fmt, w, h, tw, th, **kw)
+    n, staged = flt.table(0).strip_plan
+    assert n > 0 and 0 <= staged <= n, f"{name}: no strip plan was built ({n}, {staged})"
+    got = flt.process(planes)
+    for i, (a, b) in enumerate(zip(want, got)):
+        assert np.array_equal(a, b), f"{name}: plane {i} differs between the planned and the prologue strips"
+    ref, _ = oracle_frame(fmt, w, h, tw, th, planes, **kw)
+    for i, (g, r) in enumerate(zip(got, ref)):
+        assert_plane_close(g, r, fmt.bits == 32, f"{name}/plan/plane{i}")
+    flt.close()
+
+
+def test_non_periodic_ratio_keeps_the_prologue_strips(capi):
+    """3:2 positions are accumulated in float and never repeat exactly: every border pixel keeps its own weights
+    (src/JincResize.cpp:443-518), which the prologue path reads coalesced -- such a table builds no plan."""
+    _, fmt, w, h, tw, th, kw = CASES["up1p5_tap3_420p8"]
+    flt = make_filter(fmt, w, h, tw, th, **kw)
+    assert flt.table(0).strip_plan == (0, 0)
+    flt.close()
+
+
+@pytest.mark.parametrize("name", ["c4_rgbps_2x_tap8", "up2x_tap7_f32_y"])
+def test_bulk_copy_staging_equals_register_staging(capi, name, monkeypatch):
+    """JINCRESIZE_B200_TMA=1: float tiles of the exact-2x kernel are landed in shared memory by the bulk-copy engine
+    (cp.async.bulk + mbarrier, one copy per tile row) instead of through registers; the arithmetic is untouched, so the
+    frames are byte-identical.  Pinned device planes (16-byte aligned rows) are what the frame pipeline provides."""
+    _, fmt, w, h, tw, th, kw = CASES[name]
+    planes = make_planes(fmt, w, h, "noise", seed=5)
+    flt = make_filter(fmt, w, h, tw, th, **kw)
+    want = flt.process(planes)
+    monkeypatch.setenv("JINCRESIZE_B200_TMA", "1")
+    got = flt.process(planes)
+    monkeypatch.delenv("JINCRESIZE_B200_TMA")
+    for i, (a, b) in enumerate(zip(want, got)):
+        assert np.array_equal(a, b), f"{name}: plane {i} differs between bulk-copy and register staging"
+    flt.close()
