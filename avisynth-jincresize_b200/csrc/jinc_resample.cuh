@@ -1261,8 +1261,10 @@ constexpr int UP_TX = 4;                     // cells per thread along x
 constexpr int UP_WARPS = 4;
 constexpr int UP_THREADS = UP_WARPS * 32;
 constexpr int UP_CW = 32 * UP_TX;            // cells per tile row (128 -> 256 output samples)
-constexpr int UP_RPW = 2;                    // cell-row pairs per warp
-constexpr int UP_CH = 2 * UP_WARPS * UP_RPW; // cell rows per tile (32 -> 64 output rows)
+// cell-row pairs per warp: the smallest window (tap 3) takes twice as tall a tile -- its tiles are short-lived, and the halo
+// rows, the staging round trip and the block start-up weigh most there -- at five instead of six blocks per SM
+constexpr int up_rpw(int fs) { return fs <= 7 ? 4 : 2; }
+constexpr int up_ch(int fs) { return 2 * UP_WARPS * up_rpw(fs); } // cell rows per tile (16 -> 32 output rows, or 32 -> 64)
 constexpr int UP_STRIP_SPT = 4;              // strip role: outputs per thread (patches of 1024 outputs, up to 256 wide)
 constexpr int UP_STRIP_MAX_PW = 64;   // wide strips are cut into 64 x 8 patches: the rows of a strip share most of their source rows
 
@@ -1273,7 +1275,8 @@ struct UpGeom {
     static constexpr int NC = UP_CW + FS;           // pair columns per tile row (CW + ox1 + FS - 1)
     static constexpr int NCP = (NC + 3) & ~3;
     static constexpr int SUB = NCP / 4;             // columns are de-interleaved by (c & 3): 4 sub-rows of SUB
-    static constexpr int NR = UP_CH + 1 + FS - 1;   // pair rows per tile (CH + oy1 + FS - 1)
+    static constexpr int RPW = up_rpw(FS), CH = up_ch(FS);
+    static constexpr int NR = CH + 1 + FS - 1;      // pair rows per tile (CH + oy1 + FS - 1)
     static constexpr size_t SMEM = (size_t)NR * NCP * sizeof(float2);
 };
 

@@ -312,7 +312,7 @@ int launch_typed(const jinc_table* t, const FrameSet& fr, int n_frames, int y_be
             a.cy_begin = cb;
             a.cy_end = ce;
             a.tiles_x = (u.ncx + UP_CW - 1) / UP_CW;
-            a.tiles_per_plane = a.tiles_x * ((ce - cb + UP_CH - 1) / UP_CH);
+            a.tiles_per_plane = a.tiles_x * ((ce - cb + up_ch(t->sc.fs) - 1) / up_ch(t->sc.fs));
             a.tiles_x_magic = div_magic((unsigned)a.tiles_x);
             a.tiles_per_plane_magic = div_magic((unsigned)a.tiles_per_plane);
             a.interior_blocks = (parts & JINC_PART_INTERIOR) ? a.tiles_per_plane * fr.n_planes : 0;

@@ -86,7 +86,7 @@ __device__ __forceinline__ void up_row(const float2* __restrict__ trow, int rr, 
 }
 
 template <typename T, int FS, int OX1, int OY1, bool TMA = false>
-__global__ void __launch_bounds__(UP_THREADS, (FS >= 13 ? 4 : 6))
+__global__ void __launch_bounds__(UP_THREADS, (FS >= 13 ? 4 : FS <= 7 ? 5 : 6))
     resample_up2x(const __grid_constant__ UpArgs a, const __grid_constant__ UpWeights<FS> W)
 {
     using G = UpGeom<FS>;
@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(UP_THREADS, (FS >= 13 ? 4 : 6))
     const long long sp = pp.src_pitch[plane], dp = pp.dst_pitch[plane];
 
     const int cell_x0 = tile_x * UP_CW; // first cell of this tile
-    const int cell_y0 = a.cy_begin + tile_y * UP_CH;
+    const int cell_y0 = a.cy_begin + tile_y * G::CH;
     const int tsx = a.sx0 + cell_x0, tsy = a.sy0 + cell_y0; // source coordinates of tile(0,0)
 
     // ---- stage the source tile: every row is paired with the one below it and converted to float once.  A thread owns
@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(UP_THREADS, (FS >= 13 ? 4 : 6))
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
 #pragma unroll 1
-    for (int rp = warp; rp < UP_WARPS * UP_RPW; rp += UP_WARPS) {
+    for (int rp = warp; rp < UP_WARPS * G::RPW; rp += UP_WARPS) {
         const int cy = cell_y0 + 2 * rp; // first cell row of the pair
         if (cy >= a.cy_end)
             break;
