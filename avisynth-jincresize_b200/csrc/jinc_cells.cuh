@@ -59,7 +59,7 @@ __device__ __forceinline__ void store_cells(T* __restrict__ o, long long rstep, 
 }
 
 template <typename T, int FS, int Q>
-__global__ void __launch_bounds__((CellsGeom<FS, Q>::THREADS), (CellsGeom<FS, Q>::THREADS == 128 && FS <= 9 ? 3 : 2)) resample_cells(const __grid_constant__ CellsArgs a)
+__global__ void __launch_bounds__((CellsGeom<FS, Q>::THREADS), (CellsGeom<FS, Q>::THREADS == 128 ? (FS <= 7 && Q <= 2 ? 4 : FS <= 9 ? 3 : 2) : 2)) resample_cells(const __grid_constant__ CellsArgs a)
 {
     using G = CellsGeom<FS, Q>;
     extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -99,9 +99,9 @@ struct PeriodicPlan {
 // of JINC_CELLS_N* cells (a cell = P consecutive outputs), cut into CHUNKS inside which every residue p keeps its phase
 // rank and its window origins advance by exactly Q per cell: one chunk per group, more where a residue changes rank.
 constexpr int JINC_CELLS_NX = 4, JINC_CELLS_NY = 4;
-// y-chunks per tile (one per warp): four where the footprint is tall (Q >= 3) or the weight block needs the registers of a
-// 128-thread block (windows of 9 and more)
-constexpr int jinc_cells_warps(int q, int fs) { return (q >= 3 || fs >= 9) ? 4 : 8; }
+// y-chunks per tile (one per warp): four.  128-thread blocks, four of them per SM for the small windows and steps, overlap
+// their staging and store phases better than two 256-thread blocks did (config 6: 21.1 -> 23.3 % of the FMA peak)
+constexpr int jinc_cells_warps(int, int) { return 4; }
 // samples staged along one axis for a tile of `chunks` chunks of n cells: the chunks' cells, the window, and slack for the
 // residues' origin offsets and one irregular origin step
 constexpr int jinc_cells_footprint(int q, int fs, int n, int chunks) { return q * n * chunks + fs + q + 2; }
