@@ -146,7 +146,7 @@ struct StripPlanPatch {
     int32_t deint;                // 1: the footprint is staged de-interleaved by the window step (patches of row runs only)
     int32_t pad_;
 };
-enum { JINC_SK_NONE = 0, JINC_SK_RUN_ROWS, JINC_SK_RUN_COLS, JINC_SK_FUSED_SHARED, JINC_SK_FUSED_SEP, JINC_SK_PER_SAMPLE };
+enum { JINC_SK_NONE = 0, JINC_SK_RUN_ROWS, JINC_SK_RUN_COLS, JINC_SK_FUSED_SHARED, JINC_SK_FUSED_SEP, JINC_SK_PER_SAMPLE, JINC_SK_PER_PIXEL };
 struct StripPlan {
     bool ok = false;
     int threads = 0, spt = 0, px = 0, py = 0;
@@ -154,7 +154,8 @@ struct StripPlan {
     unsigned n_staged = 0;   // patches whose weight blocks are staged in shared memory
     StripPlanPatch* d_patches = nullptr;
     // [patch][sample k][thread]: .x = x | y << 16, .y = offset of the window origin in the staged footprint,
-    // .z = float offset of the weight block among the staged ones, .w (sample 0) = kind | live mask << 8
+    // .z = float offset of the weight block among the staged ones (JINC_SK_PER_PIXEL: the pixel's border slot),
+    // .w (sample 0) = kind | live mask << 8
     uint4* d_threads = nullptr;
     float* d_wdata = nullptr;
 };

@@ -1080,6 +1080,41 @@ __device__ __forceinline__ void plan_fused(const StripArgs& a, const uint4 (&r)[
             dst[(long long)(r[k].x >> 16) * dp + (r[k].x & 0xffffu)] = finish<T>(acc[k], peak);
 }
 
+// SPT border pixels that each keep their own weights (ratios whose positions never repeat exactly: no class blocks), stored
+// [slot / 32][tap][slot % 32]: the lanes of a warp are neighbouring pixels, so a tap's weights are one contiguous line; the
+// windows come from the staged footprint.  Same tap order as strip_sample.
+template <typename T, int FSC, int SPT>
+__device__ __forceinline__ void plan_per_pixel(const StripArgs& a, const uint4 (&r)[SPT], unsigned live, const float* __restrict__ tile, int fw,
+                                               T* __restrict__ dst, long long dp, float peak)
+{
+    const float* __restrict__ s[SPT];
+    const float* __restrict__ w[SPT];
+    float acc[SPT];
+#pragma unroll
+    for (int k = 0; k < SPT; ++k) {
+        s[k] = tile + (int)r[k].y;
+        w[k] = a.border_w + (size_t)(r[k].z >> 5) * (size_t)(FSC * FSC * 32) + (r[k].z & 31u);
+        acc[k] = 0.f;
+    }
+#pragma unroll 1
+    for (int ly = 0; ly < FSC; ++ly) {
+#pragma unroll
+        for (int lx = 0; lx < FSC; ++lx)
+#pragma unroll
+            for (int k = 0; k < SPT; ++k)
+                acc[k] = fmaf(s[k][lx], __ldg(w[k] + lx * 32), acc[k]);
+#pragma unroll
+        for (int k = 0; k < SPT; ++k) {
+            s[k] += fw;
+            w[k] += FSC * 32;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < SPT; ++k)
+        if (live & (1u << k))
+            dst[(long long)(r[k].x >> 16) * dp + (r[k].x & 0xffffu)] = finish<T>(acc[k], peak);
+}
+
 // the prologue path as a real function (row-band launches and tables without a plan)
 template <typename T, int FSC, int THREADS, int SPT, int PERIOD, int STEP>
 __device__ __noinline__ void strip_block_unplanned(const StripArgs& a, const FrameSet& fsx, unsigned sb, float* __restrict__ tile)
@@ -1118,6 +1153,8 @@ __device__ __forceinline__ void plan_accumulate(const StripArgs& a, const FrameS
         plan_fused<T, FSC, SPT, true, WS>(a, r, live, tile, rs, wbase, dst, dp, fsx.peak);
     } else if (kind == JINC_SK_FUSED_SEP) {
         plan_fused<T, FSC, SPT, false, WS>(a, r, live, tile, rs, wbase, dst, dp, fsx.peak);
+    } else if (kind == JINC_SK_PER_PIXEL) {
+        plan_per_pixel<T, FSC, SPT>(a, r, live, tile, rs, dst, dp, fsx.peak);
     } else { // JINC_SK_PER_SAMPLE: no vector-readable block (per-pixel border weights): straight from global memory
 #pragma unroll 1
         for (int k = 0; k < SPT; ++k)

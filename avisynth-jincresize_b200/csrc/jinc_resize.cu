@@ -571,7 +571,8 @@ inline void build_strip_plan_host(const jinc_table* t, const Rect* rects, int n_
     out.recs.reserve((size_t)SPT * THREADS * 256);
     struct Meta {
         int x, y, sx, sy, wstride;
-        uint32_t wkey; // sel << 31 | block; only meaningful when wstride != 0
+        uint32_t wkey; // sel << 31 | block; only meaningful when wstride != 0 (per-pixel weights: the border slot)
+        bool perpix;   // a border pixel with its own resident weights
     };
     struct Item {
         int x[8], y[8], n;
@@ -581,8 +582,12 @@ inline void build_strip_plan_host(const jinc_table* t, const Rect* rects, int n_
     std::vector<uint32_t> keys; // distinct weight blocks of the patch, in first-use order
     if (SPT > 8)
         return;
-    if (!have_classes && t->bgeom.total > 0)
-        return; // per-pixel border weights (ratios whose positions are not exactly periodic): the prologue path reads them coalesced
+    // Ratios whose positions never repeat exactly have no class blocks: every border pixel keeps its own weights, stored so
+    // that neighbouring pixels lie next to each other.  Their threads take pixels a quarter of a patch row apart (the
+    // prologue path's mapping: the lanes of a warp are neighbouring pixels), not same-phase neighbours.
+    const bool scatter = !have_classes && t->bgeom.total > 0;
+    if (scatter && !t->d_border_w)
+        return; // border weights over the residency budget are rebuilt per tap from the LUT: the prologue path
     for (int ri = 0; ri < n_rects; ++ri) {
         const Rect rc = rects[ri];
         const int w = rc.x1 - rc.x0, h = rc.y1 - rc.y0;
@@ -594,7 +599,11 @@ inline void build_strip_plan_host(const jinc_table* t, const Rect* rects, int n_
             const int nx = std::min(pw, rc.x1 - ox0);
             // patch height: as many rows as the block has threads for
             int ph;
-            if (rows) {
+            if (rows && scatter) {
+                ph = std::max(1, THREADS / ((nx + SPT - 1) / SPT));
+            } else if (!rows && scatter) {
+                ph = std::max(1, THREADS / nx) * SPT;
+            } else if (rows) {
                 int per_row = 0;
                 for (int p = 0; p < pp.px; ++p) {
                     int cnt = 0;
@@ -619,7 +628,19 @@ inline void build_strip_plan_host(const jinc_table* t, const Rect* rects, int n_
                     return; // footprints of the planned kernel families always fit; otherwise no plan at all
                 // the work items of the patch
                 items.clear();
-                if (rows) {
+                if (rows && scatter) {
+                    const int dx = (nx + SPT - 1) / SPT;
+                    for (int y = oy0; y < oy0 + ny; ++y)
+                        for (int tx = 0; tx < dx; ++tx) {
+                            Item it{};
+                            for (int k = 0; k < SPT && tx + k * dx < nx; ++k) {
+                                it.x[it.n] = ox0 + tx + k * dx;
+                                it.y[it.n] = y;
+                                ++it.n;
+                            }
+                            items.push_back(it);
+                        }
+                } else if (rows) {
                     for (int y = oy0; y < oy0 + ny; ++y)
                         for (int p = 0; p < pp.px; ++p) {
                             Item it{};
@@ -636,7 +657,7 @@ inline void build_strip_plan_host(const jinc_table* t, const Rect* rects, int n_
                             if (it.n)
                                 items.push_back(it);
                         }
-                } else if (fs > 9) {
+                } else if (fs > 9 || scatter) {
                     // wide windows never run down a column (see below): a thread's samples need not be neighbours, so
                     // neighbouring lanes take neighbouring rows (window rows `step` apart: different banks) and a thread's
                     // samples lie a quarter of the patch apart -- the prologue path's mapping
@@ -716,18 +737,20 @@ inline void build_strip_plan_host(const jinc_table* t, const Rect* rects, int n_
                             m.wkey = 0x80000000u | (uint32_t)t->h_border_block[(size_t)jinc_border_slot(t->bgeom, m.x, m.y)];
                             m.wstride = fsp;
                         } else {
-                            m.wkey = 0;
+                            m.wkey = scatter ? (uint32_t)jinc_border_slot(t->bgeom, m.x, m.y) : 0u;
                             m.wstride = 0;
                         }
+                        m.perpix = scatter && !(rx >= 0 && ry >= 0);
                     }
-                    bool same = true, vec = true;
+                    bool same = true, vec = true, perpix = true;
                     for (int k = 0; k < SPT; ++k) {
                         if (k >= it.n)
                             meta[k] = meta[0]; // computed, not stored
                         same = same && meta[k].wstride == meta[0].wstride && (meta[k].wstride == 0 || meta[k].wkey == meta[0].wkey);
                         vec = vec && meta[k].wstride != 0 && (meta[k].wstride & 3) == 0 && meta[k].wstride == meta[0].wstride;
+                        perpix = perpix && meta[k].perpix;
                     }
-                    unsigned kind = JINC_SK_PER_SAMPLE;
+                    unsigned kind = perpix ? JINC_SK_PER_PIXEL : JINC_SK_PER_SAMPLE;
                     if (vec) {
                         kind = same ? JINC_SK_FUSED_SHARED : JINC_SK_FUSED_SEP;
                         if (same && it.n == SPT) {
@@ -743,8 +766,8 @@ inline void build_strip_plan_host(const jinc_table* t, const Rect* rects, int n_
                     }
                     for (int k = 0; k < SPT; ++k) {
                         const Meta& m = meta[k];
-                        uint32_t slot = 0;
-                        if (kind != JINC_SK_PER_SAMPLE) {
+                        uint32_t slot = kind == JINC_SK_PER_PIXEL ? m.wkey : 0u;
+                        if (kind != JINC_SK_PER_SAMPLE && kind != JINC_SK_PER_PIXEL) {
                             size_t j = last_key < keys.size() && keys[last_key] == m.wkey ? last_key : 0; // neighbours share blocks
                             while (j < keys.size() && keys[j] != m.wkey)
                                 ++j;
@@ -788,7 +811,7 @@ inline void build_strip_plan_host(const jinc_table* t, const Rect* rects, int n_
                     for (int k = 0; k < SPT; ++k)
                         for (size_t tid = 0; tid < items.size(); ++tid) {
                             uint4& rk = prec[(size_t)k * THREADS + tid];
-                            if ((prec[tid].w & 0xffu) != JINC_SK_PER_SAMPLE)
+                            if ((prec[tid].w & 0xffu) != JINC_SK_PER_SAMPLE && (prec[tid].w & 0xffu) != JINC_SK_PER_PIXEL)
                                 rk.z = keys[rk.z / (uint32_t)wbf];
                         }
                 }
