@@ -277,6 +277,10 @@ int launch_cells_q(const jinc_table* t, CellsArgs& a, int n_frames, cudaStream_t
         if constexpr (jinc_cells_instantiated(Q, 9))
             return launch_cells_cfg<T, 9, Q>(t, a, n_frames, st, rects, n_rects);
         break;
+    case 10: // tap 3 at 2:3
+        if constexpr (jinc_cells_instantiated(Q, 10))
+            return launch_cells_cfg<T, 10, Q>(t, a, n_frames, st, rects, n_rects);
+        break;
     case 11: // tap 5
         if constexpr (jinc_cells_instantiated(Q, 11))
             return launch_cells_cfg<T, 11, Q>(t, a, n_frames, st, rects, n_rects);

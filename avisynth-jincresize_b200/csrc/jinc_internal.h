@@ -107,7 +107,8 @@ constexpr int jinc_cells_warps(int, int) { return 4; }
 constexpr int jinc_cells_footprint(int q, int fs, int n, int chunks) { return q * n * chunks + fs + q + 2; }
 constexpr bool jinc_cells_instantiated(int q, int fs)
 {
-    return (q >= 1 && q <= 4 && (fs == 7 || fs == 9)) || ((q == 1 || q == 2) && (fs == 5 || fs == 11));
+    return (q >= 1 && q <= 4 && (fs == 7 || fs == 9)) || ((q == 1 || q == 2) && (fs == 5 || fs == 11)) ||
+           (q == 3 && fs == 10); // tap 3 at 2:3 (1080p -> 720p): one staging per tile instead of one per pass of the periodic path
 }
 
 struct CellsAxis {
