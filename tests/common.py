@@ -87,8 +87,10 @@ SMALL_CASES = [
     ("up1p5_tap3_420p8", ah.YUV420P8, 320, 180, 480, 270, dict(tap=3)),
     ("up1p5_tap4_444p16_crop", ah.YUV444P16, 240, 136, 360, 204, dict(tap=4, src_left=1.25, src_top=0.75)),
     ("up1p5_tap3_f32_y", ah.Format("y", 32), 200, 120, 300, 180, dict(tap=3)),
-    # 2:3 downscale (1080p -> 720p class): exactly periodic (source step 1.5), four passes of the odd-ratio polyphase kernel
+    # 2:3 downscale (1080p -> 720p class): exactly periodic (source step 1.5): tap 3 on the chunked-cells kernel (one staging
+    # per tile), tap 4 as four passes of the odd-ratio polyphase kernel
     ("down2to3_tap3_420p8", ah.YUV420P8, 480, 270, 320, 180, dict(tap=3)),
+    ("down2to3_tap4_y16", ah.Format("y", 16), 300, 180, 200, 120, dict(tap=4)),
     ("down2to3_tap4_444p16_crop", ah.YUV444P16, 360, 204, 240, 136, dict(tap=4, src_left=1.5, src_top=0.75, src_width=357.0, src_height=202.5)),
     ("down2to3_tap3_f32_y", ah.Format("y", 32), 300, 180, 200, 120, dict(tap=3)),
     ("down2to3_tap3_422p10_mpeg1", ah.Format("422", 10), 384, 216, 256, 144, dict(tap=3, cplace="mpeg1")),

@@ -125,12 +125,12 @@ def test_submit_wait_pipeline_keeps_frames_apart(capi):
 
 EXPECTED_PATHS = {
     "c1_yv12_2x_tap3": 1, "c4_rgbps_2x_tap8": 1, "c5_420p10_quarter_tap6_blur": 2, "half_tap3_yv12": 2,
-    "down2to3_tap3_420p8": 3, "down2to3_tap3_f32_y": 3,
+    "down2to3_tap4_y16": 3,
     # rational ratios with piecewise-periodic phases: the chunked-cells kernel (3:2, 4:3, 4x, and a pure shift at 1:1)
     "up1p5_tap3_420p8": 4, "up1p5_tap4_444p16_crop": 4, "up1p5_tap3_f32_y": 4, "up4to3_tap3_420p8": 4, "up4to3_tap4_y16": 4,
     "up4x_tap3_420p8": 4, "up4x_tap4_rgbp16": 4, "same_size_shift": 4, "y8_tap2_1p5x": 4,
     "up5to4_tap3_420p8": 4, "up9to4_tap4_y16": 4, "down3to4_tap3_444p10": 4, "up3x_tap3_f32_y": 4, "up5to3_tap4_rgbp8": 4,
-    "up1p5_tap5_422p12": 4, "yv411_tap5": 4,
+    "up1p5_tap5_422p12": 4, "yv411_tap5": 4, "down2to3_tap3_420p8": 4, "down2to3_tap3_f32_y": 4,
     # no structure (or a window size the fast kernels are not instantiated for): the general kernel
     "irregular_up_crop_mpeg1": 0, "irregular_down_quant": 0, "f32_444_3x_tap16": 0, "down2to3_tap4_444p16_crop": 0,
 }

@@ -136,7 +136,8 @@ def test_device_batch_on_alternating_streams(capi):
 
 BAND_CASES = ["c2_420p8_2x_tap3_mpeg2", "c3_444p16_2x_tap4_crop", "c4_rgbps_2x_tap8", "c5_420p10_quarter_tap6_blur",
               "down2to3_tap3_420p8", "up4to3_tap3_420p8", "up4x_tap3_420p8", "up1p5_tap3_420p8", "irregular_up_crop_mpeg1",
-              "yuva420_14bit_2x", "third_tap3_y8", "steep_down_444p16_tap5", "down3to4_tap3_444p10", "up9to4_tap4_y16"]
+              "yuva420_14bit_2x", "third_tap3_y8", "steep_down_444p16_tap5", "down3to4_tap3_444p10", "up9to4_tap4_y16",
+              "down2to3_tap4_y16"]
 
 
 @pytest.mark.parametrize("n_bands", [2, 3, 7])
