@@ -17,12 +17,15 @@
 //       bank-conflict free.
 //       integer-ratio downscale and the passes of the periodic 2:3 / 4:3 paths (jinc_down.cuh): polyphase columns,
 //       vertical tap pairing, raw sample pairs in shared memory.
-//   strip patch (512 output samples of the border strips; strip_block below)
+//   strip patch (about 512 output samples of the border strips)
 //       One thread = 4 output samples that share a border row or column (hence, normally, one weight block): the
 //       patch's source footprint is staged in shared memory as floats, weights are read as float4 rows from the
 //       per-class border blocks or the padded phase blocks.  Border pixels that fold into no class fall back to
 //       resident per-pixel weights or to the reference's formula evaluated per tap (exact LUT index, divided by the
-//       stored per-pixel normaliser, :443-514).
+//       stored per-pixel normaliser, :443-514).  Whole-frame launches run the patches from the table's strip plan
+//       (strip_block_planned: descriptors, thread records and packed weight blocks worked out once per table, the
+//       weight blocks staged next to the footprint); row-band launches and tables without a plan derive the same
+//       work per block (strip_block).  Both accumulate every sample in the same tap order.
 //
 // General ratios (no fast path) run resample_strips in jinc_resize.cu: the same patch scheme over the whole plane, one
 // block covering the patch in every plane of the table.
