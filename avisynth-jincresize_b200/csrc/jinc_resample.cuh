@@ -943,51 +943,22 @@ __device__ __forceinline__ void plan_run_cols(const float* __restrict__ s, int f
 #pragma unroll
     for (int k = 0; k < SPT; ++k)
         acc[k] = 0.f;
-    if constexpr (FSC <= 9) {
+    static_assert(FSC <= 9, "wide windows do not run down a column: one weight row for four source rows reads less (the planner agrees)");
 #pragma unroll
-        for (int r = 0; r < FSC + (SPT - 1) * STEP; ++r) {
-            float seg[FSC];
+    for (int r = 0; r < FSC + (SPT - 1) * STEP; ++r) {
+        float seg[FSC];
 #pragma unroll
-            for (int i = 0; i < FSC; ++i)
-                seg[i] = s[r * fw + i];
+        for (int i = 0; i < FSC; ++i)
+            seg[i] = s[r * fw + i];
 #pragma unroll
-            for (int k = 0; k < SPT; ++k) {
-                const int ly = r - k * STEP; // weight row of output k (a constant after unrolling)
-                if (ly >= 0 && ly < FSC) {
-                    float wr[FSP];
-                    plan_weight_row<WS, FSP>(w + ly * FSP, wr);
+        for (int k = 0; k < SPT; ++k) {
+            const int ly = r - k * STEP; // weight row of output k (a constant after unrolling)
+            if (ly >= 0 && ly < FSC) {
+                float wr[FSP];
+                plan_weight_row<WS, FSP>(w + ly * FSP, wr);
 #pragma unroll
-                    for (int lx = 0; lx < FSC; ++lx)
-                        acc[k] = fmaf(seg[lx], wr[lx], acc[k]);
-                }
-            }
-        }
-    } else {
-        // wide windows: the row loop stays rolled, which outputs a source row feeds is tested at run time (the same for
-        // every thread)
-#pragma unroll 1
-        for (int r = 0; r < FSC + (SPT - 1) * STEP; ++r) {
-            float seg[FSC];
-#pragma unroll
-            for (int i = 0; i < FSC; ++i)
-                seg[i] = s[r * fw + i];
-#pragma unroll
-            for (int k = 0; k < SPT; ++k) {
-                const int ly = r - k * STEP;
-                if (ly >= 0 && ly < FSC) {
-                    const float* __restrict__ wrow = w + ly * FSP;
-#pragma unroll
-                    for (int q = 0; q < FSP / 4; ++q) {
-                        const float4 t = plan_w4<WS>(wrow + 4 * q);
-                        acc[k] = fmaf(seg[4 * q], t.x, acc[k]);
-                        if (4 * q + 1 < FSC)
-                            acc[k] = fmaf(seg[4 * q + 1], t.y, acc[k]);
-                        if (4 * q + 2 < FSC)
-                            acc[k] = fmaf(seg[4 * q + 2], t.z, acc[k]);
-                        if (4 * q + 3 < FSC)
-                            acc[k] = fmaf(seg[4 * q + 3], t.w, acc[k]);
-                    }
-                }
+                for (int lx = 0; lx < FSC; ++lx)
+                    acc[k] = fmaf(seg[lx], wr[lx], acc[k]);
             }
         }
     }
@@ -1142,10 +1113,12 @@ __device__ __forceinline__ void plan_accumulate(const StripArgs& a, const FrameS
             plan_run_rows<T, FSC, SPT, STEP, WS, false>(tile + (int)r0.y, rs, w0, o, a.plan_px, fsx.peak);
         return;
     }
-    if (kind == JINC_SK_RUN_COLS) {
-        plan_run_cols<T, FSC, SPT, STEP, WS>(tile + (int)r0.y, rs, w0, dst + (long long)(r0.x >> 16) * dp + (r0.x & 0xffffu),
-                                             (long long)a.plan_py * dp, fsx.peak);
-        return;
+    if constexpr (FSC <= 9) {
+        if (kind == JINC_SK_RUN_COLS) {
+            plan_run_cols<T, FSC, SPT, STEP, WS>(tile + (int)r0.y, rs, w0, dst + (long long)(r0.x >> 16) * dp + (r0.x & 0xffffu),
+                                                 (long long)a.plan_py * dp, fsx.peak);
+            return;
+        }
     }
     uint4 r[SPT];
     r[0] = r0;
