@@ -145,8 +145,9 @@ struct StripPlanPatch {
     int32_t row_stride;           // floats per staged footprint row (fw, or step * sub when de-interleaved)
     int32_t sub;                  // de-interleaved rows: column c sits at (c % step) * sub + c / step
     int32_t deint;                // 1: the footprint is staged de-interleaved by the window step (patches of row runs only)
-    int32_t pad_;
+    int32_t ring;                 // > 0: float offset of the weight-row rings in the block's shared memory (plan_run_rows_ring), else 0
 };
+constexpr int JINC_PLAN_RING_DEPTH = 8; // weight rows in flight per half-warp (wide windows read from the table's blocks)
 enum { JINC_SK_NONE = 0, JINC_SK_RUN_ROWS, JINC_SK_RUN_COLS, JINC_SK_FUSED_SHARED, JINC_SK_FUSED_SEP, JINC_SK_PER_SAMPLE, JINC_SK_PER_PIXEL };
 struct StripPlan {
     bool ok = false;

@@ -932,6 +932,66 @@ __device__ __forceinline__ void plan_run_rows(const float* __restrict__ s, int r
         o[k * xstep] = finish<T>(acc[k], peak);
 }
 
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// plan_run_rows for wide windows whose weight block stays in the table (global memory): the sixteen threads of a half-warp
+// share the block (the plan guarantees it), so its rows are streamed through a ring of JINC_PLAN_RING_DEPTH rows in shared
+// memory with cp.async, DEPTH - 1 rows in flight -- the L2 round trip of a weight row is hidden behind several rows of
+// FMAs instead of one -- and read back as broadcast LDS.128.  Same taps in the same order as plan_run_rows.
+template <typename T, int FSC, int SPT, int STEP, bool DEINT>
+__device__ __forceinline__ void plan_run_rows_ring(const float* __restrict__ s, int rs, const float* __restrict__ w, float* __restrict__ ring,
+                                                   T* __restrict__ o, int xstep, float peak)
+{
+    constexpr int FSP = (FSC + 3) & ~3, NV = FSP / 4, SEG = FSC + (SPT - 1) * STEP, D = SPT * STEP, SUBC = plan_deint_sub(STEP, SPT, FSC);
+    constexpr int DEPTH = JINC_PLAN_RING_DEPTH;
+    static_assert(NV <= 16 && (DEPTH & (DEPTH - 1)) == 0, "one 16-byte copy per thread of the half-warp and row");
+    const int j = threadIdx.x & 15;
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
+    float acc[SPT];
+#pragma unroll
+    for (int k = 0; k < SPT; ++k)
+        acc[k] = 0.f;
+#pragma unroll
+    for (int d = 0; d < DEPTH - 1; ++d) {
+        if (d < FSC && j < NV)
+            cp_async16(ring_s + (uint32_t)((d * FSP + 4 * j) * (int)sizeof(float)), w + d * FSP + 4 * j);
+        cp_async_commit();
+    }
+#pragma unroll 1
+    for (int ly = 0; ly < FSC; ++ly) {
+        const int ahead = ly + DEPTH - 1;
+        if (ahead < FSC && j < NV)
+            cp_async16(ring_s + (uint32_t)((((ahead & (DEPTH - 1)) * FSP) + 4 * j) * (int)sizeof(float)), w + ahead * FSP + 4 * j);
+        cp_async_commit();
+        cp_async_wait<DEPTH - 1>(); // row ly has landed (this thread's part; the warp barrier publishes the others')
+        __syncwarp();
+        float seg[SEG], wr[FSP];
+        plan_weight_row<true, FSP>(ring + (ly & (DEPTH - 1)) * FSP, wr);
+        const float* __restrict__ srow = s + ly * (DEINT ? D * SUBC : rs);
+#pragma unroll
+        for (int i = 0; i < SEG; ++i)
+            seg[i] = DEINT ? srow[(i % D) * SUBC + i / D] : srow[i];
+#pragma unroll
+        for (int lx = 0; lx < FSC; ++lx)
+#pragma unroll
+            for (int k = 0; k < SPT; ++k)
+                acc[k] = fmaf(seg[lx + k * STEP], wr[lx], acc[k]);
+        __syncwarp(); // the slot of row ly is overwritten by the next iteration's copy
+    }
+#pragma unroll
+    for (int k = 0; k < SPT; ++k)
+        o[k * xstep] = finish<T>(acc[k], peak);
+}
+
 // the same down one column (window origins STEP rows apart): a staged row of FSC values feeds up to SPT outputs, each
 // with its own weight row
 template <typename T, int FSC, int SPT, int STEP, bool WS>
@@ -1098,7 +1158,8 @@ __device__ __noinline__ void strip_block_unplanned(const StripArgs& a, const Fra
 
 template <typename T, int FSC, int THREADS, int SPT, int STEP, bool WS>
 __device__ __forceinline__ void plan_accumulate(const StripArgs& a, const FrameSet& fsx, unsigned plane, const uint4& r0, const uint4* __restrict__ recs,
-                                                const float* __restrict__ tile, int rs, bool deint, const float* __restrict__ wbase)
+                                                const float* __restrict__ tile, int rs, bool deint, const float* __restrict__ wbase,
+                                                float* __restrict__ ring)
 {
     const unsigned kind = r0.w & 0xffu, live = r0.w >> 8;
     const PlanePtrs& pp = frame_ptrs(fsx);
@@ -1107,6 +1168,16 @@ __device__ __forceinline__ void plan_accumulate(const StripArgs& a, const FrameS
     const float* __restrict__ w0 = WS ? wbase + r0.z : plan_block<FSC>(a, r0.z); // sample 0's weight block
     if (kind == JINC_SK_RUN_ROWS) {
         T* __restrict__ o = dst + (long long)(r0.x >> 16) * dp + (r0.x & 0xffffu);
+        if constexpr (FSC > 9 && !WS) {
+            if (ring) { // the whole patch is half-warps of row runs sharing a block: weight rows through the ring
+                float* __restrict__ mine = ring + (threadIdx.x >> 4) * (JINC_PLAN_RING_DEPTH * ((FSC + 3) & ~3));
+                if (STEP > 1 && deint)
+                    plan_run_rows_ring<T, FSC, SPT, STEP, (STEP > 1)>(tile + (int)r0.y, rs, w0, mine, o, a.plan_px, fsx.peak);
+                else
+                    plan_run_rows_ring<T, FSC, SPT, STEP, false>(tile + (int)r0.y, rs, w0, mine, o, a.plan_px, fsx.peak);
+                return;
+            }
+        }
         if (STEP > 1 && deint)
             plan_run_rows<T, FSC, SPT, STEP, WS, (STEP > 1)>(tile + (int)r0.y, rs, w0, o, a.plan_px, fsx.peak);
         else
@@ -1150,7 +1221,7 @@ __device__ __forceinline__ void strip_block_planned(const StripArgs& a, const Fr
     const int4* __restrict__ pd = reinterpret_cast<const int4*>(a.plan_patches + pid);
     const int4 pa = __ldg(pd);     // sx_lo, sy_lo, fw, fh
     const int4 pb = __ldg(pd + 1); // magic, n_wb, wdata_off, tile_floats
-    const int4 pc = __ldg(pd + 2); // row_stride, sub, deint
+    const int4 pc = __ldg(pd + 2); // row_stride, sub, deint, ring
     const uint4* __restrict__ recs = a.plan_threads + (size_t)pid * (unsigned)(SPT * THREADS) + threadIdx.x;
     const uint4 r0 = __ldg(recs);
     const PlanePtrs& pp = frame_ptrs(fsx);
@@ -1173,18 +1244,20 @@ __device__ __forceinline__ void strip_block_planned(const StripArgs& a, const Fr
 #pragma unroll
         for (int u = 0; u < 2; ++u)
             wv[u] = __ldg(wsrc + min((int)threadIdx.x + u * THREADS, max(nw4 - 1, 0)));
-        for (unsigned e0 = threadIdx.x; e0 < n; e0 += 4 * THREADS) {
-            T v[4];
-            unsigned at[4];
+        // wide windows have footprints of thousands of samples: sixteen loads per thread in flight instead of four
+        constexpr int U = FSC > 9 ? 16 : 4;
+        for (unsigned e0 = threadIdx.x; e0 < n; e0 += U * THREADS) {
+            T v[U];
+            unsigned at[U];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) { // all four loads are issued before the first conversion
+            for (int u = 0; u < U; ++u) { // all loads of a round are issued before the first conversion
                 const unsigned e = min(e0 + u * THREADS, n - 1);
                 const unsigned row = __umulhi(e, magic), col = e - row * (unsigned)fw;
                 v[u] = __ldg(src + (int)(row * (unsigned)pitch + col));
                 at[u] = deint ? row * (unsigned)(D * SUBC) + (col % (unsigned)D) * (unsigned)SUBC + col / (unsigned)D : e;
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
+            for (int u = 0; u < U; ++u)
                 if (e0 + u * THREADS < n)
                     tile[at[u]] = sample_to_float(v[u]);
         }
@@ -1199,9 +1272,9 @@ __device__ __forceinline__ void strip_block_planned(const StripArgs& a, const Fr
     if ((r0.w & 0xffu) == JINC_SK_NONE)
         return;
     if (ws)
-        plan_accumulate<T, FSC, THREADS, SPT, STEP, true>(a, fsx, plane, r0, recs, tile, rs, deint, wsm);
+        plan_accumulate<T, FSC, THREADS, SPT, STEP, true>(a, fsx, plane, r0, recs, tile, rs, deint, wsm, nullptr);
     else
-        plan_accumulate<T, FSC, THREADS, SPT, STEP, false>(a, fsx, plane, r0, recs, tile, rs, deint, nullptr);
+        plan_accumulate<T, FSC, THREADS, SPT, STEP, false>(a, fsx, plane, r0, recs, tile, rs, deint, nullptr, pc.w > 0 ? tile + pc.w : nullptr);
 }
 
 // Role of block b in a merged grid of interior tile blocks and `strips` strip blocks: strip block k sits at grid

@@ -715,6 +715,7 @@ inline void build_strip_plan_host(const jinc_table* t, const Rect* rects, int n_
                 pd.row_stride = fw;
                 pd.sub = 0;
                 pd.deint = 0;
+                pd.ring = 0;
                 const size_t rec0 = out.recs.size();
                 out.recs.resize(rec0 + (size_t)SPT * THREADS, make_uint4(0, 0, 0, 0));
                 uint4* prec = out.recs.data() + rec0;
@@ -814,6 +815,18 @@ inline void build_strip_plan_host(const jinc_table* t, const Rect* rects, int n_
                             if ((prec[tid].w & 0xffu) != JINC_SK_PER_SAMPLE && (prec[tid].w & 0xffu) != JINC_SK_PER_PIXEL)
                                 rk.z = keys[rk.z / (uint32_t)wbf];
                         }
+                }
+                // Wide windows whose blocks stay in the table: when every half-warp of the patch is sixteen row runs with one
+                // weight block (a 64-wide patch row), the block's rows are streamed through a shared-memory ring, several
+                // rows in flight (plan_run_rows_ring), instead of being loaded a row ahead into registers.
+                if (!staged && fs > 9 && items.size() % 16 == 0 && !items.empty()) {
+                    bool uniform = true;
+                    for (size_t h0 = 0; h0 < items.size() && uniform; h0 += 16)
+                        for (size_t tid = h0; tid < h0 + 16 && uniform; ++tid)
+                            uniform = (prec[tid].w & 0xffu) == JINC_SK_RUN_ROWS && prec[tid].z == prec[h0].z;
+                    const unsigned long long ring_floats = (unsigned long long)(THREADS / 16) * JINC_PLAN_RING_DEPTH * fsp;
+                    if (uniform && pd.tile_floats + ring_floats <= pp.smem_floats)
+                        pd.ring = (int32_t)pd.tile_floats;
                 }
                 out.n_staged += staged ? 1u : 0u;
                 out.patches.push_back(pd);
