@@ -9,7 +9,7 @@ for c in 6 7 8 9; do timeout 600 python bench.py --config $c --steps 10 --warmup
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 2>/dev/null | tail -1 > gpurun_out/${TAG}_bench_reference_config2.json
 B="--no-cpu --no-all-configs --plugin-threads 0 --bands 0"
 # A/B lines (kernel-only): strips from the plan vs derived per block, float tiles through registers vs the bulk-copy engine
-for c in 1 2 3 4 5 9; do for plan in 1 0; do JINCRESIZE_B200_STRIP_PLAN=$plan timeout 300 python bench.py --config $c --steps 20 --warmup 3 $B 2>/dev/null | tail -1 > gpurun_out/${TAG}_ab_config${c}_plan$plan.json; done; done
+for c in 1 2 3 4 5 6 9; do for plan in 1 0; do JINCRESIZE_B200_STRIP_PLAN=$plan timeout 300 python bench.py --config $c --steps 20 --warmup 3 $B 2>/dev/null | tail -1 > gpurun_out/${TAG}_ab_config${c}_plan$plan.json; done; done
 for tma in 0 1; do JINCRESIZE_B200_TMA=$tma timeout 300 python bench.py --config 4 --steps 20 --warmup 3 $B 2>/dev/null | tail -1 > gpurun_out/${TAG}_ab_config4_bulkcopy$tma.json; done
 ./avisynth-jincresize_b200/fma_peak > gpurun_out/${TAG}_fma_peak.jsonl
 for f in gpurun_out/${TAG}_ab_*.json gpurun_out/${TAG}_bench_config[6-9].json; do python -c "
