@@ -144,14 +144,24 @@ __global__ void __launch_bounds__((CellsGeom<FS, Q>::THREADS), (CellsGeom<FS, Q>
             if (i >= ix0 && i < ix0 + ncx && j >= iy0 && j < iy0 + ncy && cell_y + j >= a.cell_y_begin && cell_y + j < a.cell_y_end)
                 live |= 1u << (j * G::NX + i);
 
+    // px outside, py inside: the shared-memory column offsets of a pass depend on px only and are worked out once per px
 #pragma unroll 1
-    for (int py = 0; py < Py; ++py) {
-        const int oy = __ldg(a.cy_org + cyk * Py + py) - lo_y;
-        const int ry = __ldg(a.cy_rank + cyk * Py + py);
+    for (int px = 0; px < Px; ++px) {
+        const int ox = __ldg(a.cx_org + cxk * Px + px) - lo_x;
+        const int rx = __ldg(a.cx_rank + cxk * Px + px);
+        // shared-memory word of column ox + k within a footprint row
+        int addr[G::SPAN];
+        {
+            const int m0 = ox % G::D, q0 = ox / G::D;
+#pragma unroll
+            for (int k = 0; k < G::SPAN; ++k)
+                addr[k] = q0 + ((m0 + k) % G::D) * G::SUB + (m0 + k) / G::D;
+        }
 #pragma unroll 1
-        for (int px = 0; px < Px; ++px) {
-            const int ox = __ldg(a.cx_org + cxk * Px + px) - lo_x;
-            const int rx = __ldg(a.cx_rank + cxk * Px + px);
+        for (int py = 0; py < Py; ++py) {
+            const int oy = __ldg(a.cy_org + cyk * Py + py) - lo_y;
+            const int ry = __ldg(a.cy_rank + cyk * Py + py);
+            const float* __restrict__ trow = tile + oy * G::ROW; // the pass's first footprint row
 
             // the pair's weight block, in registers for the whole pass
             float w[FS][FS];
@@ -179,16 +189,6 @@ __global__ void __launch_bounds__((CellsGeom<FS, Q>::THREADS), (CellsGeom<FS, Q>
                 }
             }
 
-            // shared-memory word of column ox + k in the pass's first row
-            int addr[G::SPAN];
-            {
-                const int m0 = ox % G::D, q0 = ox / G::D;
-                const int base = oy * G::ROW + q0;
-#pragma unroll
-                for (int k = 0; k < G::SPAN; ++k)
-                    addr[k] = base + ((m0 + k) % G::D) * G::SUB + (m0 + k) / G::D;
-            }
-
             float acc[G::NY][G::NX];
 #pragma unroll
             for (int j = 0; j < G::NY; ++j)
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__((CellsGeom<FS, Q>::THREADS), (CellsGeom<FS, Q>
                 float s[G::SPAN];
 #pragma unroll
                 for (int k = 0; k < G::SPAN; ++k)
-                    s[k] = tile[addr[k] + r * G::ROW];
+                    s[k] = trow[addr[k] + r * G::ROW];
 #pragma unroll
                 for (int j = 0; j < G::NY; ++j) {
                     const int ly = r - Q * j; // weight row of output row j (a constant after unrolling)
