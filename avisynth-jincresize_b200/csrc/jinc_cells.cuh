@@ -144,86 +144,95 @@ __global__ void __launch_bounds__((CellsGeom<FS, Q>::THREADS), (CellsGeom<FS, Q>
             if (i >= ix0 && i < ix0 + ncx && j >= iy0 && j < iy0 + ncy && cell_y + j >= a.cell_y_begin && cell_y + j < a.cell_y_end)
                 live |= 1u << (j * G::NX + i);
 
-    // px outside, py inside: the shared-memory column offsets of a pass depend on px only and are worked out once per px
-#pragma unroll 1
-    for (int px = 0; px < Px; ++px) {
+    // The passes run px-major (px outside, py inside: the shared-memory column offsets of a pass depend on px only) as one
+    // flat, software-pipelined loop: the weight block of the NEXT pass is loaded into the weight registers as soon as this
+    // pass's FMAs are done -- they are dead by then -- and before its samples are converted and stored, so the loads' round
+    // trip overlaps the store phase instead of opening the next pass.
+    float w[FS][FS]; // the pair's weight block, in registers for the whole pass
+    int addr[G::SPAN]; // shared-memory word of column ox + k within a footprint row
+    int rx = 0, oy = 0;
+    auto load_px = [&](int px) {
         const int ox = __ldg(a.cx_org + cxk * Px + px) - lo_x;
-        const int rx = __ldg(a.cx_rank + cxk * Px + px);
-        // shared-memory word of column ox + k within a footprint row
-        int addr[G::SPAN];
-        {
-            const int m0 = ox % G::D, q0 = ox / G::D;
+        rx = __ldg(a.cx_rank + cxk * Px + px);
+        const int m0 = ox % G::D, q0 = ox / G::D;
+#pragma unroll
+        for (int k = 0; k < G::SPAN; ++k)
+            addr[k] = q0 + ((m0 + k) % G::D) * G::SUB + (m0 + k) / G::D;
+    };
+    auto load_py = [&](int py) {
+        oy = __ldg(a.cy_org + cyk * Py + py) - lo_y;
+        const int ry = __ldg(a.cy_rank + cyk * Py + py);
+        const float* __restrict__ wb = a.wblocks + (size_t)(ry * a.n_rank_x + rx) * (unsigned)(FS * a.wstride);
+        if (a.wstride == G::FSP) {
+#pragma unroll
+            for (int ly = 0; ly < FS; ++ly) {
+#pragma unroll
+                for (int q4 = 0; q4 < G::FSP / 4; ++q4) {
+                    const float4 t = __ldg(reinterpret_cast<const float4*>(wb + ly * G::FSP) + q4);
+                    const float tv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (4 * q4 + e < FS)
+                            w[ly][4 * q4 + e] = tv[e];
+                }
+            }
+        } else {
+#pragma unroll
+            for (int ly = 0; ly < FS; ++ly)
+#pragma unroll
+                for (int lx = 0; lx < FS; ++lx)
+                    w[ly][lx] = __ldg(wb + ly * a.wstride + lx);
+        }
+    };
+    int px = 0, py = 0;
+    load_px(0);
+    load_py(0);
+#pragma unroll 1
+    for (int pass = Px * Py; pass > 0; --pass) {
+        const float* __restrict__ trow = tile + oy * G::ROW; // the pass's first footprint row
+        float acc[G::NY][G::NX];
+#pragma unroll
+        for (int j = 0; j < G::NY; ++j)
+#pragma unroll
+            for (int i = 0; i < G::NX; ++i)
+                acc[j][i] = 0.f;
+
+#pragma unroll
+        for (int r = 0; r < G::NROW; ++r) {
+            float s[G::SPAN];
 #pragma unroll
             for (int k = 0; k < G::SPAN; ++k)
-                addr[k] = q0 + ((m0 + k) % G::D) * G::SUB + (m0 + k) / G::D;
+                s[k] = trow[addr[k] + r * G::ROW];
+#pragma unroll
+            for (int j = 0; j < G::NY; ++j) {
+                const int ly = r - Q * j; // weight row of output row j (a constant after unrolling)
+                if (ly >= 0 && ly < FS) {
+#pragma unroll
+                    for (int lx = 0; lx < FS; ++lx)
+#pragma unroll
+                        for (int i = 0; i < G::NX; ++i)
+                            acc[j][i] = fmaf(s[Q * i + lx], w[ly][lx], acc[j][i]);
+                }
+            }
         }
-#pragma unroll 1
-        for (int py = 0; py < Py; ++py) {
-            const int oy = __ldg(a.cy_org + cyk * Py + py) - lo_y;
-            const int ry = __ldg(a.cy_rank + cyk * Py + py);
-            const float* __restrict__ trow = tile + oy * G::ROW; // the pass's first footprint row
 
-            // the pair's weight block, in registers for the whole pass
-            float w[FS][FS];
-            {
-                const float* __restrict__ wb = a.wblocks + (size_t)(ry * a.n_rank_x + rx) * (unsigned)(FS * a.wstride);
-                if (a.wstride == G::FSP) {
-#pragma unroll
-                    for (int ly = 0; ly < FS; ++ly) {
-#pragma unroll
-                        for (int q4 = 0; q4 < G::FSP / 4; ++q4) {
-                            const float4 t = __ldg(reinterpret_cast<const float4*>(wb + ly * G::FSP) + q4);
-                            const float tv[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-                            for (int e = 0; e < 4; ++e)
-                                if (4 * q4 + e < FS)
-                                    w[ly][4 * q4 + e] = tv[e];
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int ly = 0; ly < FS; ++ly)
-#pragma unroll
-                        for (int lx = 0; lx < FS; ++lx)
-                            w[ly][lx] = __ldg(wb + ly * a.wstride + lx);
-                }
-            }
-
-            float acc[G::NY][G::NX];
-#pragma unroll
-            for (int j = 0; j < G::NY; ++j)
-#pragma unroll
-                for (int i = 0; i < G::NX; ++i)
-                    acc[j][i] = 0.f;
-
-#pragma unroll
-            for (int r = 0; r < G::NROW; ++r) {
-                float s[G::SPAN];
-#pragma unroll
-                for (int k = 0; k < G::SPAN; ++k)
-                    s[k] = trow[addr[k] + r * G::ROW];
-#pragma unroll
-                for (int j = 0; j < G::NY; ++j) {
-                    const int ly = r - Q * j; // weight row of output row j (a constant after unrolling)
-                    if (ly >= 0 && ly < FS) {
-#pragma unroll
-                        for (int lx = 0; lx < FS; ++lx)
-#pragma unroll
-                            for (int i = 0; i < G::NX; ++i)
-                                acc[j][i] = fmaf(s[Q * i + lx], w[ly][lx], acc[j][i]);
-                    }
-                }
-            }
-
-            // ---- this residue pair's samples of the chunk: every Px-th column of every Py-th row.  One code path for
-            //      every lane (a warp holds whole and split groups side by side): a per-thread bit mask says which of
-            //      the 4 x 4 samples belong to the chunk, and the usual cell sizes get immediate store offsets.
-            T* __restrict__ o = obase + (long long)py * dp + px;
-            switch (Px) {
-            case 3: store_cells<T, G::NX, G::NY, 3>(o, rstep, Px, live, acc, a.fr.peak); break;
-            case 4: store_cells<T, G::NX, G::NY, 4>(o, rstep, Px, live, acc, a.fr.peak); break;
-            default: store_cells<T, G::NX, G::NY, 0>(o, rstep, Px, live, acc, a.fr.peak); break;
-            }
+        // ---- this residue pair's samples of the chunk: every Px-th column of every Py-th row.  One code path for
+        //      every lane (a warp holds whole and split groups side by side): a per-thread bit mask says which of
+        //      the 4 x 4 samples belong to the chunk, and the usual cell sizes get immediate store offsets.
+        T* __restrict__ o = obase + (long long)py * dp + px;
+        // the next pass's offsets and weights, before the stores
+        if (++py == Py) {
+            py = 0;
+            ++px;
+            if (pass > 1)
+                load_px(px);
+        }
+        if (pass > 1)
+            load_py(py);
+        switch (Px) {
+        case 3: store_cells<T, G::NX, G::NY, 3>(o, rstep, Px, live, acc, a.fr.peak); break;
+        case 4: store_cells<T, G::NX, G::NY, 4>(o, rstep, Px, live, acc, a.fr.peak); break;
+        default: store_cells<T, G::NX, G::NY, 0>(o, rstep, Px, live, acc, a.fr.peak); break;
         }
     }
 }
