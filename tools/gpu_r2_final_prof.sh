@@ -14,4 +14,4 @@ for c in 2 3 4 5; do
   tail -3 gpurun_out/${TAG}_traffic_config$c.csv | cut -c1-200
 done
 timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 1 python -m pytest tests/test_gpu_parity.py tests/test_gpu_pipeline.py -m gpu -q -x -p no:cacheprovider -k "(frame_matches and noise) or (row_bands and 3) or device_batch or strip_plan or bulk_copy" > gpurun_out/${TAG}_sanitizer_memcheck.log 2>&1; tail -4 gpurun_out/${TAG}_sanitizer_memcheck.log
-timeout 900 compute-sanitizer --tool racecheck --error-exitcode 1 python -m pytest tests/test_gpu_parity.py tests/test_gpu_pipeline.py -m gpu -q -x -p no:cacheprovider -k "(frame_matches and noise and (c2_420 or c5_420 or up1p5_tap3_420p8 or down2to3_tap3_420p8 or irregular_up or up4to3_tap4)) or (strip_plan and (c2_420 or c4_rgbps or up4to3 or c5_420)) or bulk_copy" > gpurun_out/${TAG}_sanitizer_racecheck.log 2>&1; tail -4 gpurun_out/${TAG}_sanitizer_racecheck.log
+timeout 900 compute-sanitizer --tool racecheck --error-exitcode 1 python -m pytest tests/test_gpu_parity.py tests/test_gpu_pipeline.py -m gpu -q -x -p no:cacheprovider -k "(frame_matches and noise and (c2_420 or c5_420 or up1p5_tap3_420p8 or down2to3_tap3_420p8 or down2to3_tap4_y16 or irregular_up or up4to3_tap4)) or (strip_plan and (c2_420 or c4_rgbps or up4to3 or c5_420 or up1p5_tap3_420p8)) or bulk_copy" > gpurun_out/${TAG}_sanitizer_racecheck.log 2>&1; tail -4 gpurun_out/${TAG}_sanitizer_racecheck.log
